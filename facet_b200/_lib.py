@@ -1,0 +1,84 @@
+"""ctypes binding of libfacet_b200.so (the C ABI declared in include/facet_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails,
+or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfacet_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_u8p = C.c_void_p   # raw device/host addresses are passed as integers
+_P = C.c_void_p
+
+_SIGNATURES = {
+    "fb_abi_version": (C.c_int, []),
+    "fb_last_error": (C.c_char_p, []),
+    "fb_launch_count": (C.c_uint64, []),
+    "fb_device_sm_count": (C.c_int, []),
+    "fb_tech_stats": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "fb_tech_derive": (C.c_int, [_P, C.c_int, _P, _P]),
+    "fb_tech_stats_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fb_gray_hsv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "fb_roi_laplacian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "fb_clip_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                     _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int,
+                                     _P, _P, _P, _P, _P]),
+    "fb_hamming_pairs": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),
+    "fb_burst_links": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_double, _P, _P, C.c_int64, _P, _P]),
+}
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) and return the ctypes handle."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if build_if_missing:
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m facet_b200.build` (needs nvcc)")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.fb_abi_version() != 1:
+            raise RuntimeError("libfacet_b200.so ABI version mismatch; rebuild with `python -m facet_b200.build --force`")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().fb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().fb_launch_count())
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("facet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

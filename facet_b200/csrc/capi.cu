@@ -1,0 +1,160 @@
+// extern "C" surface of libfacet_b200.so — see include/facet_b200.h for the contract.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/facet_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+void count_launch(int k) { g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+        cached = sms;
+    }
+    return cached;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+const char* fb_last_error(void) { return get_error(); }
+uint64_t fb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int fb_device_sm_count(void) { return sm_count(); }
+
+int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+                  uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, int force_generic, void* stream) {
+    int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
+                               reinterpret_cast<long long*>(d_sums), force_generic, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_tech_derive(const uint32_t* d_hs_hist, int n, double* d_out, void* stream) {
+    int rc = launch_hs_derive(d_hs_hist, n, d_out, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_tech_stats_host(const uint8_t* h_images, int n, int height, int width, int rgb_order, uint32_t* h_hist256,
+                       int64_t* h_sums, double* h_derived, uint32_t* h_hs_hist) {
+    FB_REQUIRE(h_images && h_hist256 && h_sums && h_derived, "fb_tech_stats_host: null pointer");
+    FB_REQUIRE(n >= 1 && height >= 2 && width >= 2, "fb_tech_stats_host: need n>=1 and images of at least 2x2");
+    const size_t img_bytes = (size_t)height * width * 3;
+    const size_t stride = (img_bytes + 15) & ~(size_t)15;
+    uint8_t* d_img = nullptr;
+    uint32_t *d_h = nullptr, *d_hs = nullptr;
+    long long* d_s = nullptr;
+    double* d_d = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_img); cudaFree(d_h); cudaFree(d_hs); cudaFree(d_s); cudaFree(d_d);
+        if (st) cudaStreamDestroy(st);
+    };
+#define FB_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                            \
+            cleanup();                                                                            \
+            return (int)_e;                                                                       \
+        }                                                                                         \
+    } while (0)
+    FB_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    FB_TRY(cudaMalloc(&d_img, stride * n));
+    FB_TRY(cudaMalloc(&d_h, (size_t)n * 256 * 4));
+    FB_TRY(cudaMalloc(&d_hs, (size_t)n * FB_HS_BINS * 4));
+    FB_TRY(cudaMalloc(&d_s, (size_t)n * 4 * 8));
+    FB_TRY(cudaMalloc(&d_d, (size_t)n * 4 * 8));
+    if (stride == img_bytes) {
+        FB_TRY(cudaMemcpyAsync(d_img, h_images, img_bytes * n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = 0; i < n; ++i)
+            FB_TRY(cudaMemcpyAsync(d_img + stride * i, h_images + img_bytes * i, img_bytes, cudaMemcpyHostToDevice, st));
+    }
+    rc = fb_tech_stats(d_img, n, height, width, (int64_t)stride, rgb_order, d_h, d_hs, (int64_t*)d_s, 0, st);
+    if (rc == 0) rc = fb_tech_derive(d_hs, n, d_d, st);
+    if (rc != 0) {
+        cleanup();
+        return rc;
+    }
+    FB_TRY(cudaMemcpyAsync(h_hist256, d_h, (size_t)n * 256 * 4, cudaMemcpyDeviceToHost, st));
+    FB_TRY(cudaMemcpyAsync(h_sums, d_s, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost, st));
+    FB_TRY(cudaMemcpyAsync(h_derived, d_d, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost, st));
+    if (h_hs_hist) FB_TRY(cudaMemcpyAsync(h_hs_hist, d_hs, (size_t)n * FB_HS_BINS * 4, cudaMemcpyDeviceToHost, st));
+    FB_TRY(cudaStreamSynchronize(st));
+#undef FB_TRY
+    cleanup();
+    return 0;
+}
+
+int fb_gray_hsv(const uint8_t* d_image, int height, int width, int rgb_order, uint8_t* d_gray, uint8_t* d_hsv,
+                void* stream) {
+    int rc = launch_gray_hsv(d_image, height, width, rgb_order, d_gray, d_hsv, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_order, const int32_t* d_boxes, int k,
+                     int64_t* d_out, void* stream) {
+    int rc = launch_roi_laplacian(d_image, height, width, rgb_order, d_boxes, k, reinterpret_cast<long long*>(d_out),
+                                  (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+                       int out_size, const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, int h_byte_lo,
+                       int h_byte_hi, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk, int row0, int rows,
+                       const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out, void* stream) {
+    int rc = launch_clip_preprocess(d_images, n, height, width, (long long)image_stride, rgb_order, out_size, d_hbounds,
+                                    d_hcoef, hk, h_byte_lo, h_byte_hi, d_vbounds, d_vcoef, vk, row0, rows, mean3, std3,
+                                    d_tmp, d_out, (cudaStream_t)stream);
+    if (rc == 0) count_launch(2);
+    return rc;
+}
+
+int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts, int32_t* d_pairs,
+                     int64_t cap, uint64_t* d_count, void* stream) {
+    int rc = launch_hamming_pairs(reinterpret_cast<const unsigned long long*>(d_hashes), (long long)n, max_distance,
+                                  part, nparts, d_pairs, (long long)cap,
+                                  reinterpret_cast<unsigned long long*>(d_count), (cudaStream_t)stream);
+    if (rc == 0 && n >= 2) count_launch(1);
+    return rc;
+}
+
+int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint8_t* d_flags, const int32_t* d_lo,
+                   int64_t n, int thr, int64_t window_s, double rapid_s, int32_t* d_last_slow,
+                   int32_t* d_rapid_pairs, int64_t rapid_cap, uint64_t* d_rapid_count, void* stream) {
+    int rc = launch_burst_links(reinterpret_cast<const unsigned long long*>(d_hashes),
+                                reinterpret_cast<const long long*>(d_time_s), d_flags, d_lo, (long long)n, thr,
+                                (long long)window_s, rapid_s, d_last_slow, d_rapid_pairs, (long long)rapid_cap,
+                                reinterpret_cast<unsigned long long*>(d_rapid_count), (cudaStream_t)stream);
+    if (rc == 0 && n >= 1) count_launch(1);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+"""Thin host wrappers over the C ABI: torch tensors in, torch tensors out.
+
+torch is used for device memory and streams only; every kernel is in libfacet_b200.so.
+All functions run on the current CUDA stream of the current device and raise RuntimeError on
+failure.  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from .analyzers._closed_form import TechStats
+
+HS_BINS = 180 * 256
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def to_device_u8(images, device=None):
+    """numpy [H,W,3] / [n,H,W,3] uint8 or a CUDA tensor -> contiguous CUDA uint8 [n,H,W,3]."""
+    torch = _lib.require_cuda()
+    if isinstance(images, np.ndarray):
+        arr = np.ascontiguousarray(images)
+        if arr.dtype != np.uint8:
+            raise TypeError("images must be uint8")
+        t = torch.from_numpy(arr).to(device or "cuda", non_blocking=False)
+    elif isinstance(images, torch.Tensor):
+        if images.dtype != torch.uint8:
+            raise TypeError("images must be uint8")
+        t = images if images.is_cuda else images.to(device or "cuda")
+        t = t.contiguous()
+    else:
+        raise TypeError(f"unsupported image container {type(images)!r}")
+    if t.dim() == 3:
+        t = t.unsqueeze(0)
+    if t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError(f"expected [n,H,W,3] uint8, got {tuple(t.shape)}")
+    return t
+
+
+def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False):
+    """Run the technical pass.  Returns CUDA tensors (hist256 u32->int32 view [n,256],
+    hs_hist int32 [n,180,256], sums int64 [n,4], derived float64 [n,4])."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    if h < 2 or w < 2:
+        raise ValueError("images must be at least 2x2 (reflect-101 borders)")
+    dev = t.device
+    with torch.cuda.device(dev):
+        hist = torch.empty((n, 256), dtype=torch.int32, device=dev)
+        hs = torch.empty((n, 180, 256), dtype=torch.int32, device=dev)
+        sums = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        derived = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        st = _lib.stream_ptr()
+        _lib.check(lib.fb_tech_stats(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
+                                     _ptr(sums), int(bool(force_generic)), st), "fb_tech_stats")
+        _lib.check(lib.fb_tech_derive(_ptr(hs), n, _ptr(derived), st), "fb_tech_derive")
+    return hist, hs, sums, derived
+
+
+def tech_stats(images, rgb_order: bool = False, want_hs: bool = False, force_generic: bool = False) -> list[TechStats]:
+    """Technical pass + copy of the small per-image results to the host."""
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    hist, hs, sums, derived = tech_stats_raw(t, rgb_order, force_generic)
+    hist_h = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+    sums_h = sums.cpu().numpy()
+    der_h = derived.cpu().numpy()
+    hs_h = hs.cpu().numpy().view(np.uint32) if want_hs else None
+    out = []
+    for i in range(n):
+        out.append(TechStats(height=h, width=w, hist256=hist_h[i], sum_lap=int(sums_h[i, 0]),
+                             sum_lap_sq=int(sums_h[i, 1]), sum_abs_noise=int(sums_h[i, 2]),
+                             hs_entropy=float(der_h[i, 0]), sum_saturation=float(der_h[i, 1]),
+                             hs_hist=hs_h[i] if want_hs else None))
+    return out
+
+
+def tech_stats_host(images: np.ndarray, rgb_order: bool = False, want_hs: bool = False) -> list[TechStats]:
+    """Same pass through fb_tech_stats_host: host numpy in, host numpy out, copies inside the call.
+    This is the entry point a non-torch caller (the reference's analyzers) binds."""
+    lib = _lib.load()
+    arr = np.ascontiguousarray(images)
+    if arr.ndim == 3:
+        arr = arr[None]
+    n, h, w, _ = arr.shape
+    hist = np.empty((n, 256), np.uint32)
+    sums = np.empty((n, 4), np.int64)
+    der = np.empty((n, 4), np.float64)
+    hs = np.empty((n, 180, 256), np.uint32) if want_hs else None
+    _lib.check(lib.fb_tech_stats_host(arr.ctypes.data, n, h, w, int(bool(rgb_order)), hist.ctypes.data,
+                                      sums.ctypes.data, der.ctypes.data, hs.ctypes.data if want_hs else None),
+               "fb_tech_stats_host")
+    return [TechStats(height=h, width=w, hist256=hist[i].astype(np.int64), sum_lap=int(sums[i, 0]),
+                      sum_lap_sq=int(sums[i, 1]), sum_abs_noise=int(sums[i, 2]), hs_entropy=float(der[i, 0]),
+                      sum_saturation=float(der[i, 1]), hs_hist=hs[i] if want_hs else None) for i in range(n)]
+
+
+def gray_hsv_planes(image, rgb_order: bool = False):
+    """(gray uint8 [H,W], hsv uint8 [H,W,3]) numpy arrays of one image (image_cache.py:30-31)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(image)
+    if t.shape[0] != 1:
+        raise ValueError("gray_hsv_planes takes a single image")
+    _, h, w, _ = t.shape
+    gray = torch.empty((h, w), dtype=torch.uint8, device=t.device)
+    hsv = torch.empty((h, w, 3), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.fb_gray_hsv(_ptr(t), h, w, int(bool(rgb_order)), _ptr(gray), _ptr(hsv), _lib.stream_ptr()),
+                   "fb_gray_hsv")
+    return gray.cpu().numpy(), hsv.cpu().numpy()
+
+
+def roi_laplacian(image, boxes: Sequence[Sequence[int]], rgb_order: bool = False) -> np.ndarray:
+    """[k,3] int64 (pixel count, sum L, sum L^2) for crops x1,y1,x2,y2 of one image."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(image)
+    if t.shape[0] != 1:
+        raise ValueError("roi_laplacian takes a single image")
+    _, h, w, _ = t.shape
+    b = torch.as_tensor(np.asarray(boxes, dtype=np.int32).reshape(-1, 4), device=t.device)
+    out = torch.empty((b.shape[0], 3), dtype=torch.int64, device=t.device)
+    if b.shape[0] == 0:
+        return out.cpu().numpy()
+    with torch.cuda.device(t.device):
+        _lib.check(lib.fb_roi_laplacian(_ptr(t), h, w, int(bool(rgb_order)), _ptr(b), b.shape[0], _ptr(out),
+                                        _lib.stream_ptr()), "fb_roi_laplacian")
+    return out.cpu().numpy()
+
+
+def hamming_pairs(hashes, max_distance: int, part: int = 0, nparts: int = 1, cap: int | None = None):
+    """All (i<j) pairs of this part with popcount(h_i ^ h_j) <= max_distance, as a CUDA int32 [m,2]."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if isinstance(hashes, np.ndarray):
+        h = torch.from_numpy(np.ascontiguousarray(hashes.astype(np.uint64)).view(np.int64)).cuda()
+    else:
+        h = hashes.contiguous()
+        if h.dtype not in (torch.int64, torch.uint64):
+            raise TypeError("hashes must be 64-bit integers")
+    n = h.numel()
+    cap = int(cap if cap is not None else max(1 << 16, 4 * n))
+    with torch.cuda.device(h.device):
+        count = torch.zeros(1, dtype=torch.int64, device=h.device)
+        while True:
+            pairs = torch.empty((cap, 2), dtype=torch.int32, device=h.device)
+            _lib.check(lib.fb_hamming_pairs(_ptr(h), n, int(max_distance), int(part), int(nparts), _ptr(pairs), cap,
+                                            _ptr(count), _lib.stream_ptr()), "fb_hamming_pairs")
+            m = int(count.item())
+            if m <= cap:
+                return pairs[:m]
+            cap = m   # truncated: retry once with the exact size
+
+
+def burst_links(hashes: np.ndarray, time_s: np.ndarray, flags: np.ndarray, lo: np.ndarray, thr: int,
+                window_s: int, rapid_s: float):
+    """(last_slow int32[n], rapid_pairs int32[m,2]) — see fb_burst_links."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    n = int(len(hashes))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    h = torch.from_numpy(np.ascontiguousarray(hashes.astype(np.uint64)).view(np.int64)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(time_s.astype(np.int64))).to(dev)
+    f = torch.from_numpy(np.ascontiguousarray(flags.astype(np.uint8))).to(dev)
+    l = torch.from_numpy(np.ascontiguousarray(lo.astype(np.int32))).to(dev)
+    last = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    cap = max(1 << 14, 4 * n)
+    while True:
+        rp = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        _lib.check(lib.fb_burst_links(_ptr(h), _ptr(t), _ptr(f), _ptr(l), n, int(thr), int(window_s), float(rapid_s),
+                                      _ptr(last), _ptr(rp), cap, _ptr(count), _lib.stream_ptr()), "fb_burst_links")
+        m = int(count.item())
+        if m <= cap:
+            return last[:n].cpu().numpy(), rp[:m].cpu().numpy()
+        cap = m
+
+
+_PLAN_CACHE: dict = {}
+
+
+def _device_plan(height: int, width: int, out: int, device):
+    torch = _lib.require_cuda()
+    from .utils import resample as rs
+    key = (height, width, out, str(device))
+    if key not in _PLAN_CACHE:
+        p = rs.plan(height, width, out)
+        dev = {name: torch.from_numpy(getattr(p, name)).to(device) for name in ("hbounds", "hcoef", "vbounds", "vcoef")}
+        _PLAN_CACHE[key] = (p, dev)
+    return _PLAN_CACHE[key]
+
+
+def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), rgb_order: bool = False):
+    """Resize(out, bicubic, antialias) + CenterCrop + ToTensor + Normalize on the GPU.
+
+    images: [n,H,W,3] uint8 (numpy or CUDA tensor; BGR unless rgb_order).  Returns a CUDA float32
+    tensor [n,3,out,out] with planes R,G,B — what `scorer.preprocess` returns per image, stacked.
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    p, dev = _device_plan(h, w, out_size, t.device)
+    tmp = torch.empty((n, p.rows, out_size, 3), dtype=torch.uint8, device=t.device)
+    out = torch.empty((n, 3, out_size, out_size), dtype=torch.float32, device=t.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(t.device):
+        _lib.check(lib.fb_clip_preprocess(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), out_size,
+                                          _ptr(dev["hbounds"]), _ptr(dev["hcoef"]), p.hk, p.h_byte_lo, p.h_byte_hi,
+                                          _ptr(dev["vbounds"]), _ptr(dev["vcoef"]), p.vk, p.row0, p.rows,
+                                          C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), _ptr(tmp), _ptr(out),
+                                          _lib.stream_ptr()), "fb_clip_preprocess")
+    return out

@@ -1,0 +1,149 @@
+"""Global duplicate detection on pHash values — drop-in for utils/duplicate.py:44-169.
+
+The O(N^2) XOR/popcount/threshold loop (duplicate.py:94-119) runs on the GPU
+(csrc/hamming.cu, optionally sharded over ranks); Union-Find, group numbering and lead
+selection stay on the host and follow the reference step by step so the database ends up
+byte-identical: groups are numbered in ascending order of their Union-Find root
+(duplicate.py:150), the lead is the first member with the highest aggregate
+(duplicate.py:152, Python ``max`` keeps the first maximum).
+"""
+from __future__ import annotations
+
+import sqlite3
+
+import numpy as np
+
+from .. import ops
+
+
+class _UnionFind:
+    """Path-halving / union-by-rank, same tie-breaking as duplicate.py:15-36 (roots matter:
+    group ids follow sorted roots)."""
+
+    def __init__(self, n):
+        self.parent = list(range(n))
+        self.rank = [0] * n
+
+    def find(self, x):
+        p = self.parent
+        while p[x] != x:
+            p[x] = p[p[x]]
+            x = p[x]
+        return x
+
+    def union(self, a, b):
+        ra, rb = self.find(a), self.find(b)
+        if ra == rb:
+            return
+        if self.rank[ra] < self.rank[rb]:
+            ra, rb = rb, ra
+        self.parent[rb] = ra
+        if self.rank[ra] == self.rank[rb]:
+            self.rank[ra] += 1
+
+
+def max_hamming_distance(similarity_pct) -> int:
+    """duplicate.py:63 / scorer.py:1891: int(64 * (1 - pct/100))."""
+    return int(64 * (1 - similarity_pct / 100))
+
+
+def gather_pairs(pairs_local, group=None) -> np.ndarray:
+    """Concatenate the pair lists of all ranks (variable length) on every rank.
+
+    Single process: just moves the list to the host.  Multi-process: all_gather of the counts,
+    then all_gather of lists padded to the maximum.
+    """
+    import torch
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return pairs_local.cpu().numpy().astype(np.int64).reshape(-1, 2)
+    world = dist.get_world_size(group)
+    if world == 1:
+        return pairs_local.cpu().numpy().astype(np.int64).reshape(-1, 2)
+    dev = pairs_local.device
+    count = torch.tensor([pairs_local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    padded = torch.zeros((mx, 2), dtype=torch.int32, device=dev)
+    padded[: pairs_local.shape[0]] = pairs_local
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    parts = [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
+    return np.concatenate(parts, axis=0).astype(np.int64).reshape(-1, 2)
+
+
+def group_duplicates(n: int, pairs: np.ndarray, aggregates):
+    """Union-Find + numbering + lead selection.  Returns (group_id int64[n] with 0 = none,
+    is_lead uint8[n]).
+
+    The reference unions matches in lexicographic (i, j) order (duplicate.py:97-119); the shape
+    of the forest — and so the sorted roots that number the groups — depends on that order, so
+    the GPU's unordered pair list is sorted first.
+    """
+    gid = np.zeros(n, np.int64)
+    lead = np.zeros(n, np.uint8)
+    if len(pairs) == 0:
+        return gid, lead
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    order = np.lexsort((pairs[:, 1], pairs[:, 0]))
+    uf = _UnionFind(n)
+    for i, j in pairs[order].tolist():
+        uf.union(i, j)
+    groups: dict[int, list[int]] = {}
+    for idx in range(n):
+        groups.setdefault(uf.find(idx), []).append(idx)
+    next_id = 1
+    for _root, members in sorted(groups.items()):
+        if len(members) < 2:
+            continue
+        best = max(members, key=lambda k: aggregates[k])
+        for k in members:
+            gid[k] = next_id
+        lead[best] = 1
+        next_id += 1
+    return gid, lead
+
+
+def find_duplicate_groups(hashes: np.ndarray, aggregates, max_distance: int, group=None):
+    """hashes uint64[n] (row order = ORDER BY path) -> (group_id, is_lead).  With an initialised
+    torch.distributed group every rank scans its share of row tiles and the pair lists are
+    all-gathered; all ranks return the same answer."""
+    import torch.distributed as dist
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    local = ops.hamming_pairs(hashes, max_distance, part=rank, nparts=world)
+    pairs = gather_pairs(local, group)
+    return group_duplicates(len(hashes), pairs, aggregates)
+
+
+def detect_duplicates(db_path, config_path=None):
+    """Same contract as the reference's detect_duplicates(db_path, config_path): reads
+    (path, phash, aggregate) ordered by path, writes duplicate_group_id / is_duplicate_lead."""
+    from ..config import ScoringConfig
+    config = ScoringConfig(config_path, validate=False)
+    pct = config.get_duplicate_detection_settings().get("similarity_threshold_percent", 90)
+    max_distance = max_hamming_distance(pct)
+    print(f"Duplicate detection: similarity >= {pct}% (Hamming distance <= {max_distance})")
+    with sqlite3.connect(db_path) as conn:
+        rows = conn.execute("SELECT path, phash, aggregate FROM photos WHERE phash IS NOT NULL ORDER BY path").fetchall()
+    if not rows:
+        print("No photos with pHash found.")
+        return
+    paths = [r[0] for r in rows]
+    aggregates = [r[2] or 0.0 for r in rows]
+    hashes = np.array([int(r[1], 16) for r in rows], dtype=np.uint64)
+    print(f"Comparing {len(paths)} photos...")
+    gid, lead = find_duplicate_groups(hashes, aggregates, max_distance)
+    with sqlite3.connect(db_path) as conn:
+        conn.execute("UPDATE photos SET duplicate_group_id = NULL, is_duplicate_lead = 0")
+        sel = np.flatnonzero(gid)
+        if len(sel) == 0:
+            print("No duplicates found.")
+        else:
+            conn.executemany("UPDATE photos SET duplicate_group_id = ?, is_duplicate_lead = ? WHERE path = ?",
+                             [(int(gid[k]), int(lead[k]), paths[k]) for k in sel.tolist()])
+            print(f"Marked {int(gid.max())} groups: {len(sel)} photos")
+        conn.commit()

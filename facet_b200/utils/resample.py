@@ -1,0 +1,134 @@
+"""Coefficient tables for the CLIP preprocess kernels.
+
+`scorer.preprocess` in the reference (processing/scorer.py:508-510) is open_clip's inference
+transform: torchvision ``Resize(224, BICUBIC)`` (shorter side, on a PIL image, hence Pillow's
+antialiased resampler) -> ``CenterCrop(224)`` -> ``ToTensor`` -> ``Normalize``.  Pillow and
+torchvision are third-party to the reference (pillow>=10.0.0, torchvision; requirements.txt)
+and their sources are not under /root/reference; this module restates Pillow's published
+algorithm (src/libImaging/Resample.c: ``precompute_coeffs`` + ``normalize_coeffs_8bpc``) in
+float64, tap by tap, so the integer taps are identical.  Parity is pinned in
+tests/test_preprocess.py against the installed Pillow/torchvision themselves.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from functools import lru_cache
+
+import numpy as np
+
+PRECISION_BITS = 32 - 8 - 2
+BICUBIC_SUPPORT = 2.0
+
+# open_clip's pretrained config for ViT-L-14 / laion2b_s32b_b82k; OpenAI CLIP
+# statistics are kept for callers that load OpenAI weights.
+LAION_MEAN = (0.5, 0.5, 0.5)
+LAION_STD = (0.5, 0.5, 0.5)
+OPENAI_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _bicubic(x: np.ndarray) -> np.ndarray:
+    a = -0.5
+    x = np.abs(x)
+    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    far = (((x - 5) * x + 8) * x - 4) * a
+    return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
+
+
+def precompute_coeffs(in_size: int, out_size: int):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for box (0, in_size), bicubic.
+
+    Returns (bounds int32 [out,2] = first tap / tap count, coef int32 [out,ksize], ksize).
+    """
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = BICUBIC_SUPPORT * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.float64)
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        xmin = max(xmin, 0)
+        xmax = int(center + support + 0.5)
+        xmax = min(xmax, in_size)
+        cnt = xmax - xmin
+        w = _bicubic((np.arange(cnt, dtype=np.float64) + xmin - center + 0.5) * ss)
+        ww = 0.0
+        for v in w:            # sequential double accumulation, as in C
+            ww += float(v)
+        if ww != 0.0:
+            w = w / ww
+        kk[xx, :cnt] = w
+        bounds[xx] = (xmin, cnt)
+    scaled = kk * float(1 << PRECISION_BITS)
+    coef = np.where(kk < 0, np.trunc(-0.5 + scaled), np.trunc(0.5 + scaled)).astype(np.int32)
+    return bounds, coef, ksize
+
+
+def resized_size(height: int, width: int, size: int):
+    """torchvision Resize(int): shorter side -> size, longer side int(size*long/short)."""
+    short, long_ = (width, height) if width <= height else (height, width)
+    new_short, new_long = size, int(size * long_ / short)
+    return (new_long, new_short) if width <= height else (new_short, new_long)   # (new_h, new_w)
+
+
+@dataclass(frozen=True)
+class ResamplePlan:
+    height: int
+    width: int
+    out: int
+    hbounds: np.ndarray
+    hcoef: np.ndarray
+    hk: int
+    h_byte_lo: int
+    h_byte_hi: int
+    vbounds: np.ndarray
+    vcoef: np.ndarray
+    vk: int
+    row0: int
+    rows: int
+
+
+@lru_cache(maxsize=64)
+def plan(height: int, width: int, out: int = 224) -> ResamplePlan:
+    """Tables for Resize(out) + CenterCrop(out) of an HxW image, cropped to the kept outputs."""
+    new_h, new_w = resized_size(height, width, out)
+    if new_h < out or new_w < out:
+        raise ValueError("image too small for the crop")
+    top = int(round((new_h - out) / 2.0))
+    left = int(round((new_w - out) / 2.0))
+    hb, hc, hk = precompute_coeffs(width, new_w)
+    vb, vc, vk = precompute_coeffs(height, new_h)
+    hb, hc = hb[left:left + out].copy(), hc[left:left + out].copy()
+    vb, vc = vb[top:top + out].copy(), vc[top:top + out].copy()
+    x_lo = int(hb[:, 0].min())
+    x_hi = int((hb[:, 0] + hb[:, 1]).max())
+    row0 = int(vb[:, 0].min())
+    row1 = int((vb[:, 0] + vb[:, 1]).max())
+    return ResamplePlan(height, width, out, np.ascontiguousarray(hb), np.ascontiguousarray(hc), hk,
+                        x_lo * 3, x_hi * 3, np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk,
+                        row0, row1 - row0)
+
+
+def resample_reference_numpy(img_rgb: np.ndarray, out: int = 224) -> np.ndarray:
+    """Host evaluation of the same integer plan (used by CPU tests of the tables, not by the
+    product path): returns the uint8 [out,out,3] crop Pillow would produce."""
+    p = plan(img_rgb.shape[0], img_rgb.shape[1], out)
+    src = img_rgb.astype(np.int64)
+    tmp = np.zeros((p.rows, out, 3), np.uint8)
+    for xo in range(out):
+        f, c = p.hbounds[xo]
+        acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(src[p.row0:p.row0 + p.rows, f:f + c, :],
+                                                         p.hcoef[xo, :c].astype(np.int64), axes=([1], [0]))
+        tmp[:, xo, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
+    res = np.zeros((out, out, 3), np.uint8)
+    t64 = tmp.astype(np.int64)
+    for yo in range(out):
+        f, c = p.vbounds[yo]
+        f -= p.row0
+        acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(p.vcoef[yo, :c].astype(np.int64), t64[f:f + c], axes=([0], [0]))
+        res[yo] = np.clip(acc >> PRECISION_BITS, 0, 255)
+    return res

@@ -1,0 +1,128 @@
+/* facet_b200 — C ABI of the B200-native scoring-pass library (libfacet_b200.so).
+ *
+ * Every entry point takes plain pointers and sizes; there are no torch / C++ types in the
+ * signatures.  Device pointers are prefixed d_, host pointers h_.  `stream` is a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  All functions return 0
+ * on success, a positive cudaError_t on a CUDA failure and a negative value on a contract
+ * violation; fb_last_error() returns the message for the calling thread.
+ *
+ * Each function cites the reference interface it replaces (paths under rlorenzo/facet).
+ * The Python host mirror (facet_b200/analyzers, facet_b200/processing, facet_b200/utils)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ */
+#ifndef FACET_B200_H_
+#define FACET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+#define FB_HS_BINS (180 * 256)
+
+int fb_abi_version(void);
+const char* fb_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench gpu_launches). */
+uint64_t fb_launch_count(void);
+int fb_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Technical metrics — replaces analyzers/image_cache.py:22-32 (ImageCache: gray, hsv,
+ * Laplacian variance) and the pixel passes of analyzers/technical.py:94 (H-S calcHist),
+ * :153 (luminance calcHist), :263-264/:326 (percentiles — derived from hist256),
+ * :302 (Immerkaer filter2D sum).
+ *
+ * d_images   [n][height][width][3] uint8, interleaved, C-contiguous rows; image i starts at
+ *            d_images + i*image_stride.  rgb_order = 0 for the reference's BGR arrays
+ *            (utils/image_loading.py:106), 1 for RGB.
+ * d_hist256  [n][256]      uint32  luminance histogram (exact counts)
+ * d_hs_hist  [n][180][256] uint32  hue x saturation histogram (exact counts)
+ * d_sums     [n][4]        int64   { sum Laplacian, sum Laplacian^2, sum |Immerkaer|, 0 }
+ * force_generic != 0 selects the any-shape kernel (used by tests as a second opinion).
+ * Outputs are overwritten.  Images must be at least 2x2 (reflect-101 borders).
+ */
+int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
+                  int rgb_order, uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums,
+                  int force_generic, void* stream);
+
+/* Per-image reductions of the H-S histogram — technical.py:97-104 (entropy) and :237
+ * (mean saturation).  d_out [n][4] float64 = { entropy_bits, sum_saturation, nonzero_bins,
+ * total_count }. */
+int fb_tech_derive(const uint32_t* d_hs_hist, int n, double* d_out, void* stream);
+
+/* Host-buffer convenience for the same pass (the call the reference-facing plugin makes with
+ * numpy arrays): H2D copy, both kernels, D2H copy, synchronises.  h_hs_hist may be NULL. */
+int fb_tech_stats_host(const uint8_t* h_images, int n, int height, int width, int rgb_order,
+                       uint32_t* h_hist256, int64_t* h_sums, double* h_derived,
+                       uint32_t* h_hs_hist);
+
+/* gray [H][W] and hsv [H][W][3] uint8 planes of one image — the arrays ImageCache exposes
+ * (analyzers/image_cache.py:30-31) for callers outside the technical metrics. */
+int fb_gray_hsv(const uint8_t* d_image, int height, int width, int rgb_order, uint8_t* d_gray,
+                uint8_t* d_hsv, void* stream);
+
+/* Laplacian sums of image crops — analyzers/face.py:272-279 `_get_crop_sharpness`
+ * (isolation bonus, processing/batch_processor.py:254-260).  Each crop is filtered with its
+ * own reflect-101 border.  d_boxes [k][4] int32 = x1,y1,x2,y2 (exclusive end, clipped by the
+ * caller); d_out [k][3] int64 = { pixel count, sum Laplacian, sum Laplacian^2 }. */
+int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_order,
+                     const int32_t* d_boxes, int k, int64_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CLIP preprocess — replaces `scorer.preprocess` (processing/scorer.py:508-510, used at
+ * processing/batch_processor.py:95): torchvision Resize(shorter side, BICUBIC, antialias on
+ * PIL) -> CenterCrop -> ToTensor -> Normalize.  Bit-exact with Pillow's 8-bit resampler
+ * (22-bit fixed-point coefficients, horizontal pass first, uint8 intermediate).
+ *
+ * The caller supplies the coefficient tables (facet_b200/utils/resample.py computes them the
+ * way Pillow's precompute_coeffs/normalize_coeffs_8bpc do):
+ *   d_hbounds [out][2] int32 (first tap, tap count), d_hcoef [out][hk] int32   horizontal
+ *   d_vbounds / d_vcoef likewise for the vertical pass
+ *   h_byte_lo/h_byte_hi  byte range of an input row the horizontal taps touch
+ *   row0/rows            input rows the vertical taps touch (the only rows pass 1 produces)
+ * d_tmp      scratch [n][rows][out][3] uint8 (horizontal pass output)
+ * d_out      [n][3][out][out] float32, planes R,G,B, (x/255 - mean[c]) / std[c]
+ * mean3/std3 are HOST pointers to 3 floats each.
+ */
+int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
+                       int rgb_order, int out_size,
+                       const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
+                       int h_byte_lo, int h_byte_hi,
+                       const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
+                       int row0, int rows,
+                       const float* mean3, const float* std3,
+                       uint8_t* d_tmp, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Duplicate / burst grouping — replaces the O(N^2) loop of utils/duplicate.py:94-119 and the
+ * pairwise predicate of processing/scorer.py:1943-1968.
+ *
+ * fb_hamming_pairs: all pairs (i, j), i < j, i in this part's rows, with
+ * popcount(h[i]^h[j]) <= max_distance.  Rows are dealt to parts in tiles of
+ * FB_HAMMING_ROW_TILE (tile t belongs to part t % nparts) so a triangular problem balances
+ * across GPUs.  d_pairs [cap][2] int32 receives the pairs in no particular order; *d_count
+ * (uint64, device) receives how many pairs exist — if it exceeds cap the list is truncated
+ * and the caller retries with a larger buffer.
+ */
+#define FB_HAMMING_ROW_TILE 2048
+int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts,
+                     int32_t* d_pairs, int64_t cap, uint64_t* d_count, void* stream);
+
+/* fb_burst_links: for photo i (rows in the reference's ORDER BY date_taken order) the largest
+ * b in [d_lo[i], i) that satisfies the "slow" rule |t_i - t_b| <= window_s && hamming <= thr
+ * (scorer.py:1962-1965), or -1.  Candidates of the "rapid" rule (|dt| <= rapid_s &&
+ * hamming <= 2*thr, scorer.py:1957-1960) are appended to d_rapid_pairs [(i,b)] so the host can
+ * apply the shares_person check.  d_flags[i]: bit0 = date parsed (scorer.py:1946-1952),
+ * bit1 = hash present (scorer.py:1927-1929).  d_lo[i] is a host-computed lower bound of the
+ * window (any b < d_lo[i] is farther than window_s from i). */
+int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint8_t* d_flags,
+                   const int32_t* d_lo, int64_t n, int thr, int64_t window_s, double rapid_s,
+                   int32_t* d_last_slow, int32_t* d_rapid_pairs, int64_t rapid_cap,
+                   uint64_t* d_rapid_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACET_B200_H_ */
