@@ -35,6 +35,11 @@ constexpr int kLanePx = 16;
 constexpr int kTileW = 32 * kLanePx;   // 512 px per warp row
 constexpr int kH256Copies = 32;        // one luminance-histogram column per lane
 constexpr size_t kSmemWords = kHsBins + 256 * kH256Copies + 512;
+constexpr int kOffH256 = kHsBins;                       // word offsets inside the dynamic smem block
+constexpr int kOffSdiv = kOffH256 + 256 * kH256Copies;
+constexpr int kOffHdiv = kOffSdiv + 256;
+
+extern __shared__ __align__(16) unsigned int fb_smem[];
 
 struct TechArgs {
     const uint8_t* img;
@@ -44,6 +49,7 @@ struct TechArgs {
     unsigned int* hist256;
     unsigned int* hs;
     unsigned long long* sums;
+    int gray_round;   // 1 << 14, passed through the constant bank so IMAD can take it as an addend
 };
 
 __device__ __forceinline__ int sdiv_entry(int i) {   // round-half-even(255*4096 / i)
@@ -94,6 +100,12 @@ struct RowRegs {
     uint32_t halo;      // 3 bytes of the one extra pixel lane 0 / lane 31 may need
 };
 
+// histogram increment in shared memory (ptxas turns "+1" into the warp-aggregating
+// ATOMS.POPC.INC, which must not be predicated: FULL tiles call it unconditionally)
+__device__ __forceinline__ void smem_inc(uint32_t smem_base, int word) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_base + 4u * (uint32_t)word), "r"(1u) : "memory");
+}
+
 template <bool RGB>
 __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl, bool need_halo, int hx) {
     const uint8_t* p = row + (size_t)xl * 3;
@@ -107,10 +119,8 @@ __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl,
     }
 }
 
-template <bool RGB>
+template <bool RGB, bool FULL>
 __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* img, int tx, int uy,
-                                             unsigned int* s_hs, unsigned int* s_h256,
-                                             const unsigned int* s_sdiv, const unsigned int* s_hdiv,
                                              unsigned long long& out_l2, unsigned long long& out_n,
                                              long long& out_l) {
     const int lane = (int)lane_id();
@@ -137,6 +147,8 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
         return img + (size_t)y * row_bytes;
     };
 
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fb_smem);
+    const int kRound = a.gray_round;
     const int nrows = rb + 2;
     RowRegs cur, nx1, nx2;
     load_row<RGB>(cur, row_ptr(0), xl, need_halo, hx);
@@ -160,17 +172,40 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
         uint32_t w[12] = {cur.q0.x, cur.q0.y, cur.q0.z, cur.q0.w, cur.q1.x, cur.q1.y,
                           cur.q1.z, cur.q1.w, cur.q2.x, cur.q2.y, cur.q2.z, cur.q2.w};
         int gr[16];
+        if (owned) {
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const int o = 3 * p;
-            int c0 = (int)__byte_perm(w[o >> 2], 0u, 0x4440 + (o & 3));
-            int c1 = (int)__byte_perm(w[(o + 1) >> 2], 0u, 0x4440 + ((o + 1) & 3));
-            int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
-            const int b = RGB ? c2 : c0, g = c1, r = RGB ? c0 : c2;
-            gr[p] = gray_of(b, g, r);
-            if (owned && active) {
-                atomicAdd(&s_hs[hs_bin_of(b, g, r, s_sdiv, s_hdiv)], 1u);
-                atomicAdd(&s_h256[gr[p] * kH256Copies + lane], 1u);
+            for (int p = 0; p < 16; ++p) {
+                const int o = 3 * p;
+                const int c0 = (int)__byte_perm(w[o >> 2], 0u, 0x4440 + (o & 3));
+                const int c1 = (int)__byte_perm(w[(o + 1) >> 2], 0u, 0x4440 + ((o + 1) & 3));
+                const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
+                const int b = RGB ? c2 : c0, g = c1, r = RGB ? c0 : c2;
+                gr[p] = (3735 * b + kRound + 19235 * g + 9798 * r) >> 15;
+                // OpenCV RGB2HSV_b (hue range 180), branch-free
+                const int v = max(max(b, g), r);
+                const int d = v - min(min(b, g), r);
+                const int sd = (int)fb_smem[kOffSdiv + v];
+                const int hd = (int)fb_smem[kOffHdiv + d];
+                const bool vr = (v == r), vg = (v == g);
+                const int x = vr ? g : (vg ? b : r);
+                const int y = vr ? b : (vg ? r : g);
+                const int off = vr ? 0 : (vg ? 2 * d : 4 * d);
+                const int sat = (d * sd + 2048) >> 12;
+                int hue = ((x - y + off) * hd + 2048) >> 12;
+                hue += (hue >> 31) & 180;
+                if (FULL || active) {
+                    smem_inc(smem_base, hue * 256 + sat);
+                    smem_inc(smem_base, kOffH256 + gr[p] * kH256Copies + lane);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int o = 3 * p;
+                const int c0 = (int)__byte_perm(w[o >> 2], 0u, 0x4440 + (o & 3));
+                const int c1 = (int)__byte_perm(w[(o + 1) >> 2], 0u, 0x4440 + ((o + 1) & 3));
+                const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
+                gr[p] = (3735 * (RGB ? c2 : c0) + kRound + 19235 * c1 + 9798 * (RGB ? c0 : c2)) >> 15;
             }
         }
         int gh;
@@ -255,11 +290,11 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
 
 template <bool RGB>
 __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
-    extern __shared__ __align__(16) unsigned int smem[];
-    unsigned int* s_hs = smem;
-    unsigned int* s_h256 = smem + kHsBins;
-    unsigned int* s_sdiv = s_h256 + 256 * kH256Copies;
-    unsigned int* s_hdiv = s_sdiv + 256;
+    unsigned int* const smem = fb_smem;
+    unsigned int* const s_hs = fb_smem;
+    unsigned int* const s_h256 = fb_smem + kOffH256;
+    unsigned int* const s_sdiv = fb_smem + kOffSdiv;
+    unsigned int* const s_hdiv = fb_smem + kOffHdiv;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -285,8 +320,9 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         long long acc_l = 0;
         for (long long u = u0 + warp; u < seg_end; u += kWarps) {
             const int ul = (int)(u - img_first);
-            process_unit<RGB>(a, img, ul % a.tiles_x, ul / a.tiles_x, s_hs, s_h256, s_sdiv, s_hdiv,
-                              acc_l2, acc_n, acc_l);
+            const int tx = ul % a.tiles_x;
+            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
+            else process_unit<RGB, false>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
         }
         acc_l2 = warp_sum_u64(acc_l2);
         acc_n = warp_sum_u64(acc_n);
@@ -500,6 +536,7 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     a.hist256 = d_hist256;
     a.hs = d_hs_hist;
     a.sums = reinterpret_cast<unsigned long long*>(d_sums);
+    a.gray_round = 1 << 14;
     const bool aligned = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_images) & 15) == 0) &&
                          (image_stride % 16 == 0);
     const int sms = sm_count();

@@ -1,0 +1,16 @@
+"""One technical-pass launch on 8 'photo' 24 MP frames (target of the ncu capture)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "scripts")
+from facet_b200 import ops  # noqa: E402
+from time_tech import make_frames  # noqa: E402
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "photo"
+fr = make_frames(kind, 8)
+for _ in range(3):
+    ops.tech_stats_raw(fr)
+torch.cuda.synchronize()
+print("ok")
