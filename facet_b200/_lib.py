@@ -36,6 +36,28 @@ _SIGNATURES = {
 }
 
 
+class VitLayer(C.Structure):
+    _fields_ = [(n, _P) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_out", "b_out",
+                                  "w_fc", "b_fc", "w_proj", "b_proj")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [(n, _P) for n in ("w_patch", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b",
+                                  "proj", "head_w1", "head_b1", "head_w2", "head_b2", "tag_emb")] + [
+        ("n_tags", C.c_int), ("n_layers", C.c_int), ("layers", C.POINTER(VitLayer))]
+
+
+_SIGNATURES.update({
+    "fb_gemm_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
+                               _P, C.c_int64, _P]),
+    "fb_vit_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "fb_vit_forward": (C.c_int, [C.POINTER(VitWeights), _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P]),
+    "fb_vit_im2col": (C.c_int, [_P, C.c_int, _P, _P]),
+    "fb_vit_layernorm": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "fb_vit_attention": (C.c_int, [_P, C.c_int, _P, _P]),
+})
+
+
 def declared_symbols():
     return sorted(_SIGNATURES)
 

@@ -8,6 +8,11 @@
 #include "kernels.h"
 
 namespace fb {
+int vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void* d_workspace, size_t workspace_bytes,
+                float* d_features, float* d_embedding, float* d_aesthetic_raw, float* d_tag_sims, cudaStream_t st);
+}
+
+namespace fb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -154,6 +159,41 @@ int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint
                                 (long long)window_s, rapid_s, d_last_slow, d_rapid_pairs, (long long)rapid_cap,
                                 reinterpret_cast<unsigned long long*>(d_rapid_count), (cudaStream_t)stream);
     if (rc == 0 && n >= 1) count_launch(1);
+    return rc;
+}
+
+int fb_gemm_bf16(const void* d_a, int64_t lda, const void* d_b, int64_t ldb, int m, int n, int k, int mode,
+                 const float* d_bias, void* d_out, int64_t ldo, const float* d_residual, int64_t ldr, void* stream) {
+    int rc = launch_gemm_bf16(d_a, lda, d_b, ldb, m, n, k, mode, d_bias, d_out, ldo, d_residual, ldr, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+size_t fb_vit_workspace_bytes(int batch) { return vit_workspace_bytes(batch); }
+
+int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void* d_workspace, size_t workspace_bytes,
+                   float* d_features, float* d_embedding, float* d_aesthetic_raw, float* d_tag_sims, void* stream) {
+    return vit_forward(w, d_clip_in, batch, d_workspace, workspace_bytes, d_features, d_embedding, d_aesthetic_raw,
+                       d_tag_sims, (cudaStream_t)stream);
+}
+
+int fb_vit_im2col(const float* d_clip_in, int batch, void* d_out_bf16, void* stream) {
+    int rc = launch_im2col_patch14(d_clip_in, batch, d_out_bf16, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* gamma, const float* beta,
+                     const float* class_emb, const float* pos_emb, void* d_out, int64_t ld_out, int out_bf16,
+                     void* stream) {
+    int rc = launch_layernorm(d_in, ld_in, rows, gamma, beta, class_emb, pos_emb, d_out, ld_out, out_bf16, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
+    int rc = launch_attention(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
     return rc;
 }
 

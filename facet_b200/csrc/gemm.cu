@@ -1,0 +1,272 @@
+// bf16 GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] * B[N,K]^T (+ fused epilogue).
+//
+// This is the GEMM under the CLIP ViT-L/14 image tower that the reference runs through
+// open_clip / cuBLAS (`self.model.encode_image`, processing/scorer.py:662): QKV, attention
+// out-projection, MLP fc / proj and the patch-embedding convolution (as an im2col GEMM), and the
+// cosine all-pairs GEMM of the similarity stage.  Both operands are K-major (PyTorch Linear
+// weights [out,in] are already "B[N,K]").
+//
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: 128x64 A tile + 256x64 B tile per stage, 4-stage mbarrier ring,
+//               128-byte swizzle
+//   warp 1      tcgen05.mma issuer (one elected lane): 128x256x16 UMMAs, fp32 accumulators in
+//               TMEM, two 256-column accumulator buffers so tile i+1 overlaps the epilogue of i
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / GELU / residual, direct
+//               16-byte global stores
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int kABytes = BM * BK * 2;     // 16 KB
+constexpr int kBBytes = BN * BK * 2;     // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+    int M, N, K;
+    int mode;             // FB_GEMM_*
+    const float* bias;    // [N] or nullptr
+    void* out;            // bf16 or f32, row-major
+    long long ldo;        // elements
+    const float* residual;
+    long long ldr;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (p.M + BM - 1) / BM;
+    const int num_tiles = tiles_m * tiles_n;
+    const int kblocks = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tmem_full[a], 1);
+            tc::mbar_init(&tmem_empty[a], kEpiWarps);
+        }
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_a);
+        tc::tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    tc::mbar_expect_tx(&full_bar[stage], kStageBytes);
+                    tc::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                    tc::tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                tc::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = tc::make_desc_k_sw128(sa);
+                    const uint64_t db = tc::make_desc_k_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the address field
+                        tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tmem_full[acc]);            // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int ew = warp - 2;
+        const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        const int half = ew >> 2;              // which 128 of the 256 accumulator columns
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
+            tc::tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = n0 + half * 128 + c * 32;
+                uint32_t v[32];
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128 + c * 32, v);
+                tc::tmem_ld_wait();
+                if (col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    }
+                    if (p.mode == FB_GEMM_BIAS_GELU_BF16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    }
+                    if (row_ok) {
+                        if (p.mode == FB_GEMM_BIAS_BF16 || p.mode == FB_GEMM_BIAS_GELU_BF16) {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                dst[j] = make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                                    tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0);
+                            if (p.mode == FB_GEMM_BIAS_RESIDUAL_F32) {
+                                const float4* res = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r4 = res[j];
+                                    dst[j] = make_float4(f[4 * j] + r4.x, f[4 * j + 1] + r4.y, f[4 * j + 2] + r4.z, f[4 * j + 3] + r4.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- tensor-map encoding through the driver entry point (no link against libcuda) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = encode_fn();
+    FB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride_elems * 2) % 16 == 0,
+               "TMA needs a 16-byte aligned base and row pitch");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
+                     const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
+                     cudaStream_t stream) {
+    FB_REQUIRE(d_a && d_b && d_out, "fb_gemm_bf16: null pointer");
+    FB_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % BK == 0, "fb_gemm_bf16: K must be a positive multiple of %d (got %d)", BK, K);
+    FB_REQUIRE(N % 32 == 0, "fb_gemm_bf16: N must be a multiple of 32 (got %d)", N);
+    FB_REQUIRE(mode >= 0 && mode <= 3, "fb_gemm_bf16: unknown epilogue mode %d", mode);
+    FB_REQUIRE(mode != FB_GEMM_BIAS_RESIDUAL_F32 || d_residual, "fb_gemm_bf16: residual pointer required");
+    const int out_elt = (mode == FB_GEMM_BIAS_BF16 || mode == FB_GEMM_BIAS_GELU_BF16) ? 2 : 4;
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (ldo * out_elt) % 16 == 0, "fb_gemm_bf16: output not 16-byte aligned");
+    FB_REQUIRE(!d_bias || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "fb_gemm_bf16: bias not 16-byte aligned");
+    FB_REQUIRE(!d_residual || ((reinterpret_cast<uintptr_t>(d_residual) & 15) == 0 && (ldr * 4) % 16 == 0), "fb_gemm_bf16: residual not aligned");
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d(&ta, d_a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
+    if (rc) return rc;
+    GemmArgs p;
+    p.M = M; p.N = N; p.K = K; p.mode = mode; p.bias = d_bias; p.out = d_out; p.ldo = ldo;
+    p.residual = d_residual; p.ldr = ldr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fb

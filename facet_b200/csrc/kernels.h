@@ -3,6 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define FB_GEMM_BIAS_BF16 0
+#define FB_GEMM_BIAS_GELU_BF16 1
+#define FB_GEMM_BIAS_RESIDUAL_F32 2
+#define FB_GEMM_F32 3
+
 namespace fb {
 
 int tech_rows_per_unit(int n, int H, int W, int sms);
@@ -27,5 +32,19 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                            cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
+
+int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
+                     const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
+                     cudaStream_t stream);
+int launch_im2col_patch14(const float* d_x, int batch, void* d_out, cudaStream_t stream);
+int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
+                     const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,
+                     cudaStream_t stream);
+int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);
+int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
+                    const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
+                    float* emb, float* raw, float* sims, cudaStream_t stream);
+void count_launch(int k);
+size_t vit_workspace_bytes(int batch);
 
 }  // namespace fb

@@ -221,3 +221,53 @@ def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5,
                                           C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), _ptr(tmp), _ptr(out),
                                           _lib.stream_ptr()), "fb_clip_preprocess")
     return out
+
+
+GEMM_BIAS_BF16, GEMM_BIAS_GELU_BF16, GEMM_BIAS_RESIDUAL_F32, GEMM_F32 = 0, 1, 2, 3
+
+
+def gemm_bf16(a, b, mode: int = GEMM_F32, bias=None, residual=None, out=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T with the tcgen05 kernel.  a, b: CUDA bf16, row-major (last dim
+    contiguous).  Returns bf16 (modes 0/1) or float32 (modes 2/3)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise TypeError("gemm_bf16 takes bf16 operands")
+    if a.stride(-1) != 1 or b.stride(-1) != 1:
+        raise ValueError("operands must be K-contiguous")
+    m, k = a.shape
+    n, kb = b.shape
+    if k != kb:
+        raise ValueError("K mismatch")
+    odt = torch.bfloat16 if mode in (GEMM_BIAS_BF16, GEMM_BIAS_GELU_BF16) else torch.float32
+    if out is None:
+        out = torch.empty((m, n), dtype=odt, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.fb_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), m, n, k, int(mode),
+                                    _ptr(bias) if bias is not None else None, _ptr(out), out.stride(0),
+                                    _ptr(residual) if residual is not None else None,
+                                    residual.stride(0) if residual is not None else 0, _lib.stream_ptr()), "fb_gemm_bf16")
+    return out
+
+
+def vit_layernorm(x, gamma, beta, out_bf16=True, class_emb=None, pos_emb=None, rows=None):
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    rows = int(rows if rows is not None else x.shape[0])
+    out = torch.empty((rows, 1024), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.fb_vit_layernorm(_ptr(x), x.stride(0), rows, _ptr(gamma), _ptr(beta),
+                                        _ptr(class_emb) if class_emb is not None else None,
+                                        _ptr(pos_emb) if pos_emb is not None else None, _ptr(out), 1024,
+                                        int(bool(out_bf16)), _lib.stream_ptr()), "fb_vit_layernorm")
+    return out
+
+
+def vit_attention(qkv, batch: int):
+    """qkv: CUDA bf16 [batch*257, 3072] -> bf16 [batch*257, 1024]."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    out = torch.empty((batch * 257, 1024), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.fb_vit_attention(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
+    return out

@@ -13,6 +13,7 @@
 #ifndef FACET_B200_H_
 #define FACET_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -121,6 +122,65 @@ int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint
                    const int32_t* d_lo, int64_t n, int thr, int64_t window_s, double rapid_s,
                    int32_t* d_last_slow, int32_t* d_rapid_pairs, int64_t rapid_cap,
                    uint64_t* d_rapid_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CLIP ViT-L/14 image tower + heads — replaces `self.model.encode_image(inputs)`,
+ * `F.normalize(features)`, `self.aesthetic_head(features.float())`
+ * (processing/scorer.py:661-664; twins at :596, :610 and processing/multi_pass.py:523) and the
+ * tag similarity `image_features @ self.text_embeddings.T` (models/tagger.py:99-101).
+ *
+ * fb_gemm_bf16: C[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores, A/B bf16 row-major
+ * (K-major; a PyTorch Linear weight [out,in] is B as is), K % 64 == 0, N % 32 == 0.
+ * Epilogue modes: 0 bf16 out = acc + bias; 1 bf16 out = gelu_erf(acc + bias);
+ * 2 f32 out = acc + bias + residual (out may alias residual); 3 f32 out = acc (+ bias). */
+#define FB_GEMM_BIAS_BF16 0
+#define FB_GEMM_BIAS_GELU_BF16 1
+#define FB_GEMM_BIAS_RESIDUAL_F32 2
+#define FB_GEMM_F32 3
+int fb_gemm_bf16(const void* d_a, int64_t lda, const void* d_b, int64_t ldb, int m, int n, int k, int mode,
+                 const float* d_bias, void* d_out, int64_t ldo, const float* d_residual, int64_t ldr,
+                 void* stream);
+
+/* Device pointers of one packed ViT-L/14 (width 1024, 24 layers, 16 heads, MLP 4096, patch 14,
+ * 224 px, 257 tokens, output 768).  GEMM weights are bf16 [out][in]; everything else fp32. */
+typedef struct fb_vit_layer {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    const void *w_qkv;  const float *b_qkv;    /* [3072][1024] bf16, [3072] */
+    const void *w_out;  const float *b_out;    /* [1024][1024] */
+    const void *w_fc;   const float *b_fc;     /* [4096][1024] */
+    const void *w_proj; const float *b_proj;   /* [1024][4096] */
+} fb_vit_layer;
+
+typedef struct fb_vit_weights {
+    const void *w_patch;                       /* [1024][640] bf16: conv1 weight flattened (c,ky,kx), zero padded */
+    const float *class_emb;                    /* [1024] */
+    const float *pos_emb;                      /* [257][1024] */
+    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+    const float *proj;                         /* [1024][768] fp32 */
+    const float *head_w1, *head_b1;            /* aesthetic head Linear(768,256): [256][768], [256] (scorer.py:578-582) */
+    const float *head_w2, *head_b2;            /* Linear(256,1): [256], [1] */
+    const float *tag_emb;                      /* [n_tags][768] L2-normalised text embeddings (tagger.py:73) or NULL */
+    int n_tags;
+    int n_layers;                              /* 24 */
+    const fb_vit_layer *layers;                /* HOST array of n_layers entries */
+} fb_vit_weights;
+
+size_t fb_vit_workspace_bytes(int batch);
+
+/* d_clip_in [batch][3][224][224] float32 (output of fb_clip_preprocess).  Outputs (device):
+ * d_features [batch][768] un-normalised, d_embedding [batch][768] L2-normalised,
+ * d_aesthetic_raw [batch] (the reference maps it with clip((raw+1)*5, 0, 10), scorer.py:669),
+ * d_tag_sims [batch][n_tags] (may be NULL when n_tags == 0). */
+int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void* d_workspace,
+                   size_t workspace_bytes, float* d_features, float* d_embedding, float* d_aesthetic_raw,
+                   float* d_tag_sims, void* stream);
+
+/* Individual stages (exposed for tests and for callers that schedule the tower themselves). */
+int fb_vit_im2col(const float* d_clip_in, int batch, void* d_out_bf16, void* stream);
+int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* gamma, const float* beta,
+                     const float* class_emb, const float* pos_emb, void* d_out, int64_t ld_out,
+                     int out_bf16, void* stream);
+int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);
 
 #ifdef __cplusplus
 }

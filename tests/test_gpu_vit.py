@@ -1,0 +1,81 @@
+"""GPU numerics for the tensor-core path: GEMM / LayerNorm / attention vs plain PyTorch fp32, and
+the whole ViT-L/14 tower + heads vs the fp32 oracle (north_star: cosine >= 0.999, aesthetic +-0.01)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_bf16(shape, seed, scale=1.0):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 256, 128), (1000, 768, 1024), (257 * 8, 3072, 1024),
+                                   (2056, 1024, 4096), (129, 32, 640), (4096, 1024, 640)])
+def test_gemm_all_epilogues(m, n, k):
+    import torch
+    from facet_b200 import ops
+    a, b = _rand_bf16((m, k), 1), _rand_bf16((n, k), 2, scale=k ** -0.5)
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda")
+    ref = a.float() @ b.float().T
+    tol = dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(ops.gemm_bf16(a, b, ops.GEMM_F32), ref, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(ops.gemm_bf16(a, b, ops.GEMM_F32, bias=bias), ref + bias, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(ops.gemm_bf16(a, b, ops.GEMM_BIAS_BF16, bias=bias).float(), ref + bias, **tol)
+    torch.testing.assert_close(ops.gemm_bf16(a, b, ops.GEMM_BIAS_GELU_BF16, bias=bias).float(),
+                               torch.nn.functional.gelu(ref + bias), **tol)
+    out = res.clone()
+    ops.gemm_bf16(a, b, ops.GEMM_BIAS_RESIDUAL_F32, bias=bias, residual=out, out=out)   # in place
+    torch.testing.assert_close(out, ref + bias + res, rtol=1e-4, atol=1e-3)
+
+
+def test_layernorm_and_assembly():
+    import torch
+    from facet_b200 import ops
+    x = torch.randn(1000, 1024, device="cuda") * 3 + 0.5
+    g, b = torch.randn(1024, device="cuda"), torch.randn(1024, device="cuda")
+    ref = torch.nn.functional.layer_norm(x, (1024,), g, b, 1e-5)
+    torch.testing.assert_close(ops.vit_layernorm(x, g, b, out_bf16=False), ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ops.vit_layernorm(x, g, b, out_bf16=True).float(), ref, rtol=1e-2, atol=1e-2)
+    pe = torch.randn(3 * 256, 1024, device="cuda")
+    cls, pos = torch.randn(1024, device="cuda"), torch.randn(257, 1024, device="cuda")
+    tok = torch.cat([cls.expand(3, 1, 1024), pe.reshape(3, 256, 1024)], 1) + pos
+    ref = torch.nn.functional.layer_norm(tok, (1024,), g, b, 1e-5).reshape(-1, 1024)
+    got = ops.vit_layernorm(pe, g, b, out_bf16=False, class_emb=cls, pos_emb=pos, rows=3 * 257)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_attention_vs_torch():
+    import torch
+    from facet_b200 import ops
+    bsz = 3
+    qkv = _rand_bf16((bsz * 257, 3072), 5, scale=1.5)
+    got = ops.vit_attention(qkv, bsz).float().reshape(bsz, 257, 16, 64)
+    q, k, v = qkv.float().reshape(bsz, 257, 3, 16, 64).unbind(2)
+    att = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125, dim=-1)
+    ref = torch.einsum("bhqk,bkhd->bqhd", att, v)
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
+
+
+def test_vit_tower_vs_fp32_oracle():
+    import torch
+    from facet_b200.models.clip_vit import ClipVitL14, random_state_dict
+    from oracle import vit_torch
+    sd = random_state_dict(0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    tags = torch.nn.functional.normalize(torch.randn(240, 768, generator=torch.Generator().manual_seed(7)), dim=-1)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    ref = vit_torch.score_batch(sd_gpu, x.cuda(), tags.cuda())       # fp32 oracle (TF32 off by default)
+    model = ClipVitL14(sd, tag_embeddings=tags.numpy())
+    out = model.encode(x.cuda())
+    cos = torch.nn.functional.cosine_similarity(out["embedding"], ref["embedding"], dim=-1)
+    assert float(cos.min()) >= 0.999, cos
+    aest = ((out["aesthetic_raw"] + 1) * 5).clamp(0, 10)
+    assert float((aest - ref["aesthetic"]).abs().max()) <= 0.01, (aest, ref["aesthetic"])
+    assert float((out["tag_sims"] - ref["tag_sims"]).abs().max()) <= 5e-3
+    nrm = out["embedding"].norm(dim=-1)
+    torch.testing.assert_close(nrm, torch.ones_like(nrm), rtol=1e-5, atol=1e-5)
