@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the legacy per-image scoring pass (BASELINE.json metric: images/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of B synthetic 24 MP frames per GPU:
+technical metrics (csrc/tech_stats.cu) + CLIP preprocess (csrc/preprocess.cu) + ViT-L/14 tower,
+aesthetic head and tag similarities (csrc/gemm.cu, csrc/vit.cu) + the similarity stage on the
+step's embeddings (all-gather across ranks, cosine pairs, csrc/gemm.cu + csrc/similarity.cu).
+`value` is the whole-job rate with the frames already resident in HBM; `e2e` is the same pass
+through the host-buffer pipeline (pinned host frames, H2D and D2H inside the timed region).
+Prints ONE JSON line on rank 0.  `--impl reference` times the reference's CPU path (oracle port;
+/root/reference does not exist on the GPU box) on a bounded sample instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 4000, 6000
+GFLOP_PER_IMAGE = 162.0          # ViT-L/14 224 px incl. attention and patch embedding
+GEMM_GFLOP_PER_IMAGE = 24 * (1.617 + 0.539 + 4.312) + 0.308   # the part the tcgen05 GEMM kernel executes
+TECH_BYTES_PER_IMAGE = 3 * H * W
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="24 MP frames per GPU per step")
+    ap.add_argument("--impl", default="facet_b200", choices=["facet_b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (sustained bf16, copy HBM)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median of the upper half: samples taken while the GPU was busy
+        busy = sm[len(sm) // 2:] if sm else []
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pool(n, seed, device):
+    """n distinct device-resident 24 MP BGR frames (gradients + texture + noise; 1 in 8 pure noise, 1 in 8 flat)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
+    yy = torch.linspace(0, 1, H, device=device)[:, None, None]
+    xx = torch.linspace(0, 1, W, device=device)[None, :, None]
+    for i in range(n):
+        kind = i % 8
+        if kind == 6:
+            out[i] = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=device, generator=g)
+            continue
+        ph = torch.rand((1, 1, 3), device=device, generator=g) * 6.28
+        fr = 1 + 5 * torch.rand((1, 1, 3), device=device, generator=g)
+        base = 0.5 + 0.25 * torch.sin(fr * 6.28 * xx + ph) + 0.22 * torch.cos(fr * 4.1 * yy + 2 * ph)
+        if kind == 3:
+            base = torch.round(base * 5) / 5
+        gain = 0.6 + 0.5 * float(torch.rand(1, device=device, generator=g))
+        sigma = (0.0, 2.0, 4.0, 1.0, 6.0, 3.0, 0.0, 1.5)[kind]
+        noise = torch.randn((H, W, 3), device=device, generator=g) * sigma
+        out[i] = (base * 255 * gain + noise).clamp(0, 255).to(torch.uint8)
+        if kind == 0:
+            out[i, :, :, 0] = out[i, :, :, 1]
+            out[i, :, :, 2] = out[i, :, :, 1]
+    return out
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference's own CPU path (oracle port: cv2/NumPy/SciPy/PIL/torch-CPU calls in the
+    order of processing/batch_processor.py:198-233) timed on the host cores.  One 24 MP frame per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.synth import synth_embeddings, synth_image_bgr
+    from oracle import cpu_port, grouping
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = random_state_dict(0)
+    tags = torch.from_numpy(synth_embeddings(240, seed=7, cluster_fraction=0.0))
+    frames = [synth_image_bgr(2000 + i, H, W) for i in range(2)]
+    embs = []
+
+    def step(i):
+        _, vit = cpu_port.score_images_cpu([frames[i % len(frames)]], sd, tags)
+        embs.append(vit["embedding"].numpy())
+        e = np.concatenate(embs[-64:], axis=0)
+        grouping.cosine_pairs(e, 0.9)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, note="CPU arm: one 24 MP frame per step (bounded sample of the same workload)"),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 synthetic 24 MP frame, oracle/cpu_port.py (cv2+NumPy+PIL+torch fp32)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, note=None):
+    cfg = {"workload": "full legacy scoring pass on synthetic 6000x4000 (24 MP) BGR frames: technical metrics + CLIP "
+                       "preprocess + ViT-L/14 224px + MLP aesthetic + tag similarities + cosine duplicate pairs "
+                       "(BASELINE.json configs[4], per-GPU share)",
+           "image": [H, W, 3], "batch_per_gpu": batch, "parallelism": "data-parallel, one rank per GPU",
+           "l2": "inputs larger than L2 (pool of batch x 72 MB frames per step)", "weights": "random-init ViT-L/14 (seed 0)"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from facet_b200 import _lib, ops
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.processing.pipeline import ScoringPipeline
+    from facet_b200.processing.scorer import Facet
+    from facet_b200.synth import synth_embeddings
+    from facet_b200.utils.duplicate import all_gather_embeddings
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+
+    B = args.batch
+    tags = synth_embeddings(240, seed=7, cluster_fraction=0.0)
+    scorer = Facet(random_state_dict(0), text_embeddings=tags, tag_names=[f"tag{i // 4}" for i in range(240)], device=device)
+    pool = make_pool(B, seed=2000 + 17 * rank, device=device)
+    torch.cuda.synchronize()
+
+    def step():
+        out = scorer.score_images_device(pool)
+        emb = all_gather_embeddings(out["embedding"]) if world > 1 else out["embedding"]
+        pairs, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)
+        return out, pairs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: K steps, CUDA events on the launching stream -------------------------------------
+    launches0 = int(lib.fb_launch_count())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, pairs = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = int(lib.fb_launch_count()) - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- per-kernel device times of the same step (events around each stage, same stream) ---------------
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, r
+
+    ms_tech, _ = timed(lambda: ops.tech_stats_raw(pool))
+    ms_pre, clip_in = timed(lambda: ops.clip_preprocess(pool))
+    ms_vit, _ = timed(lambda: scorer.model.encode(clip_in))
+    stages = {"technical_ms": ms_tech, "preprocess_ms": ms_pre, "vit_ms": ms_vit,
+              "technical_gbs": B * TECH_BYTES_PER_IMAGE / (ms_tech * 1e-3) / 1e9,
+              "vit_tflops": B * GFLOP_PER_IMAGE * 1e9 / (ms_vit * 1e-3) / 1e12}
+    # the dominant kernel of the step: the tcgen05 GEMM (98 launches per ViT forward); timed per launch shape
+    M = B * 257
+    gemm_ms = 0.0
+    for (m, n, k, reps_in_fwd, mode) in [(B * 256, 1024, 640, 1, ops.GEMM_F32), (M, 3072, 1024, 24, ops.GEMM_BIAS_BF16),
+                                        (M, 1024, 1024, 24, ops.GEMM_BIAS_BF16), (M, 4096, 1024, 24, ops.GEMM_BIAS_GELU_BF16),
+                                        (M, 1024, 4096, 24, ops.GEMM_BIAS_BF16)]:
+        a = torch.randn(m, k, device=device).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=device) * k ** -0.5).to(torch.bfloat16)
+        bias = torch.zeros(n, device=device)
+        o = torch.empty((m, n), device=device, dtype=torch.float32 if mode == ops.GEMM_F32 else torch.bfloat16)
+        ms, _ = timed(lambda: ops.gemm_bf16(a, w, mode, bias=bias, out=o), reps=5)
+        gemm_ms += ms * reps_in_fwd
+        del a, w, o
+    peaks = measured_peaks()
+    gemm_tflops = B * GEMM_GFLOP_PER_IMAGE * 1e9 / (gemm_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, 97 launches per step)",
+                "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "share_of_step": gemm_ms / ms_step,
+                "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
+                                     "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"]}}
+
+    # ---- e2e: pinned host frames -> pipeline (H2D + kernels + D2H inside the timed region) ---------------
+    e2e = None
+    if not args.no_e2e:
+        pipe = ScoringPipeline(scorer, chunk=8)
+        host = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        host.copy_(pool)
+        torch.cuda.synchronize()
+        pipe.run_host(host)          # warm-up
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(2, min(args.steps, 5))
+        a.record()
+        for _ in range(n_e2e):
+            res = pipe.run_host(host)
+            emb = torch.from_numpy(res["embedding"]).to(device)
+            emb = all_gather_embeddings(emb) if world > 1 else emb
+            p_, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)
+            p_.cpu()
+        b.record()
+        barrier()
+        ms_e = a.elapsed_time(b) / n_e2e
+        if world > 1:
+            t = torch.tensor([ms_e], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * B / (ms_e * 1e-3), "unit": "images/s", "steps": n_e2e,
+               "h2d_bytes_per_step": pipe.h2d_bytes(B, H, W) + B * 768 * 4,
+               "d2h_bytes_per_step": pipe.d2h_bytes(B, 240) + int(p_.numel()) * 4}
+        del host
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -----------------
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_port
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = random_state_dict(0)
+        frames = [pool[i].cpu().numpy() for i in (1, 2, 4)]
+        cpu_port.score_images_cpu(frames[:1], sd, torch.from_numpy(tags))
+        t0 = time.perf_counter()
+        tech_cpu, vit_cpu = cpu_port.score_images_cpu(frames, sd, torch.from_numpy(tags))
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": len(frames) / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"{len(frames)} of the step's 24 MP frames through oracle/cpu_port.py "
+                                  "(cv2+NumPy+SciPy technical metrics, PIL preprocess, fp32 torch-CPU ViT-L/14)"}
+        # parity spot check on those frames (checker only)
+        got = scorer.score_images(np.stack(frames))
+        cosv = [float(np.dot(np.frombuffer(g["clip_embedding"], np.float32), vit_cpu["embedding"][i].numpy())) for i, g in enumerate(got)]
+        cpu_baseline["parity_spot_check"] = {
+            "hist_exact": all(g["histogram_data"] == t["histogram"]["histogram_bytes"] for g, t in zip(got, tech_cpu)),
+            "min_embedding_cosine": min(cosv)}
+
+    if rank == 0:
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(B),
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "stages": stages, "pairs_last_step": int(pairs.shape[0]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,31 @@ int fb_gemm_bf16(const void* d_a, int64_t lda, const void* d_b, int64_t ldb, int
     return rc;
 }
 
+int fb_f32_to_bf16(const float* d_in, void* d_out_bf16, int64_t n, void* stream) {
+    int rc = launch_f32_to_bf16(d_in, d_out_bf16, (long long)n, (cudaStream_t)stream);
+    if (rc == 0 && n > 0) count_launch(1);
+    return rc;
+}
+
+int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, int dim, float tau, float band,
+                    int64_t row_offset, int64_t rows, int32_t* d_cand, float* d_cand_sims, int64_t cand_cap,
+                    uint64_t* d_cand_count, int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count, void* stream) {
+    FB_REQUIRE(n >= 1 && n < (1ll << 31), "fb_cosine_pairs: n out of range");
+    FB_REQUIRE(d_cand_count && d_count, "fb_cosine_pairs: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    FB_CUDA_OK(cudaMemsetAsync(d_cand_count, 0, sizeof(uint64_t), st));
+    FB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (rows <= 0 || n < 2) return 0;
+    int rc = launch_cosine_candidates(d_emb_bf16, dim, (int)n, (int)row_offset, (int)rows, dim, tau - band, d_cand, d_cand_sims,
+                                      (long long)cand_cap, reinterpret_cast<unsigned long long*>(d_cand_count), st);
+    if (rc) return rc;
+    rc = launch_cosine_recheck(d_emb_f32, dim, dim, d_cand, reinterpret_cast<unsigned long long*>(d_cand_count),
+                               (long long)cand_cap, tau, d_pairs, d_sims, (long long)cap,
+                               reinterpret_cast<unsigned long long*>(d_count), st);
+    if (rc == 0) count_launch(2);
+    return rc;
+}
+
 size_t fb_vit_workspace_bytes(int batch) { return vit_workspace_bytes(batch); }
 
 int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void* d_workspace, size_t workspace_bytes,

@@ -41,6 +41,13 @@ struct GemmArgs {
     long long ldo;        // elements
     const float* residual;
     long long ldr;
+    // FB_GEMM_THRESHOLD_PAIRS: candidates (row_offset + row, col) with acc >= tau and col > row_offset + row
+    float tau;
+    int row_offset;
+    int* pairs;
+    float* pair_sims;
+    long long pair_cap;
+    unsigned long long* pair_count;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -62,6 +69,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int tiles_m = (p.M + BM - 1) / BM;
     const int num_tiles = tiles_m * tiles_n;
     const int kblocks = p.K / BK;
+    // similarity mode only needs tiles that contain an element with col > global row
+    const bool tri = (p.mode == FB_GEMM_THRESHOLD_PAIRS);
+#define FB_TILE_SKIPPED(m0_, n0_) (tri && ((n0_) + BN <= (m0_) + p.row_offset + 1))
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -92,6 +102,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                if (FB_TILE_SKIPPED(m0, n0)) continue;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kStageBytes;
@@ -109,7 +120,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                if (FB_TILE_SKIPPED((tile / tiles_n) * BM, (tile % tiles_n) * BN)) continue;
                 const int acc = iter & 1;
                 tc::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
@@ -129,6 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(&tmem_full[acc]);            // accumulator complete
+                ++iter;
             }
         }
     } else {
@@ -137,9 +150,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
         const int half = ew >> 2;              // which 128 of the 256 accumulator columns
         int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-            const int acc = iter & 1;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            if (FB_TILE_SKIPPED(m0, n0)) continue;
+            const int acc = iter & 1;
             tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc::tc_fence_after();
             const int row = m0 + quarter * 32 + lane;
@@ -150,7 +164,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint32_t v[32];
                 tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128 + c * 32, v);
                 tc::tmem_ld_wait();
-                if (col0 < p.N) {
+                if (p.mode == FB_GEMM_THRESHOLD_PAIRS) {
+                    const int grow = p.row_offset + row;
+                    if (row_ok && col0 + 31 > grow) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float sim = __uint_as_float(v[j]);
+                            const int col = col0 + j;
+                            if (sim >= p.tau && col > grow && col < p.N) {
+                                const unsigned long long pos = atomicAdd(p.pair_count, 1ull);
+                                if ((long long)pos < p.pair_cap) {
+                                    p.pairs[2 * pos] = grow;
+                                    p.pairs[2 * pos + 1] = col;
+                                    p.pair_sims[pos] = sim;
+                                }
+                            }
+                        }
+                    }
+                } else if (col0 < p.N) {
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -192,6 +223,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+            ++iter;
         }
     }
     tc::tc_fence_before();
@@ -237,6 +269,38 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return 0;
 }
 
+static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, long long ldb, GemmArgs p, cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d(&ta, d_a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, BM, BK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb, BN, BK);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Candidate pairs of the cosine similarity stage: rows [row_offset, row_offset+m) of E against all n rows.
+int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int row_offset, int m, int k, float tau,
+                             int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count,
+                             cudaStream_t stream) {
+    FB_REQUIRE(d_emb_bf16 && d_pairs && d_sims && d_count, "fb_cosine_pairs: null pointer");
+    FB_REQUIRE(n >= 1 && m >= 1 && row_offset >= 0 && row_offset + m <= n, "fb_cosine_pairs: bad row range");
+    FB_REQUIRE(k >= BK && k % BK == 0, "fb_cosine_pairs: embedding dim must be a multiple of %d", BK);
+    GemmArgs p{};
+    p.M = m; p.N = n; p.K = k; p.mode = FB_GEMM_THRESHOLD_PAIRS;
+    p.tau = tau; p.row_offset = row_offset; p.pairs = d_pairs; p.pair_sims = d_sims; p.pair_cap = cap; p.pair_count = d_count;
+    const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d_emb_bf16) + (size_t)row_offset * ld;
+    return launch_gemm_common(a, ld, d_emb_bf16, ld, p, stream);
+}
+
 int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
                      const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
                      cudaStream_t stream) {
@@ -249,24 +313,10 @@ int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long 
     FB_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (ldo * out_elt) % 16 == 0, "fb_gemm_bf16: output not 16-byte aligned");
     FB_REQUIRE(!d_bias || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "fb_gemm_bf16: bias not 16-byte aligned");
     FB_REQUIRE(!d_residual || ((reinterpret_cast<uintptr_t>(d_residual) & 15) == 0 && (ldr * 4) % 16 == 0), "fb_gemm_bf16: residual not aligned");
-    CUtensorMap ta, tb;
-    int rc = make_tmap_bf16_2d(&ta, d_a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
-    if (rc) return rc;
-    GemmArgs p;
+    GemmArgs p{};
     p.M = M; p.N = N; p.K = K; p.mode = mode; p.bias = d_bias; p.out = d_out; p.ldo = ldo;
     p.residual = d_residual; p.ldr = ldr;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
-    }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
-    FB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_gemm_common(d_a, lda, d_b, ldb, p, stream);
 }
 
 }  // namespace fb

@@ -7,6 +7,7 @@
 #define FB_GEMM_BIAS_GELU_BF16 1
 #define FB_GEMM_BIAS_RESIDUAL_F32 2
 #define FB_GEMM_F32 3
+#define FB_GEMM_THRESHOLD_PAIRS 4
 
 namespace fb {
 
@@ -36,6 +37,13 @@ int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, co
 int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
                      const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
                      cudaStream_t stream);
+int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int row_offset, int m, int k, float tau,
+                             int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count,
+                             cudaStream_t stream);
+int launch_cosine_recheck(const float* d_emb_f32, long long ld, int k, const int* d_cand, const unsigned long long* d_ncand,
+                          long long cand_cap, float tau, int* d_pairs, float* d_sims, long long cap,
+                          unsigned long long* d_count, cudaStream_t stream);
+int launch_f32_to_bf16(const float* d_in, void* d_out, long long n, cudaStream_t stream);
 int launch_im2col_patch14(const float* d_x, int batch, void* d_out, cudaStream_t stream);
 int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
                      const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,

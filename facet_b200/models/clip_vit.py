@@ -28,6 +28,9 @@ def random_state_dict(seed: int = 0, layers: int = LAYERS, dtype=None):
     """Random-init visual tower + aesthetic head with open_clip's init scales (CPU float32).
 
     Biases get a small random value (open_clip zero-inits them) so the bias paths are exercised.
+    The five GEMM weight families (conv1, in_proj, out_proj, c_fc, c_proj) are drawn and then
+    rounded to bf16-representable values: the tower stores them in bf16, so the oracle and the
+    CUDA path hold bit-identical weights and the comparison measures arithmetic, not storage.
     """
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -35,9 +38,12 @@ def random_state_dict(seed: int = 0, layers: int = LAYERS, dtype=None):
     def rn(*shape, std=1.0):
         return torch.randn(*shape, generator=g, dtype=torch.float32) * std
 
+    def rw(*shape, std=1.0):
+        return rn(*shape, std=std).to(torch.bfloat16).to(torch.float32)
+
     sd = {}
     scale = WIDTH ** -0.5
-    sd["conv1.weight"] = rn(WIDTH, 3, 14, 14, std=(3 * 14 * 14) ** -0.5)
+    sd["conv1.weight"] = rw(WIDTH, 3, 14, 14, std=(3 * 14 * 14) ** -0.5)
     sd["class_embedding"] = rn(WIDTH, std=scale)
     sd["positional_embedding"] = rn(TOKENS, WIDTH, std=scale)
     for name in ("ln_pre", "ln_post"):
@@ -52,13 +58,13 @@ def random_state_dict(seed: int = 0, layers: int = LAYERS, dtype=None):
         sd[p + "ln_1.bias"] = rn(WIDTH, std=0.02)
         sd[p + "ln_2.weight"] = 1.0 + rn(WIDTH, std=0.02)
         sd[p + "ln_2.bias"] = rn(WIDTH, std=0.02)
-        sd[p + "attn.in_proj_weight"] = rn(3 * WIDTH, WIDTH, std=attn_std)
+        sd[p + "attn.in_proj_weight"] = rw(3 * WIDTH, WIDTH, std=attn_std)
         sd[p + "attn.in_proj_bias"] = rn(3 * WIDTH, std=0.02)
-        sd[p + "attn.out_proj.weight"] = rn(WIDTH, WIDTH, std=proj_std)
+        sd[p + "attn.out_proj.weight"] = rw(WIDTH, WIDTH, std=proj_std)
         sd[p + "attn.out_proj.bias"] = rn(WIDTH, std=0.02)
-        sd[p + "mlp.c_fc.weight"] = rn(MLP, WIDTH, std=fc_std)
+        sd[p + "mlp.c_fc.weight"] = rw(MLP, WIDTH, std=fc_std)
         sd[p + "mlp.c_fc.bias"] = rn(MLP, std=0.02)
-        sd[p + "mlp.c_proj.weight"] = rn(WIDTH, MLP, std=proj_std)
+        sd[p + "mlp.c_proj.weight"] = rw(WIDTH, MLP, std=proj_std)
         sd[p + "mlp.c_proj.bias"] = rn(WIDTH, std=0.02)
     sd["proj"] = rn(WIDTH, OUT_DIM, std=scale)
     # aesthetic head: Sequential(Linear(768,256), ReLU, Linear(256,1)) left at its random init in the

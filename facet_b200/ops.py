@@ -271,3 +271,38 @@ def vit_attention(qkv, batch: int):
     with torch.cuda.device(qkv.device):
         _lib.check(lib.fb_vit_attention(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
     return out
+
+
+def balanced_row_blocks(n: int, parts: int):
+    """Row boundaries that give every part the same number of upper-triangle (i<j) pairs."""
+    bounds = [int(round(n * (1.0 - (1.0 - k / parts) ** 0.5))) for k in range(parts + 1)]
+    bounds[0], bounds[-1] = 0, n
+    return bounds
+
+
+def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: float = 0.01, cap: int | None = None):
+    """All (i<j) pairs of this part's row block with float32 <e_i,e_j> >= tau.
+    emb_f32: CUDA float32 [n,d] (L2-normalised, d % 64 == 0).  Returns (pairs int32 [m,2], sims float32 [m])."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    e = emb_f32.contiguous()
+    n, d = e.shape
+    bounds = balanced_row_blocks(n, nparts)
+    r0, r1 = bounds[part], bounds[part + 1]
+    with torch.cuda.device(e.device):
+        eb = torch.empty((n, d), dtype=torch.bfloat16, device=e.device)
+        _lib.check(lib.fb_f32_to_bf16(_ptr(e), _ptr(eb), n * d, _lib.stream_ptr()), "fb_f32_to_bf16")
+        cap = int(cap if cap is not None else max(1 << 16, 8 * n))
+        counts = torch.zeros(2, dtype=torch.int64, device=e.device)
+        while True:
+            cand = torch.empty((cap, 2), dtype=torch.int32, device=e.device)
+            cand_s = torch.empty((cap,), dtype=torch.float32, device=e.device)
+            pairs = torch.empty((cap, 2), dtype=torch.int32, device=e.device)
+            sims = torch.empty((cap,), dtype=torch.float32, device=e.device)
+            _lib.check(lib.fb_cosine_pairs(_ptr(e), _ptr(eb), n, d, float(tau), float(band), r0, r1 - r0, _ptr(cand),
+                                           _ptr(cand_s), cap, C.c_void_p(counts.data_ptr()), _ptr(pairs), _ptr(sims), cap,
+                                           C.c_void_p(counts.data_ptr() + 8), _lib.stream_ptr()), "fb_cosine_pairs")
+            nc, m = (int(x) for x in counts.tolist())
+            if nc <= cap and m <= cap:
+                return pairs[:m], sims[:m]
+            cap = max(nc, m)

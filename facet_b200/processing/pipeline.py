@@ -1,0 +1,67 @@
+"""Data-parallel driver of the per-image pass (the role of `BatchProcessor`,
+processing/batch_processor.py:27-658, for device-side work).
+
+One process per GPU.  `ScoringPipeline.run_host` takes batches of same-shaped frames that live in
+(pinned) host memory, streams them to the device in chunks on a copy stream while the previous
+chunk is being scored on the compute stream, and reads back only the small per-image results.
+Images are independent, so ranks never communicate here; the similarity stage
+(utils/duplicate.py, processing/bursts.py) is the only place with a collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib, ops
+
+
+class ScoringPipeline:
+    def __init__(self, scorer, chunk: int = 8):
+        torch = _lib.require_cuda()
+        self.scorer = scorer
+        self.chunk = int(chunk)
+        self.device = scorer.device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._bufs = None
+
+    def _buffers(self, h, w):
+        torch = _lib.require_cuda()
+        shape = (self.chunk, h, w, 3)
+        if self._bufs is None or tuple(self._bufs[0].shape) != shape:
+            self._bufs = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+        return self._bufs
+
+    def run_host(self, host_batch, rgb_order=False):
+        """host_batch: CPU uint8 tensor [n,H,W,3] (pinned for full PCIe rate).  Returns a dict of
+        host numpy arrays: hist256 [n,256], sums [n,4], derived [n,4], embedding [n,768],
+        aesthetic_raw [n], tag_sims [n,T] (or None).  H2D and D2H happen inside this call."""
+        torch = _lib.require_cuda()
+        n, h, w, _ = host_batch.shape
+        bufs = self._buffers(h, w)
+        compute = torch.cuda.current_stream(self.device)
+        outs = []
+        for ci, start in enumerate(range(0, n, self.chunk)):
+            k = min(self.chunk, n - start)
+            slot = ci & 1
+            with torch.cuda.stream(self.copy_stream):
+                if ci >= 2:
+                    self.copy_stream.wait_event(self._free[slot])     # compute finished with this buffer
+                bufs[slot][:k].copy_(host_batch[start:start + k], non_blocking=True)
+                self._ready[slot].record(self.copy_stream)
+            compute.wait_event(self._ready[slot])
+            dev = self.scorer.score_images_device(bufs[slot][:k], rgb_order=rgb_order)
+            self._free[slot].record(compute)
+            outs.append(dev)
+        cat = lambda key: torch.cat([o[key] for o in outs]).cpu().numpy() if outs[0][key] is not None else None
+        res = {key: cat(key) for key in ("hist256", "sums", "derived", "embedding", "aesthetic_raw", "tag_sims")}
+        res["hist256"] = res["hist256"].view(np.uint32)
+        return res
+
+    @staticmethod
+    def h2d_bytes(n, h, w):
+        return int(n) * h * w * 3
+
+    @staticmethod
+    def d2h_bytes(n, n_tags):
+        return int(n) * (256 * 4 + 4 * 8 + 4 * 8 + 768 * 4 + 4 + n_tags * 4)

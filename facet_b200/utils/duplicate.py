@@ -147,3 +147,34 @@ def detect_duplicates(db_path, config_path=None):
                              [(int(gid[k]), int(lead[k]), paths[k]) for k in sel.tolist()])
             print(f"Marked {int(gid.max())} groups: {len(sel)} photos")
         conn.commit()
+
+
+# ---------------------------------------------------------------------------------------------
+# Cosine mode over CLIP embeddings (north_star kernel 3; formula sites models/tagger.py:99-101,
+# api/routers/gallery.py:465-471).  Ranks hold disjoint shards of the [N,768] embedding matrix;
+# one NCCL all-gather makes the matrix resident everywhere, then every rank scans its balanced
+# row block against all columns and the surviving pair lists are gathered (SURVEY.md §8e).
+# ---------------------------------------------------------------------------------------------
+
+def all_gather_embeddings(local_emb, group=None):
+    """[n_local,d] float32 shards (equal n_local on every rank) -> [world*n_local, d] on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_emb
+    world = dist.get_world_size(group)
+    out = torch.empty((world * local_emb.shape[0], local_emb.shape[1]), dtype=local_emb.dtype, device=local_emb.device)
+    dist.all_gather_into_tensor(out, local_emb.contiguous(), group=group)
+    return out
+
+
+def find_similar_groups(local_emb, aggregates, tau: float, group=None):
+    """Cosine-threshold grouping: returns (group_id, is_lead) for the gathered rows on every rank."""
+    import torch.distributed as dist
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    emb = all_gather_embeddings(local_emb, group)
+    local_pairs, _ = ops.cosine_pairs(emb, tau, part=rank, nparts=world)
+    pairs = gather_pairs(local_pairs, group)
+    return group_duplicates(emb.shape[0], pairs, aggregates)

@@ -123,6 +123,19 @@ int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint
                    int32_t* d_last_slow, int32_t* d_rapid_pairs, int64_t rapid_cap,
                    uint64_t* d_rapid_count, void* stream);
 
+/* Cosine mode of the similarity stage (north_star kernel 3): all pairs (i<j), i in
+ * [row_offset, row_offset+rows), with <e_i, e_j> >= tau on the stored L2-normalised float32
+ * embeddings (formula sites models/tagger.py:99-101, api/routers/gallery.py:465-471; grouping as
+ * utils/duplicate.py).  The N x N product runs as a bf16 tcgen05 GEMM whose epilogue emits
+ * candidates with sim >= tau - band into d_cand; they are then re-scored in fp32 from d_emb_f32
+ * and the survivors written to d_pairs [(i,j)] / d_sims.  Counts above the capacities mean the
+ * lists were truncated (caller retries with larger buffers).  band >= 2^-8 is loss-free. */
+int fb_f32_to_bf16(const float* d_in, void* d_out_bf16, int64_t n, void* stream);
+int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, int dim, float tau, float band,
+                    int64_t row_offset, int64_t rows, int32_t* d_cand, float* d_cand_sims, int64_t cand_cap,
+                    uint64_t* d_cand_count, int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count,
+                    void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * CLIP ViT-L/14 image tower + heads — replaces `self.model.encode_image(inputs)`,
  * `F.normalize(features)`, `self.aesthetic_head(features.float())`

@@ -1,0 +1,52 @@
+"""GPU parity for the cosine similarity stage: tcgen05 GEMM + threshold epilogue + fp32 re-score."""
+import numpy as np
+import pytest
+
+from facet_b200.synth import synth_embeddings
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [2, 130, 1000, 5000, 12000])
+def test_cosine_pair_set_matches_oracle(n):
+    import torch
+    from facet_b200 import ops
+    from oracle import grouping as og
+    e = synth_embeddings(n, seed=n, cluster_fraction=0.3)
+    et = torch.from_numpy(e).cuda()
+    for tau in (0.90, 0.97):
+        want = og.cosine_pairs(e, tau)
+        pairs, sims = ops.cosine_pairs(et, tau)
+        got = pairs.cpu().numpy().astype(np.int64)
+        got = got[np.lexsort((got[:, 1], got[:, 0]))] if len(got) else got.reshape(0, 2)
+        # pairs whose fp32 similarity sits within 2e-6 of tau may legitimately flip with summation order
+        full = e @ e.T
+        def strict(p, margin):
+            return {tuple(x) for x in p.tolist() if abs(float(full[x[0], x[1]]) - tau) > margin}
+        assert strict(got, 2e-6) == strict(want, 2e-6)
+        if len(got):
+            ref = np.einsum("ij,ij->i", e[got[:, 0]], e[got[:, 1]])
+            srt = sims.cpu().numpy()[np.lexsort((pairs.cpu().numpy()[:, 1], pairs.cpu().numpy()[:, 0]))]
+            np.testing.assert_allclose(srt, ref, rtol=0, atol=2e-6)
+
+
+def test_cosine_parts_and_grouping():
+    import torch
+    from facet_b200 import ops
+    from facet_b200.utils.duplicate import group_duplicates
+    from oracle import grouping as og
+    n = 6000
+    e = synth_embeddings(n, seed=3, cluster_fraction=0.4)
+    et = torch.from_numpy(e).cuda()
+    full = {tuple(p) for p in ops.cosine_pairs(et, 0.9)[0].cpu().numpy().tolist()}
+    for nparts in (2, 8):
+        sets = [{tuple(p) for p in ops.cosine_pairs(et, 0.9, part=r, nparts=nparts)[0].cpu().numpy().tolist()} for r in range(nparts)]
+        assert sum(len(s) for s in sets) == len(full)
+        assert set().union(*sets) == full
+    aggs = np.random.default_rng(0).uniform(0, 10, n).round(2).tolist()
+    gid, lead = group_duplicates(n, np.array(sorted(full), dtype=np.int64), aggs)
+    wg, wl = og.cosine_groups(e, aggs, 0.9)
+    assert gid.tolist() == wg.tolist() and lead.tolist() == wl.tolist()
+    # truncated candidate buffer -> retried
+    small = {tuple(p) for p in ops.cosine_pairs(et, 0.9, cap=5)[0].cpu().numpy().tolist()}
+    assert small == full
