@@ -27,8 +27,8 @@ int launch_burst_links(const unsigned long long* d_hashes, const long long* d_ti
                        int* d_last_slow, int* d_rapid_pairs, long long rapid_cap,
                        unsigned long long* d_rapid_count, cudaStream_t stream);
 int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
-                           int out_size, const int* d_hbounds, const int* d_hcoef, int hk, int h_byte_lo,
-                           int h_byte_hi, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
+                           int out_size, const int* d_hp0, const int* d_hcpad, int hgroups, int h_px_lo,
+                           int h_span_px, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
                            const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
                            cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,

@@ -21,40 +21,72 @@ __device__ __forceinline__ int clip8(int v) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// One CTA = kRowsPerBlock input rows of one image; thread = output column.
-constexpr int kRowsPerBlock = 8;
+// Horizontal pass.  One CTA = kRowsPerBlock input rows of one image, staged in shared memory with
+// 16-byte loads; thread = output column, accumulating all staged rows at once so every coefficient is
+// fetched once per kRowsPerBlock rows.  Taps are re-based per column to a multiple of 4 pixels
+// (12 bytes = 3 aligned words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3); the host pads the
+// coefficient table with zeros accordingly (facet_b200/utils/resample.py, ResamplePlan.hcpad).
+constexpr int kRowsPerBlock = 4;
 
 __global__ void __launch_bounds__(256) resample_h_kernel(
-    const uint8_t* __restrict__ img, long long img_stride, int H, int W, int out, const int* __restrict__ bounds,
-    const int* __restrict__ coef, int ksize, int row0, int rows, int byte_lo, int byte_hi,
+    const uint8_t* __restrict__ img, long long img_stride, int H, int W, int out, const int* __restrict__ p0tab,
+    const int* __restrict__ cpad, int ngroups, int row0, int rows, int px_lo, int span_px,
     uint8_t* __restrict__ tmp) {
-    extern __shared__ __align__(16) uint8_t s_row[];
+    extern __shared__ __align__(16) uint8_t s_rows[];     // [kRowsPerBlock][span_bytes], span_bytes % 48 == 0
     const int n_img = blockIdx.y;
     const uint8_t* base = img + (size_t)n_img * img_stride;
     uint8_t* tbase = tmp + (size_t)n_img * rows * out * 3;
-    const int span = byte_hi - byte_lo;
+    const int span_bytes = span_px * 3;
+    const int r_first = blockIdx.x * kRowsPerBlock;
+    const size_t row_bytes = (size_t)W * 3;
+    const int valid_bytes = min(span_bytes, (W - px_lo) * 3);      // bytes of the span that exist in the row
+    const bool vec_ok = ((row_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
     for (int rr = 0; rr < kRowsPerBlock; ++rr) {
-        const int r = blockIdx.x * kRowsPerBlock + rr;
-        if (r >= rows) break;
-        const uint8_t* src = base + (size_t)(row0 + r) * W * 3 + byte_lo;
-        __syncthreads();
-        for (int i = threadIdx.x; i < span; i += blockDim.x) s_row[i] = __ldg(src + i);
-        __syncthreads();
-        for (int xo = threadIdx.x; xo < out; xo += blockDim.x) {
-            const int first = bounds[2 * xo], cnt = bounds[2 * xo + 1];
-            const int* k = coef + (size_t)xo * ksize;
-            const uint8_t* p = s_row + first * 3 - byte_lo;
-            int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-            for (int x = 0; x < cnt; ++x) {
-                const int kv = __ldg(k + x);
-                a0 += (int)p[3 * x] * kv;
-                a1 += (int)p[3 * x + 1] * kv;
-                a2 += (int)p[3 * x + 2] * kv;
+        const int r = min(r_first + rr, rows - 1);
+        const uint8_t* src = base + (size_t)(row0 + r) * row_bytes + (size_t)px_lo * 3;
+        uint8_t* dst = s_rows + (size_t)rr * span_bytes;
+        if (vec_ok) {
+            for (int i = threadIdx.x * 16; i < span_bytes; i += blockDim.x * 16) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (i + 16 <= valid_bytes) v = __ldg(reinterpret_cast<const uint4*>(src + i));
+                else {
+                    uint8_t t[16];
+                    for (int b = 0; b < 16; ++b) t[b] = (i + b < valid_bytes) ? __ldg(src + i + b) : (uint8_t)0;
+                    v = *reinterpret_cast<uint4*>(t);
+                }
+                *reinterpret_cast<uint4*>(dst + i) = v;
             }
-            uint8_t* o = tbase + ((size_t)r * out + xo) * 3;
-            o[0] = (uint8_t)clip8(a0);
-            o[1] = (uint8_t)clip8(a1);
-            o[2] = (uint8_t)clip8(a2);
+        } else {
+            for (int i = threadIdx.x; i < span_bytes; i += blockDim.x) dst[i] = (i < valid_bytes) ? __ldg(src + i) : (uint8_t)0;
+        }
+    }
+    __syncthreads();
+    for (int xo = threadIdx.x; xo < out; xo += blockDim.x) {
+        const int word0 = ((p0tab[xo] - px_lo) * 3) >> 2;
+        int acc[kRowsPerBlock][3];
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerBlock; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 1 << (kPrecisionBits - 1);
+        for (int g = 0; g < ngroups; ++g) {
+            const int c0 = __ldg(cpad + (size_t)(4 * g) * out + xo), c1 = __ldg(cpad + (size_t)(4 * g + 1) * out + xo);
+            const int c2 = __ldg(cpad + (size_t)(4 * g + 2) * out + xo), c3 = __ldg(cpad + (size_t)(4 * g + 3) * out + xo);
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerBlock; ++rr) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_rows + (size_t)rr * span_bytes) + word0 + 3 * g;
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                acc[rr][0] += (int)(w0 & 255) * c0 + (int)(w0 >> 24) * c1 + (int)((w1 >> 16) & 255) * c2 + (int)((w2 >> 8) & 255) * c3;
+                acc[rr][1] += (int)((w0 >> 8) & 255) * c0 + (int)(w1 & 255) * c1 + (int)(w1 >> 24) * c2 + (int)((w2 >> 16) & 255) * c3;
+                acc[rr][2] += (int)((w0 >> 16) & 255) * c0 + (int)((w1 >> 8) & 255) * c1 + (int)(w2 & 255) * c2 + (int)(w2 >> 24) * c3;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerBlock; ++rr) {
+            const int r = r_first + rr;
+            if (r < rows) {
+                uint8_t* o = tbase + ((size_t)r * out + xo) * 3;
+                o[0] = (uint8_t)clip8(acc[rr][0]);
+                o[1] = (uint8_t)clip8(acc[rr][1]);
+                o[2] = (uint8_t)clip8(acc[rr][2]);
+            }
         }
     }
 }
@@ -134,21 +166,26 @@ __global__ void __launch_bounds__(256) roi_laplacian_kernel(const uint8_t* __res
 }  // namespace
 
 int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
-                           int out_size, const int* d_hbounds, const int* d_hcoef, int hk, int h_byte_lo,
-                           int h_byte_hi, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
+                           int out_size, const int* d_hp0, const int* d_hcpad, int hgroups, int h_px_lo,
+                           int h_span_px, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
                            const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
                            cudaStream_t stream) {
-    FB_REQUIRE(d_images && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_out && mean3 && std3,
+    FB_REQUIRE(d_images && d_hp0 && d_hcpad && d_vbounds && d_vcoef && d_tmp && d_out && mean3 && std3,
                "fb_clip_preprocess: null pointer");
     FB_REQUIRE(n >= 1 && out_size >= 1 && out_size <= 1024, "fb_clip_preprocess: bad n/out_size");
     FB_REQUIRE(row0 >= 0 && rows >= 1 && row0 + rows <= H, "fb_clip_preprocess: row range outside the image");
-    FB_REQUIRE(h_byte_lo >= 0 && h_byte_hi <= W * 3 && h_byte_lo < h_byte_hi, "fb_clip_preprocess: byte range outside the row");
-    const int span = h_byte_hi - h_byte_lo;
-    FB_REQUIRE(span <= 200 * 1024, "fb_clip_preprocess: row span %d B exceeds shared memory staging", span);
-    FB_CUDA_OK(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FB_REQUIRE(h_px_lo >= 0 && h_px_lo % 16 == 0 && h_span_px % 16 == 0 && h_px_lo < W && hgroups >= 1,
+               "fb_clip_preprocess: horizontal span must start and end on multiples of 16 pixels");
+    const size_t smem = (size_t)kRowsPerBlock * h_span_px * 3;
+    FB_REQUIRE(smem <= 200 * 1024, "fb_clip_preprocess: row span %d px exceeds shared memory staging", h_span_px);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB_CUDA_OK(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
     dim3 gh((rows + kRowsPerBlock - 1) / kRowsPerBlock, n);
-    resample_h_kernel<<<gh, 256, span, stream>>>(d_images, image_stride, H, W, out_size, d_hbounds, d_hcoef, hk,
-                                                row0, rows, h_byte_lo, h_byte_hi, d_tmp);
+    resample_h_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, out_size, d_hp0, d_hcpad, hgroups, row0, rows,
+                                                 h_px_lo, h_span_px, d_tmp);
     FB_CUDA_OK(cudaGetLastError());
     dim3 gv(out_size, n);
     int threads = out_size * 3;

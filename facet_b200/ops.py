@@ -194,7 +194,7 @@ def _device_plan(height: int, width: int, out: int, device):
     key = (height, width, out, str(device))
     if key not in _PLAN_CACHE:
         p = rs.plan(height, width, out)
-        dev = {name: torch.from_numpy(getattr(p, name)).to(device) for name in ("hbounds", "hcoef", "vbounds", "vcoef")}
+        dev = {name: torch.from_numpy(getattr(p, name)).to(device) for name in ("hp0", "hcpad", "vbounds", "vcoef")}
         _PLAN_CACHE[key] = (p, dev)
     return _PLAN_CACHE[key]
 
@@ -216,7 +216,7 @@ def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5,
     s = (C.c_float * 3)(*[float(v) for v in std])
     with torch.cuda.device(t.device):
         _lib.check(lib.fb_clip_preprocess(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), out_size,
-                                          _ptr(dev["hbounds"]), _ptr(dev["hcoef"]), p.hk, p.h_byte_lo, p.h_byte_hi,
+                                          _ptr(dev["hp0"]), _ptr(dev["hcpad"]), p.hgroups, p.h_px_lo, p.h_span_px,
                                           _ptr(dev["vbounds"]), _ptr(dev["vcoef"]), p.vk, p.row0, p.rows,
                                           C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), _ptr(tmp), _ptr(out),
                                           _lib.stream_ptr()), "fb_clip_preprocess")

@@ -83,8 +83,11 @@ class ResamplePlan:
     hbounds: np.ndarray
     hcoef: np.ndarray
     hk: int
-    h_byte_lo: int
-    h_byte_hi: int
+    hp0: np.ndarray        # int32 [out]: first tap of each column rounded down to a multiple of 4 pixels
+    hcpad: np.ndarray      # int32 [4*hgroups, out]: coefficient of pixel hp0[xo]+i, zero padded
+    hgroups: int
+    h_px_lo: int           # staged pixel range of a row (multiples of 16)
+    h_span_px: int
     vbounds: np.ndarray
     vcoef: np.ndarray
     vk: int
@@ -104,13 +107,21 @@ def plan(height: int, width: int, out: int = 224) -> ResamplePlan:
     vb, vc, vk = precompute_coeffs(height, new_h)
     hb, hc = hb[left:left + out].copy(), hc[left:left + out].copy()
     vb, vc = vb[top:top + out].copy(), vc[top:top + out].copy()
-    x_lo = int(hb[:, 0].min())
-    x_hi = int((hb[:, 0] + hb[:, 1]).max())
     row0 = int(vb[:, 0].min())
     row1 = int((vb[:, 0] + vb[:, 1]).max())
+    # horizontal taps re-based to 4-pixel (12-byte, word-aligned) groups for the kernel
+    hp0 = (hb[:, 0] & ~3).astype(np.int32)
+    hgroups = int(np.max((hb[:, 0] + hb[:, 1] - hp0 + 3) // 4))
+    hcpad = np.zeros((4 * hgroups, out), np.int32)
+    for xo in range(out):
+        off = int(hb[xo, 0] - hp0[xo])
+        cnt = int(hb[xo, 1])
+        hcpad[off:off + cnt, xo] = hc[xo, :cnt]
+    px_lo = int(hp0.min()) // 16 * 16
+    px_hi = -(-int((hp0 + 4 * hgroups).max()) // 16) * 16
     return ResamplePlan(height, width, out, np.ascontiguousarray(hb), np.ascontiguousarray(hc), hk,
-                        x_lo * 3, x_hi * 3, np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk,
-                        row0, row1 - row0)
+                        np.ascontiguousarray(hp0), np.ascontiguousarray(hcpad), hgroups, px_lo, px_hi - px_lo,
+                        np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk, row0, row1 - row0)
 
 
 def resample_reference_numpy(img_rgb: np.ndarray, out: int = 224) -> np.ndarray:

@@ -79,18 +79,19 @@ int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_orde
  *
  * The caller supplies the coefficient tables (facet_b200/utils/resample.py computes them the
  * way Pillow's precompute_coeffs/normalize_coeffs_8bpc do):
- *   d_hbounds [out][2] int32 (first tap, tap count), d_hcoef [out][hk] int32   horizontal
- *   d_vbounds / d_vcoef likewise for the vertical pass
- *   h_byte_lo/h_byte_hi  byte range of an input row the horizontal taps touch
- *   row0/rows            input rows the vertical taps touch (the only rows pass 1 produces)
+ *   horizontal pass, per output column xo: d_hp0[xo] = first tap rounded down to a multiple of 4
+ *   pixels, d_hcpad[4*hgroups][out] = coefficient of pixel d_hp0[xo]+i at [i][xo] (zero padded);
+ *   h_px_lo (multiple of 16) / h_span_px (multiple of 16) = pixel range of a row that is staged
+ *   vertical pass: d_vbounds [out][2] int32 (first tap, tap count), d_vcoef [out][vk] int32
+ *   row0/rows = input rows the vertical taps touch (the only rows pass 1 produces)
  * d_tmp      scratch [n][rows][out][3] uint8 (horizontal pass output)
  * d_out      [n][3][out][out] float32, planes R,G,B, (x/255 - mean[c]) / std[c]
  * mean3/std3 are HOST pointers to 3 floats each.
  */
 int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
                        int rgb_order, int out_size,
-                       const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
-                       int h_byte_lo, int h_byte_hi,
+                       const int32_t* d_hp0, const int32_t* d_hcpad, int hgroups,
+                       int h_px_lo, int h_span_px,
                        const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
                        int row0, int rows,
                        const float* mean3, const float* std3,
