@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(256) resample_h_kernel(
     }
 }
 
-// One CTA = one output row of one image; thread = (column, channel) byte of the row.
-__global__ void __launch_bounds__(1024) resample_v_kernel(
+// Vertical pass.  One CTA = one output row of one image; thread = 4 consecutive (column, channel)
+// bytes of the row (32-bit loads of the uint8 intermediate), then ToTensor + Normalize in float32.
+__global__ void __launch_bounds__(256) resample_v_kernel(
     const uint8_t* __restrict__ tmp, int rows, int row0, int out, const int* __restrict__ bounds,
     const int* __restrict__ coef, int ksize, int rgb_order, float m0, float m1, float m2, float s0, float s1,
     float s2, float* __restrict__ dst) {
@@ -102,16 +103,41 @@ __global__ void __launch_bounds__(1024) resample_v_kernel(
     const int first = bounds[2 * yo] - row0, cnt = bounds[2 * yo + 1];
     const int* k = coef + (size_t)yo * ksize;
     const int rowb = out * 3;
-    for (int i = threadIdx.x; i < rowb; i += blockDim.x) {
-        int acc = 1 << (kPrecisionBits - 1);
-        for (int y = 0; y < cnt; ++y) acc += (int)tbase[(size_t)(first + y) * rowb + i] * __ldg(k + y);
-        const int u = clip8(acc);
-        const int xo = i / 3, c = i - 3 * xo;
-        const int co = rgb_order ? c : 2 - c;                 // output planes are R,G,B
-        const float mean = co == 0 ? m0 : (co == 1 ? m1 : m2);
-        const float sd = co == 0 ? s0 : (co == 1 ? s1 : s2);
-        const float v = __fdiv_rn((float)u, 255.0f);          // ToTensor
-        dst[(((size_t)n_img * 3 + co) * out + yo) * out + xo] = __fdiv_rn(__fsub_rn(v, mean), sd);   // Normalize
+    const bool vec = (rowb & 3) == 0 && ((reinterpret_cast<uintptr_t>(tbase) & 3) == 0);
+    for (int i = threadIdx.x * 4; i < rowb; i += blockDim.x * 4) {
+        int acc[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[b] = 1 << (kPrecisionBits - 1);
+        if (vec) {
+#pragma unroll 4
+            for (int y = 0; y < cnt; ++y) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(tbase + (size_t)(first + y) * rowb + i));
+                const int kv = __ldg(k + y);
+                acc[0] += (int)(w & 255) * kv;
+                acc[1] += (int)((w >> 8) & 255) * kv;
+                acc[2] += (int)((w >> 16) & 255) * kv;
+                acc[3] += (int)(w >> 24) * kv;
+            }
+        } else {
+            for (int y = 0; y < cnt; ++y) {
+                const int kv = __ldg(k + y);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (i + b < rowb) acc[b] += (int)tbase[(size_t)(first + y) * rowb + i + b] * kv;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int ib = i + b;
+            if (ib >= rowb) break;
+            const int u = clip8(acc[b]);
+            const int xo = ib / 3, c = ib - 3 * xo;
+            const int co = rgb_order ? c : 2 - c;                 // output planes are R,G,B
+            const float mean = co == 0 ? m0 : (co == 1 ? m1 : m2);
+            const float sd = co == 0 ? s0 : (co == 1 ? s1 : s2);
+            const float v = __fdiv_rn((float)u, 255.0f);          // ToTensor
+            dst[(((size_t)n_img * 3 + co) * out + yo) * out + xo] = __fdiv_rn(__fsub_rn(v, mean), sd);   // Normalize
+        }
     }
 }
 
@@ -188,8 +214,8 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                                                  h_px_lo, h_span_px, d_tmp);
     FB_CUDA_OK(cudaGetLastError());
     dim3 gv(out_size, n);
-    int threads = out_size * 3;
-    threads = threads > 1024 ? 1024 : ((threads + 31) / 32) * 32;
+    int threads = (out_size * 3 + 3) / 4;
+    threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
     resample_v_kernel<<<gv, threads, 0, stream>>>(d_tmp, rows, row0, out_size, d_vbounds, d_vcoef, vk, rgb_order,
                                                   mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], d_out);
     FB_CUDA_OK(cudaGetLastError());

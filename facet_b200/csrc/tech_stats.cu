@@ -97,7 +97,8 @@ __device__ __forceinline__ float add_f32_f16(uint16_t a, float c) {   // c + a
 
 struct RowRegs {
     uint4 q0, q1, q2;   // 48 bytes = 16 pixels
-    uint32_t halo;      // 3 bytes of the one extra pixel lane 0 / lane 31 may need
+    uint32_t h0, h1, h2;   // the 3 bytes of the one extra pixel lane 0 / lane 31 may need (kept raw:
+                           // combining them here would stall on the load two rows early)
 };
 
 // histogram increment in shared memory (ptxas turns "+1" into the warp-aggregating
@@ -112,10 +113,12 @@ __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl,
     r.q0 = ldg_nc_v4(p);
     r.q1 = ldg_nc_v4(p + 16);
     r.q2 = ldg_nc_v4(p + 32);
-    r.halo = 0;
+    r.h0 = r.h1 = r.h2 = 0;
     if (need_halo) {
         const uint8_t* h = row + (size_t)hx * 3;
-        r.halo = (uint32_t)__ldg(h) | ((uint32_t)__ldg(h + 1) << 8) | ((uint32_t)__ldg(h + 2) << 16);
+        r.h0 = __ldg(h);
+        r.h1 = __ldg(h + 1);
+        r.h2 = __ldg(h + 2);
     }
 }
 
@@ -210,7 +213,7 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
         }
         int gh;
         {
-            int c0 = cur.halo & 255, c1 = (cur.halo >> 8) & 255, c2 = (cur.halo >> 16) & 255;
+            const int c0 = (int)cur.h0, c1 = (int)cur.h1, c2 = (int)cur.h2;
             gh = gray_of(RGB ? c2 : c0, c1, RGB ? c0 : c2);
         }
 
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
     unsigned int* const s_h256 = fb_smem + kOffH256;
     unsigned int* const s_sdiv = fb_smem + kOffSdiv;
     unsigned int* const s_hdiv = fb_smem + kOffHdiv;
+    unsigned int* const s_next = fb_smem + kOffHdiv + 256;       // next unclaimed unit of the current segment
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         s_sdiv[tid] = (unsigned int)sdiv_entry(tid);
         s_hdiv[tid] = (unsigned int)hdiv_entry(tid);
     }
+    if (tid == 0) *s_next = 0u;
     __syncthreads();
 
     const long long upi = (long long)a.tiles_x * a.units_y;
@@ -318,7 +323,12 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
 
         unsigned long long acc_l2 = 0ull, acc_n = 0ull;
         long long acc_l = 0;
-        for (long long u = u0 + warp; u < seg_end; u += kWarps) {
+        // warps claim units of the segment dynamically (s_next is reset between segments)
+        for (;;) {
+            long long u = 0;
+            if ((tid & 31) == 0) u = u0 + (long long)atomicAdd(s_next, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= seg_end) break;
             const int ul = (int)(u - img_first);
             const int tx = ul % a.tiles_x;
             if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
@@ -335,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         }
         __syncthreads();
         // merge the CTA-private histograms into the image's global ones
+        if (tid == 0) *s_next = 0u;
         unsigned int* g_hs = a.hs + (size_t)img_idx * kHsBins;
         for (int i = tid; i < kHsBins; i += kThreads) {
             unsigned int c = s_hs[i];

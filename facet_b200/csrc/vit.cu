@@ -212,7 +212,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[4][4], uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(kAttnWarps * 32, 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                     __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t attn_smem[];
     uint8_t* ksm = attn_smem;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const __nv_b
 //   emb = feat / max(||feat||, 1e-12)                      F.normalize, scorer.py:663
 //   raw = W2 . relu(W1 feat + b1) + b2                     aesthetic head on un-normalised features, scorer.py:664
 //   sims = emb @ T^T                                       tagger.py:101
-__global__ void __launch_bounds__(256) vit_tail_kernel(const float* __restrict__ x, const float* __restrict__ g,
+__global__ void __launch_bounds__(768) vit_tail_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ be, const float* __restrict__ proj /*[1024][768]*/,
                                                        const float* __restrict__ w1 /*[256][768]*/, const float* __restrict__ b1,
                                                        const float* __restrict__ w2 /*[256]*/, const float* __restrict__ b2,
@@ -284,69 +284,71 @@ __global__ void __launch_bounds__(256) vit_tail_kernel(const float* __restrict__
                                                        float* __restrict__ raw_out, float* __restrict__ sims_out) {
     __shared__ float y[kWidth];
     __shared__ float feat[768];
-    __shared__ float red[8];
+    __shared__ float red[24];
     __shared__ float hid[256];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;   // 24 warps
     const float* row = x + (size_t)b * kTokens * kWidth;
-    float v[4];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { v[j] = row[tid + 256 * j]; s += v[j]; }
+    // ln_post on the class token (two-pass, fp32)
+    float v0 = row[tid], v1 = (tid < 256) ? row[768 + tid] : 0.f;
+    float s = v0 + v1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[warp] = s;
     __syncthreads();
     float mean = 0.f;
-    for (int i = 0; i < 8; ++i) mean += red[i];
+    for (int i = 0; i < 24; ++i) mean += red[i];
     mean *= (1.0f / kWidth);
     __syncthreads();
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const float d = v[j] - mean; q += d * d; }
+    float d0 = v0 - mean, d1 = (tid < 256) ? (v1 - mean) : 0.f;
+    float q = d0 * d0 + d1 * d1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     if (lane == 0) red[warp] = q;
     __syncthreads();
     float var = 0.f;
-    for (int i = 0; i < 8; ++i) var += red[i];
+    for (int i = 0; i < 24; ++i) var += red[i];
     const float rstd = rsqrtf(var * (1.0f / kWidth) + 1e-5f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[tid + 256 * j] = (v[j] - mean) * rstd * g[tid + 256 * j] + be[tid + 256 * j];
+    y[tid] = d0 * rstd * g[tid] + be[tid];
+    if (tid < 256) y[768 + tid] = d1 * rstd * g[768 + tid] + be[768 + tid];
     __syncthreads();
-    // projection: thread -> 3 output columns, coalesced over the 768 columns of proj
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (int k = 0; k < kWidth; ++k) {
-        const float yk = y[k];
-        const float* pr = proj + (size_t)k * 768;
+    // projection: one output column per thread, coalesced rows of proj, 8 independent accumulators
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < kWidth; k += 8) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j] = fmaf(yk, __ldg(pr + tid + 256 * j), acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(y[k + j], __ldg(proj + (size_t)(k + j) * 768 + tid), acc[j]);
     }
-    float nrm = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { feat[tid + 256 * j] = acc[j]; nrm += acc[j] * acc[j]; }
-    __syncthreads();
+    const float f = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    feat[tid] = f;
+    float nrm = f * f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    __syncthreads();            // red[] reads above are done, feat[] is complete after the next barrier
     if (lane == 0) red[warp] = nrm;
     __syncthreads();
     float tot = 0.f;
-    for (int i = 0; i < 8; ++i) tot += red[i];
+    for (int i = 0; i < 24; ++i) tot += red[i];
     const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    feat_out[(size_t)b * 768 + tid] = f;
+    emb_out[(size_t)b * 768 + tid] = f * inv;
+    // MLP head: warp per hidden unit, coalesced rows of w1
+    for (int u = warp; u < 256; u += 24) {
+        const float* wr = w1 + (size_t)u * 768;
+        float h = 0.f;
+#pragma unroll 8
+        for (int k = lane; k < 768; k += 32) h = fmaf(__ldg(wr + k), feat[k], h);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        feat_out[(size_t)b * 768 + tid + 256 * j] = acc[j];
-        emb_out[(size_t)b * 768 + tid + 256 * j] = acc[j] * inv;
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        if (lane == 0) hid[u] = fmaxf(h + b1[u], 0.f) * w2[u];
     }
-    // MLP head: hidden unit per thread
-    {
-        const float* wr = w1 + (size_t)tid * 768;
-        float hsum = b1[tid];
-        for (int k = 0; k < 768; k += 4) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
-            hsum = fmaf(w4.x, feat[k], hsum); hsum = fmaf(w4.y, feat[k + 1], hsum);
-            hsum = fmaf(w4.z, feat[k + 2], hsum); hsum = fmaf(w4.w, feat[k + 3], hsum);
-        }
-        hid[tid] = fmaxf(hsum, 0.f) * w2[tid];
+    // tag similarities on the normalised embedding: warp per prompt
+    for (int tg = warp; tg < ntags; tg += 24) {
+        const float* tr = tags + (size_t)tg * 768;
+        float d = 0.f;
+#pragma unroll 8
+        for (int k = lane; k < 768; k += 32) d = fmaf(feat[k] * inv, __ldg(tr + k), d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) sims_out[(size_t)b * ntags + tg] = d;
     }
     __syncthreads();
     if (warp == 0) {
@@ -355,15 +357,6 @@ __global__ void __launch_bounds__(256) vit_tail_kernel(const float* __restrict__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
         if (lane == 0) raw_out[b] = r + b2[0];
-    }
-    // tag similarities on the normalised embedding
-    for (int tg = warp; tg < ntags; tg += 8) {
-        const float* tr = tags + (size_t)tg * 768;
-        float d = 0.f;
-        for (int k = lane; k < 768; k += 32) d = fmaf(feat[k] * inv, __ldg(tr + k), d);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0) sims_out[(size_t)b * ntags + tg] = d;
     }
 }
 
@@ -415,7 +408,7 @@ int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be
                     float* emb, float* raw, float* sims, cudaStream_t stream) {
     FB_REQUIRE(d_x && g && be && proj && w1 && b1 && w2 && b2 && feat && emb && raw && batch >= 1, "fb_vit_tail: bad arguments");
     FB_REQUIRE(ntags == 0 || (tags && sims), "fb_vit_tail: tag matrix / output missing");
-    vit_tail_kernel<<<batch, 256, 0, stream>>>(d_x, g, be, proj, w1, b1, w2, b2, tags, ntags, feat, emb, raw, sims);
+    vit_tail_kernel<<<batch, 768, 0, stream>>>(d_x, g, be, proj, w1, b1, w2, b2, tags, ntags, feat, emb, raw, sims);
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }
