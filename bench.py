@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="24 MP frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=128, help="24 MP frames per GPU per step")
     ap.add_argument("--impl", default="facet_b200", choices=["facet_b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -277,13 +277,15 @@ def main():
     M = B * 257
     gemm_ms = 0.0
     for (m, n, k, reps_in_fwd, mode) in [(B * 256, 1024, 640, 1, ops.GEMM_F32), (M, 3072, 1024, 24, ops.GEMM_BIAS_BF16),
-                                        (M, 1024, 1024, 24, ops.GEMM_BIAS_BF16), (M, 4096, 1024, 24, ops.GEMM_BIAS_GELU_BF16),
-                                        (M, 1024, 4096, 24, ops.GEMM_BIAS_BF16)]:
+                                        (M, 1024, 1024, 24, ops.GEMM_BIAS_RESIDUAL_F32), (M, 4096, 1024, 24, ops.GEMM_BIAS_GELU_BF16),
+                                        (M, 1024, 4096, 24, ops.GEMM_BIAS_RESIDUAL_F32)]:
         a = torch.randn(m, k, device=device).to(torch.bfloat16)
         w = (torch.randn(n, k, device=device) * k ** -0.5).to(torch.bfloat16)
         bias = torch.zeros(n, device=device)
-        o = torch.empty((m, n), device=device, dtype=torch.float32 if mode == ops.GEMM_F32 else torch.bfloat16)
-        ms, _ = timed(lambda: ops.gemm_bf16(a, w, mode, bias=bias, out=o), reps=5)
+        f32_out = mode in (ops.GEMM_F32, ops.GEMM_BIAS_RESIDUAL_F32)
+        o = torch.zeros((m, n), device=device, dtype=torch.float32 if f32_out else torch.bfloat16)
+        res = o if mode == ops.GEMM_BIAS_RESIDUAL_F32 else None      # in place, as the forward pass does
+        ms, _ = timed(lambda: ops.gemm_bf16(a, w, mode, bias=bias, residual=res, out=o), reps=5)
         gemm_ms += ms * reps_in_fwd
         del a, w, o
     peaks = measured_peaks()

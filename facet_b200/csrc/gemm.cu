@@ -31,7 +31,10 @@ constexpr int kBBytes = BN * BK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kEpiPitch = 80;                               // bytes per staged row (64 B of bf16 + 16 B pad: conflict-free)
+constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch;  // per-warp 32x32 bf16 transpose buffers (20 KB)
+constexpr int kEpiBiasBytes = kEpiWarps * 512;              // per-warp copy of the 128 bias values of its columns
+constexpr int kSmemBytes = STAGES * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct GemmArgs {
     int M, N, K;
@@ -52,11 +55,14 @@ struct GemmArgs {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint8_t* epi_stage = smem + STAGES * kStageBytes;
+    uint8_t* epi_bias = epi_stage + kEpiStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kEpiStageBytes + kEpiBiasBytes);
     uint64_t* full_bar = bars;                   // [STAGES]
     uint64_t* empty_bar = bars + STAGES;         // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
@@ -70,7 +76,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int num_tiles = tiles_m * tiles_n;
     const int kblocks = p.K / BK;
     // similarity mode only needs tiles that contain an element with col > global row
-    const bool tri = (p.mode == FB_GEMM_THRESHOLD_PAIRS);
+    constexpr bool tri = (MODE == FB_GEMM_THRESHOLD_PAIRS);
 #define FB_TILE_SKIPPED(m0_, n0_) (tri && ((n0_) + BN <= (m0_) + p.row_offset + 1))
 
     if (threadIdx.x == 0) {
@@ -149,22 +155,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ew = warp - 2;
         const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
         const int half = ew >> 2;              // which 128 of the 256 accumulator columns
+        uint8_t* stg = epi_stage + ew * (32 * kEpiPitch);
+        float* bias_s = reinterpret_cast<float*>(epi_bias + ew * 512);
+        constexpr bool bf16_out = (MODE == FB_GEMM_BIAS_BF16 || MODE == FB_GEMM_BIAS_GELU_BF16);
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             if (FB_TILE_SKIPPED(m0, n0)) continue;
             const int acc = iter & 1;
+            const int rbase = m0 + quarter * 32;
+            const int row = rbase + lane;
+            const bool row_ok = row < p.M;
+            const int ncol0 = n0 + half * 128;
+            // bias of this warp's 128 columns -> smem, while the MMAs of the tile are still running
+            __syncwarp();
+            {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && ncol0 + lane * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + lane * 4));
+                *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+            }
+            __syncwarp();
             tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc::tc_fence_after();
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = n0 + half * 128 + c * 32;
-                uint32_t v[32];
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128 + c * 32, v);
-                tc::tmem_ld_wait();
-                if (p.mode == FB_GEMM_THRESHOLD_PAIRS) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+
+            // coalesced residual prefetch for chunk c: lane -> row (lane>>2)+8j, 16-byte piece (lane&3) of each 64-byte half
+            auto prefetch_res = [&](float4 (&rr)[8], int c) {
+                if (MODE != FB_GEMM_BIAS_RESIDUAL_F32) return;
+                const int col0 = ncol0 + c * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int rl = (lane >> 2) + 8 * (q & 3);
+                    rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rbase + rl < p.M && col0 < p.N)
+                        rr[q] = *reinterpret_cast<const float4*>(p.residual + (size_t)(rbase + rl) * p.ldr + col0 + 16 * (q >> 2) + 4 * (lane & 3));
+                }
+            };
+            auto process = [&](const uint32_t (&v)[32], int c, const float4 (&rr)[8]) {
+                const int col0 = ncol0 + c * 32;
+                if (MODE == FB_GEMM_THRESHOLD_PAIRS) {
                     const int grow = p.row_offset + row;
                     if (row_ok && col0 + 31 > grow) {
 #pragma unroll
@@ -181,48 +210,128 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                     }
-                } else if (col0 < p.N) {
-                    float f[32];
+                    return;
+                }
+                if (col0 >= p.N) return;          // warp-uniform
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias) {
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+                    f[j] = __uint_as_float(v[j]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (MODE == FB_GEMM_BIAS_GELU_BF16) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                        }
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                }
+                // thread = row holds 32 consecutive outputs.  Transpose through the per-warp smem buffer so that
+                // 4 lanes write 64 contiguous bytes of one row (full sectors) instead of 32 rows x 16 bytes.
+                if (bf16_out) {
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(stg + lane * kEpiPitch + 16 * j) =
+                            make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                       tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rl = (lane >> 2) + 8 * j;
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * kEpiPitch + 16 * (lane & 3));
+                        if (rbase + rl < p.M)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(rbase + rl) * p.ldo + col0 + 8 * (lane & 3)) = val;
                     }
-                    if (p.mode == FB_GEMM_BIAS_GELU_BF16) {
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    }
-                    if (row_ok) {
-                        if (p.mode == FB_GEMM_BIAS_BF16 || p.mode == FB_GEMM_BIAS_GELU_BF16) {
-                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dst[j] = make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                                    tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-                        } else {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0);
-                            if (p.mode == FB_GEMM_BIAS_RESIDUAL_F32) {
-                                const float4* res = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.ldr + col0);
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(stg + lane * kEpiPitch + 16 * j) =
+                                make_float4(f[16 * hh + 4 * j], f[16 * hh + 4 * j + 1], f[16 * hh + 4 * j + 2], f[16 * hh + 4 * j + 3]);
+                        __syncwarp();
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 r4 = res[j];
-                                    dst[j] = make_float4(f[4 * j] + r4.x, f[4 * j + 1] + r4.y, f[4 * j + 2] + r4.z, f[4 * j + 3] + r4.w);
+                        for (int j = 0; j < 4; ++j) {
+                            const int rl = (lane >> 2) + 8 * j;
+                            float4 val = *reinterpret_cast<const float4*>(stg + rl * kEpiPitch + 16 * (lane & 3));
+                            if (rbase + rl < p.M) {
+                                if (MODE == FB_GEMM_BIAS_RESIDUAL_F32) {
+                                    const float4 r4 = rr[hh * 4 + j];
+                                    val.x += r4.x; val.y += r4.y; val.z += r4.z; val.w += r4.w;
                                 }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)(rbase + rl) * p.ldo + col0 + 16 * hh + 4 * (lane & 3)) = val;
                             }
                         }
                     }
                 }
+            };
+
+            if (MODE == FB_GEMM_BIAS_GELU_BF16) {
+                // erf-GELU is register hungry: one register set, chunk after chunk
+                uint32_t va[32];
+                float4 rz[8];
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    tc::tmem_ld_32x32(taddr + 32 * c, va);
+                    tc::tmem_ld_wait();
+                    if (c == 3) {
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                    }
+                    process(va, c, rz);
+                }
+            } else if (MODE == FB_GEMM_BIAS_RESIDUAL_F32) {
+                // one accumulator register set, two residual sets: the (coalesced) residual loads of chunk
+                // c+1 are in flight while chunk c is added and stored
+                uint32_t va[32];
+                float4 ra[8], rb[8];
+                prefetch_res(ra, 0);
+                tc::tmem_ld_32x32(taddr, va);
+                prefetch_res(rb, 1);
+                tc::tmem_ld_wait();
+                process(va, 0, ra);
+                tc::tmem_ld_32x32(taddr + 32, va);
+                prefetch_res(ra, 2);
+                tc::tmem_ld_wait();
+                process(va, 1, rb);
+                tc::tmem_ld_32x32(taddr + 64, va);
+                prefetch_res(rb, 3);
+                tc::tmem_ld_wait();
+                process(va, 2, ra);
+                tc::tmem_ld_32x32(taddr + 96, va);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                process(va, 3, rb);
+            } else {
+                // two register sets: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+                uint32_t va[32], vb[32];
+                float4 ra[8], rb[8];
+                tc::tmem_ld_32x32(taddr, va);
+                prefetch_res(ra, 0);
+                tc::tmem_ld_wait();
+                tc::tmem_ld_32x32(taddr + 32, vb);
+                prefetch_res(rb, 1);
+                process(va, 0, ra);
+                tc::tmem_ld_wait();
+                tc::tmem_ld_32x32(taddr + 64, va);
+                prefetch_res(ra, 2);
+                process(vb, 1, rb);
+                tc::tmem_ld_wait();
+                tc::tmem_ld_32x32(taddr + 96, vb);
+                prefetch_res(rb, 3);
+                process(va, 2, ra);
+                tc::tmem_ld_wait();
+                // the accumulator is in registers now: hand the TMEM buffer back before the last chunk's math
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                process(vb, 3, rb);
             }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
             ++iter;
         }
     }
@@ -275,14 +384,28 @@ static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, l
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb, BN, BK);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
-    }
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+#define FB_LAUNCH_MODE(MODE_)                                                                                          \
+    case MODE_: {                                                                                                      \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        gemm_bf16_kernel<MODE_><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                                    \
+        break;                                                                                                         \
+    }
+    switch (p.mode) {
+        FB_LAUNCH_MODE(FB_GEMM_BIAS_BF16)
+        FB_LAUNCH_MODE(FB_GEMM_BIAS_GELU_BF16)
+        FB_LAUNCH_MODE(FB_GEMM_BIAS_RESIDUAL_F32)
+        FB_LAUNCH_MODE(FB_GEMM_F32)
+        FB_LAUNCH_MODE(FB_GEMM_THRESHOLD_PAIRS)
+        default:
+            FB_REQUIRE(false, "fb_gemm_bf16: unknown epilogue mode %d", p.mode);
+    }
+#undef FB_LAUNCH_MODE
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -34,7 +34,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kLanePx = 16;
 constexpr int kTileW = 32 * kLanePx;   // 512 px per warp row
 constexpr int kH256Copies = 32;        // one luminance-histogram column per lane
-constexpr size_t kSmemWords = kHsBins + 256 * kH256Copies + 512;
+constexpr size_t kSmemWords = kHsBins + 256 * kH256Copies + 512 + 16;   // + work counter
 constexpr int kOffH256 = kHsBins;                       // word offsets inside the dynamic smem block
 constexpr int kOffSdiv = kOffH256 + 256 * kH256Copies;
 constexpr int kOffHdiv = kOffSdiv + 256;
