@@ -1,0 +1,352 @@
+// Attention of the ViT-L/14 tower on tcgen05: softmax(Q K^T / 8) V per (image, head), 257 tokens, d = 64.
+// (what open_clip's nn.MultiheadAttention does inside `encode_image`, processing/scorer.py:662.)
+//
+// Persistent kernel, one CTA per SM, 256 threads = two independent warpgroups; each warpgroup walks
+// its own queue of (image, head) pairs with its own shared-memory tiles and its own 256 TMEM
+// columns, so the tensor-core / TMA phases of one warpgroup overlap the softmax of the other.
+// Per (image, head), for the two 128-row query tiles t = 0, 1:
+//   TMA      Q (2 x 128 rows), K and V (256 rows each) from the fused qkv buffer, 128-byte swizzle;
+//            the next pair's Q/K (V) loads are issued as soon as the last MMA reading them retires
+//   tcgen05  S = Q_t K^T           M=128, N=256, K=64, fp32 accumulator in TMEM columns [0,256)
+//   softmax  one thread per query row (tcgen05.ld), exact fp32 max / exp2 / sum; P is written back
+//            to TMEM as packed bf16 over the S columns it has already consumed (tcgen05.st)
+//   tcgen05  O = P V               A operand from TMEM, V as an MN-major B operand straight from
+//            the TMA tile; M=128, N=64, K=256; accumulator in TMEM columns [128,192)
+//   the 257th token is handled on the CUDA cores: as a key (one extra score per row folded into the
+//   softmax, one rank-1 update in the epilogue) and as a query (one row against all 257 keys)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int kTok = 257, kW = 1024, kD = 64;
+constexpr int kThreadsAttn = 256;
+constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
+
+// per-warpgroup shared memory map (bytes)
+constexpr int kOffQ = 0;                 // 2 x [128][64] bf16, 128B swizzle
+constexpr int kOffK = 32768;             // [256][64]
+constexpr int kOffV = 65536;             // [256][64]
+constexpr int kOffX = 98304;             // scalars, exchange arrays, barriers
+constexpr int kWgBytes = 98304 + 4096;
+constexpr int kSmemAttn = 2 * kWgBytes + 1024;
+
+struct XArea {
+    float q256[64], k256[64], v256[64];
+    float cls_p[264];
+    float cls_red[8];
+    float cls_o[2][64];
+    uint64_t bar_qk, bar_v, bar_s, bar_pv;
+};
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 16-byte chunk c of row r in a [rows][64] bf16 tile stored with the 128-byte swizzle
+__device__ __forceinline__ const uint4* sw_chunk(const uint8_t* tile, int r, int c) {
+    return reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ float dot64_row(const uint8_t* tile, int r, const float* vec) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 w = *sw_chunk(tile, r, c);
+        const float* v = vec + 8 * c;
+        acc = fmaf(bf16_lo(w.x), v[0], acc); acc = fmaf(bf16_hi(w.x), v[1], acc);
+        acc = fmaf(bf16_lo(w.y), v[2], acc); acc = fmaf(bf16_hi(w.y), v[3], acc);
+        acc = fmaf(bf16_lo(w.z), v[4], acc); acc = fmaf(bf16_hi(w.z), v[5], acc);
+        acc = fmaf(bf16_lo(w.w), v[6], acc); acc = fmaf(bf16_hi(w.w), v[7], acc);
+    }
+    return acc;
+}
+
+// MN-major B operand (V: [keys][64 d], d contiguous, 128-byte swizzle): groups of 8 keys are 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (64u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {      // MUFU.EX2, flush-to-zero: arguments here are <= 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+__global__ void __launch_bounds__(kThreadsAttn, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfloat16* __restrict__ qkv,
+                    __nv_bfloat16* __restrict__ out, int n_pairs) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = warp >> 2;                       // warpgroup 0 / 1
+    const int wt = tid & 127;                       // thread within the warpgroup == query row within a tile
+    uint8_t* smem = smem0 + wg * kWgBytes;
+    XArea* X = reinterpret_cast<XArea*>(smem + kOffX);
+
+    if (wt == 0) {
+        tc::mbar_init(&X->bar_qk, 1);
+        tc::mbar_init(&X->bar_v, 1);
+        tc::mbar_init(&X->bar_s, 1);
+        tc::mbar_init(&X->bar_pv, 1);
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+        if (tid == 0) tc::tma_prefetch_desc(&tmap_qkv);
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot + wg * 256;                               // this warpgroup's 256 columns
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;             // TMEM lanes this warp may touch
+    const uint32_t t_s = tmem + lane_base;                                    // S: columns [0,256); P aliases [0,128)
+    const uint32_t t_o = tmem + lane_base + 128;                              // O: columns [128,192)
+    const uint32_t idesc_s = tc::make_idesc_bf16(128, 256);
+    const uint32_t idesc_o = tc::make_idesc_bf16(128, 64, 0, 1);
+
+    const int first = blockIdx.x * 2 + wg, stride = gridDim.x * 2;
+    auto issue_qk = [&](int pair) {
+        const int b = pair >> 4, h = pair & 15, r0 = b * kTok;
+        tc::mbar_expect_tx(&X->bar_qk, 4 * 16384);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_qk, smem + kOffQ, h * kD, r0);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_qk, smem + kOffQ + 16384, h * kD, r0 + 128);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_qk, smem + kOffK, kW + h * kD, r0);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_qk, smem + kOffK + 16384, kW + h * kD, r0 + 128);
+    };
+    auto issue_v = [&](int pair) {
+        const int b = pair >> 4, h = pair & 15, r0 = b * kTok;
+        tc::mbar_expect_tx(&X->bar_v, 2 * 16384);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_v, smem + kOffV, 2 * kW + h * kD, r0);
+        tc::tma_load_2d(&tmap_qkv, &X->bar_v, smem + kOffV + 16384, 2 * kW + h * kD, r0 + 128);
+    };
+    if (wt == 0 && first < n_pairs) {
+        issue_qk(first);
+        issue_v(first);
+    }
+
+    uint32_t ph_load = 0, ph_s = 0, ph_pv = 0;
+    for (int pair = first; pair < n_pairs; pair += stride) {
+        const int b = pair >> 4, h = pair & 15;
+        const size_t tok0 = (size_t)b * kTok;
+        // the 257th token's q / k / v rows as fp32 (plain loads, overlapped with the TMA)
+        if (wt < 96) {
+            const int which = wt >> 5, d2 = (wt & 31) * 2;
+            const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(qkv + (tok0 + 256) * (3 * kW) + which * kW + h * kD + d2);
+            float* dst = which == 0 ? X->q256 : (which == 1 ? X->k256 : X->v256);
+            dst[d2] = __low2float(v2);
+            dst[d2 + 1] = __high2float(v2);
+        }
+        wg_sync(wg);
+        tc::mbar_wait(&X->bar_qk, ph_load);
+        if (wt == 0) {
+            // S = Q_0 K^T
+            const uint64_t dk = tc::make_desc_k_sw128(tc::smem_u32(smem + kOffK));
+            const uint64_t dq = tc::make_desc_k_sw128(tc::smem_u32(smem + kOffQ));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+            tc::umma_commit(&X->bar_s);
+        }
+        // scores of this thread's row (both tiles) against key 256; CUDA cores, overlaps the MMA
+        const float s256_0 = dot64_row(smem + kOffQ, wt, X->k256);
+        const float s256_1 = dot64_row(smem + kOffQ + 16384, wt, X->k256);
+
+        // ---- query row 256 against all 257 keys ----
+        tc::mbar_wait(&X->bar_v, ph_load);
+        {
+            const float sa = dot64_row(smem + kOffK, wt, X->q256);
+            const float sb = dot64_row(smem + kOffK, wt + 128, X->q256);
+            float s_last = -INFINITY;
+            if (wt == 0) {
+                s_last = 0.f;
+                for (int d = 0; d < 64; ++d) s_last = fmaf(X->q256[d], X->k256[d], s_last);
+            }
+            float mx = fmaxf(fmaxf(sa, sb), s_last);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) X->cls_red[warp & 3] = mx;
+            wg_sync(wg);
+            mx = fmaxf(fmaxf(X->cls_red[0], X->cls_red[1]), fmaxf(X->cls_red[2], X->cls_red[3]));
+            const float pa = ex2_fast((sa - mx) * kScaleLog2), pb = ex2_fast((sb - mx) * kScaleLog2);
+            X->cls_p[wt] = pa;
+            X->cls_p[wt + 128] = pb;
+            float sum = pa + pb;
+            if (wt == 0) {
+                const float pl = ex2_fast((s_last - mx) * kScaleLog2);
+                X->cls_p[256] = pl;
+                sum += pl;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) X->cls_red[4 + (warp & 3)] = sum;
+            wg_sync(wg);
+            // o[d] = sum_j p_j V[j][d]: thread = (d, half of the keys)
+            const int d = wt & 63, part = wt >> 6;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int j = part * 128; j < part * 128 + 128; ++j) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(sw_chunk(smem + kOffV, j, d >> 3))[(d & 7) >> 1];
+                acc = fmaf(X->cls_p[j], (d & 1) ? bf16_hi(w) : bf16_lo(w), acc);
+            }
+            X->cls_o[part][d] = acc;
+            wg_sync(wg);
+            if (wt < 64) {
+                const float tot = (X->cls_red[4] + X->cls_red[5]) + (X->cls_red[6] + X->cls_red[7]);
+                const float o = X->cls_o[0][wt] + X->cls_o[1][wt] + X->cls_p[256] * X->v256[wt];
+                out[(tok0 + 256) * kW + h * kD + wt] = __float2bfloat16(o / tot);
+            }
+        }
+
+        const int next = pair + stride;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&X->bar_s, ph_s);
+            ph_s ^= 1;
+            tc::tc_fence_after();
+            if (t == 1 && wt == 0 && next < n_pairs) issue_qk(next);     // Q and K are dead once S_1 is complete
+            const float s256 = t == 0 ? s256_0 : s256_1;
+            // pass 1: row maximum over the 256 keys in TMEM and key 256 (TMEM loads double-buffered)
+            float mx = s256;
+            {
+                uint32_t va[32], vb[32];
+                tc::tmem_ld_32x32(t_s, va);
+#pragma unroll 1
+                for (int c = 0; c < 8; c += 2) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld_32x32(t_s + (c + 1) * 32, vb);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+                    tc::tmem_ld_wait();
+                    if (c + 2 < 8) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                }
+            }
+            // pass 2: p = exp2((s - m) / 8 * log2 e); P (bf16 pairs) overwrites S columns already consumed
+            const float mxs = mx * kScaleLog2;
+            const float p_last = ex2_fast(fmaf(s256, kScaleLog2, -mxs));
+            float sum = p_last;
+            {
+                uint32_t va[32], vb[32];
+                auto emit = [&](const uint32_t (&v)[32], int c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), kScaleLog2, -mxs));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2, -mxs));
+                        sum += p0 + p1;
+                        pk[j] = tc::pack_bf16(p0, p1);
+                    }
+                    tmem_st_32x16(t_s + c * 16, pk);
+                };
+                tc::tmem_ld_32x32(t_s, va);
+#pragma unroll 1
+                for (int c = 0; c < 8; c += 2) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld_32x32(t_s + (c + 1) * 32, vb);
+                    emit(va, c);
+                    tc::tmem_ld_wait();
+                    if (c + 2 < 8) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
+                    emit(vb, c + 1);
+                }
+            }
+            tmem_st_wait();
+            const float inv_l = 1.0f / sum;
+            tc::tc_fence_before();
+            wg_sync(wg);
+            if (wt == 0) {
+                tc::tc_fence_after();
+                // O = P V : 16 UMMAs of K = 16 keys (8 TMEM columns of P, 16 rows of V each)
+                const uint32_t vbase = tc::smem_u32(smem + kOffV);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    umma_bf16_ts(tmem + 128, tmem + 8 * i, make_desc_mn_sw128(vbase + i * 2048), idesc_o, i != 0);
+                tc::umma_commit(&X->bar_pv);
+            }
+            tc::mbar_wait(&X->bar_pv, ph_pv);
+            ph_pv ^= 1;
+            tc::tc_fence_after();
+            if (t == 1 && wt == 0 && next < n_pairs) issue_v(next);      // V is dead once O_1 is complete
+            // epilogue: O row + rank-1 contribution of key 256, normalised, bf16
+            {
+                uint32_t v0[32], v1[32];
+                tc::tmem_ld_32x32(t_o, v0);
+                tc::tmem_ld_32x32(t_o + 32, v1);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                wg_sync(wg);                       // every row of O is in registers: the accumulator columns may be reused
+                if (t == 0 && wt == 0) {
+                    tc::tc_fence_after();
+                    const uint64_t dk = tc::make_desc_k_sw128(tc::smem_u32(smem + kOffK));
+                    const uint64_t dq = tc::make_desc_k_sw128(tc::smem_u32(smem + kOffQ + 16384));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    tc::umma_commit(&X->bar_s);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out + (tok0 + t * 128 + wt) * kW + h * kD);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int dcol = 8 * q + j;
+                        const float acc = __uint_as_float(dcol < 32 ? v0[dcol] : v1[dcol - 32]);
+                        o[j] = (acc + p_last * X->v256[dcol]) * inv_l;
+                    }
+                    dst[q] = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]), tc::pack_bf16(o[4], o[5]),
+                                        tc::pack_bf16(o[6], o[7]));
+                }
+            }
+        }
+        ph_load ^= 1;
+        wg_sync(wg);        // X arrays (q256 / k256 / v256 / cls_*) are rewritten by the next pair
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 0) tc::tmem_dealloc(tmem_slot, 512);
+}
+
+}  // namespace
+
+int launch_attention_tc(const void* d_qkv, int batch, void* d_out, cudaStream_t stream) {
+    FB_REQUIRE(d_qkv && d_out && batch >= 1, "fb_vit_attention: bad arguments");
+    CUtensorMap tm;
+    int rc = make_tmap_bf16_2d(&tm, d_qkv, (uint64_t)batch * kTok, 3 * kW, 3 * kW, 128, 64);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
+        attr_set = true;
+    }
+    const int n_pairs = batch * 16;
+    int grid = (n_pairs + 1) / 2;
+    if (grid > sm_count()) grid = sm_count();
+    attention_tc_kernel<<<grid, kThreadsAttn, kSmemAttn, stream>>>(tm, reinterpret_cast<const __nv_bfloat16*>(d_qkv),
+                                                                 reinterpret_cast<__nv_bfloat16*>(d_out), n_pairs);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fb

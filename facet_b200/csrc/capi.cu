@@ -216,8 +216,14 @@ int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* ga
     return rc;
 }
 
-int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
+int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
     int rc = launch_attention(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
+    int rc = launch_attention_tc(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }

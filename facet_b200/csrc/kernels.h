@@ -48,7 +48,8 @@ int launch_im2col_patch14(const float* d_x, int batch, void* d_out, cudaStream_t
 int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
                      const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,
                      cudaStream_t stream);
-int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);
+int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);      // mma.sync (legacy path)
+int launch_attention_tc(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);   // tcgen05
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream);

@@ -65,7 +65,7 @@ int vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void
         STEP(launch_layernorm(ws.x, kWidth, M, L.ln1_g, L.ln1_b, nullptr, nullptr, ws.xn, kWidth, 1, st), 1);
         STEP(launch_gemm_bf16(ws.xn, kWidth, L.w_qkv, kWidth, M, 3 * kWidth, kWidth, FB_GEMM_BIAS_BF16, L.b_qkv, ws.qkv,
                               3 * kWidth, nullptr, 0, st), 1);
-        STEP(launch_attention(ws.qkv, batch, ws.attn, st), 1);
+        STEP(launch_attention_tc(ws.qkv, batch, ws.attn, st), 1);
         STEP(launch_gemm_bf16(ws.attn, kWidth, L.w_out, kWidth, M, kWidth, kWidth, FB_GEMM_BIAS_RESIDUAL_F32, L.b_out, ws.x,
                               kWidth, ws.x, kWidth, st), 1);
         STEP(launch_layernorm(ws.x, kWidth, M, L.ln2_g, L.ln2_b, nullptr, nullptr, ws.xn, kWidth, 1, st), 1);

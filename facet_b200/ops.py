@@ -263,13 +263,15 @@ def vit_layernorm(x, gamma, beta, out_bf16=True, class_emb=None, pos_emb=None, r
     return out
 
 
-def vit_attention(qkv, batch: int):
-    """qkv: CUDA bf16 [batch*257, 3072] -> bf16 [batch*257, 1024]."""
+def vit_attention(qkv, batch: int, legacy_mma: bool = False):
+    """qkv: CUDA bf16 [batch*257, 3072] -> bf16 [batch*257, 1024] (tcgen05 kernel; legacy_mma selects the
+    mma.sync variant kept for A/B checks)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     out = torch.empty((batch * 257, 1024), dtype=torch.bfloat16, device=qkv.device)
+    fn = lib.fb_vit_attention_mma if legacy_mma else lib.fb_vit_attention
     with torch.cuda.device(qkv.device):
-        _lib.check(lib.fb_vit_attention(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
+        _lib.check(fn(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
     return out
 
 

@@ -194,7 +194,8 @@ int fb_vit_im2col(const float* d_clip_in, int batch, void* d_out_bf16, void* str
 int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* gamma, const float* beta,
                      const float* class_emb, const float* pos_emb, void* d_out, int64_t ld_out,
                      int out_bf16, void* stream);
-int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);
+int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);      /* tcgen05 */
+int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);  /* mma.sync variant, kept for A/B checks */
 
 #ifdef __cplusplus
 }

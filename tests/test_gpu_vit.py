@@ -48,12 +48,13 @@ def test_layernorm_and_assembly():
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
 
 
-def test_attention_vs_torch():
+@pytest.mark.parametrize("legacy", [False, True])
+def test_attention_vs_torch(legacy):
     import torch
     from facet_b200 import ops
     bsz = 3
     qkv = _rand_bf16((bsz * 257, 3072), 5, scale=1.5)
-    got = ops.vit_attention(qkv, bsz).float().reshape(bsz, 257, 16, 64)
+    got = ops.vit_attention(qkv, bsz, legacy_mma=legacy).float().reshape(bsz, 257, 16, 64)
     q, k, v = qkv.float().reshape(bsz, 257, 3, 16, 64).unbind(2)
     att = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125, dim=-1)
     ref = torch.einsum("bhqk,bkhd->bqhd", att, v)
