@@ -44,7 +44,7 @@ class VitLayer(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [(n, _P) for n in ("w_patch", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b",
                                   "proj", "head_w1", "head_b1", "head_w2", "head_b2", "tag_emb")] + [
-        ("n_tags", C.c_int), ("n_layers", C.c_int), ("layers", C.POINTER(VitLayer))]
+        ("n_tags", C.c_int), ("f16", C.c_int), ("n_layers", C.c_int), ("layers", C.POINTER(VitLayer))]
 
 
 _SIGNATURES.update({
@@ -59,6 +59,7 @@ _SIGNATURES.update({
     "fb_vit_layernorm": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "fb_vit_attention": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_vit_attention_mma": (C.c_int, [_P, C.c_int, _P, _P]),
+    "fb_vit_attention_f16": (C.c_int, [_P, C.c_int, _P, _P]),
 })
 
 

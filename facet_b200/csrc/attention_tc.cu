@@ -44,24 +44,23 @@ struct XArea {
     uint64_t bar_qk, bar_v, bar_s, bar_pv;
 };
 
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // 16-byte chunk c of row r in a [rows][64] bf16 tile stored with the 128-byte swizzle
 __device__ __forceinline__ const uint4* sw_chunk(const uint8_t* tile, int r, int c) {
     return reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
 }
 
+template <bool F16>
 __device__ __forceinline__ float dot64_row(const uint8_t* tile, int r, const float* vec) {
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const uint4 w = *sw_chunk(tile, r, c);
         const float* v = vec + 8 * c;
-        acc = fmaf(bf16_lo(w.x), v[0], acc); acc = fmaf(bf16_hi(w.x), v[1], acc);
-        acc = fmaf(bf16_lo(w.y), v[2], acc); acc = fmaf(bf16_hi(w.y), v[3], acc);
-        acc = fmaf(bf16_lo(w.z), v[4], acc); acc = fmaf(bf16_hi(w.z), v[5], acc);
-        acc = fmaf(bf16_lo(w.w), v[6], acc); acc = fmaf(bf16_hi(w.w), v[7], acc);
+        acc = fmaf(tc::lo16<F16>(w.x), v[0], acc); acc = fmaf(tc::hi16<F16>(w.x), v[1], acc);
+        acc = fmaf(tc::lo16<F16>(w.y), v[2], acc); acc = fmaf(tc::hi16<F16>(w.y), v[3], acc);
+        acc = fmaf(tc::lo16<F16>(w.z), v[4], acc); acc = fmaf(tc::hi16<F16>(w.z), v[5], acc);
+        acc = fmaf(tc::lo16<F16>(w.w), v[6], acc); acc = fmaf(tc::hi16<F16>(w.w), v[7], acc);
     }
     return acc;
 }
@@ -94,9 +93,10 @@ __device__ __forceinline__ float ex2_fast(float x) {      // MUFU.EX2, flush-to-
 }
 __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreadsAttn, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfloat16* __restrict__ qkv,
-                    __nv_bfloat16* __restrict__ out, int n_pairs) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t* __restrict__ qkv,
+                    uint16_t* __restrict__ out, int n_pairs) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -123,8 +123,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;             // TMEM lanes this warp may touch
     const uint32_t t_s = tmem + lane_base;                                    // S: columns [0,256); P aliases [0,128)
     const uint32_t t_o = tmem + lane_base + 128;                              // O: columns [128,192)
-    const uint32_t idesc_s = tc::make_idesc_bf16(128, 256);
-    const uint32_t idesc_o = tc::make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t idesc_s = tc::make_idesc16<F16>(128, 256);
+    const uint32_t idesc_o = tc::make_idesc16<F16>(128, 64, 0, 1);
 
     const int first = blockIdx.x * 2 + wg, stride = gridDim.x * 2;
     auto issue_qk = [&](int pair) {
@@ -153,10 +153,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
         // the 257th token's q / k / v rows as fp32 (plain loads, overlapped with the TMA)
         if (wt < 96) {
             const int which = wt >> 5, d2 = (wt & 31) * 2;
-            const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(qkv + (tok0 + 256) * (3 * kW) + which * kW + h * kD + d2);
+            const uint32_t v2 = *reinterpret_cast<const uint32_t*>(qkv + (tok0 + 256) * (3 * kW) + which * kW + h * kD + d2);
             float* dst = which == 0 ? X->q256 : (which == 1 ? X->k256 : X->v256);
-            dst[d2] = __low2float(v2);
-            dst[d2 + 1] = __high2float(v2);
+            dst[d2] = tc::lo16<F16>(v2);
+            dst[d2 + 1] = tc::hi16<F16>(v2);
         }
         wg_sync(wg);
         tc::mbar_wait(&X->bar_qk, ph_load);
@@ -169,14 +169,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
             tc::umma_commit(&X->bar_s);
         }
         // scores of this thread's row (both tiles) against key 256; CUDA cores, overlaps the MMA
-        const float s256_0 = dot64_row(smem + kOffQ, wt, X->k256);
-        const float s256_1 = dot64_row(smem + kOffQ + 16384, wt, X->k256);
+        const float s256_0 = dot64_row<F16>(smem + kOffQ, wt, X->k256);
+        const float s256_1 = dot64_row<F16>(smem + kOffQ + 16384, wt, X->k256);
 
         // ---- query row 256 against all 257 keys ----
         tc::mbar_wait(&X->bar_v, ph_load);
         {
-            const float sa = dot64_row(smem + kOffK, wt, X->q256);
-            const float sb = dot64_row(smem + kOffK, wt + 128, X->q256);
+            const float sa = dot64_row<F16>(smem + kOffK, wt, X->q256);
+            const float sb = dot64_row<F16>(smem + kOffK, wt + 128, X->q256);
             float s_last = -INFINITY;
             if (wt == 0) {
                 s_last = 0.f;
@@ -207,14 +207,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
 #pragma unroll 8
             for (int j = part * 128; j < part * 128 + 128; ++j) {
                 const uint32_t w = reinterpret_cast<const uint32_t*>(sw_chunk(smem + kOffV, j, d >> 3))[(d & 7) >> 1];
-                acc = fmaf(X->cls_p[j], (d & 1) ? bf16_hi(w) : bf16_lo(w), acc);
+                acc = fmaf(X->cls_p[j], (d & 1) ? tc::hi16<F16>(w) : tc::lo16<F16>(w), acc);
             }
             X->cls_o[part][d] = acc;
             wg_sync(wg);
             if (wt < 64) {
                 const float tot = (X->cls_red[4] + X->cls_red[5]) + (X->cls_red[6] + X->cls_red[7]);
                 const float o = X->cls_o[0][wt] + X->cls_o[1][wt] + X->cls_p[256] * X->v256[wt];
-                out[(tok0 + 256) * kW + h * kD + wt] = __float2bfloat16(o / tot);
+                out[(tok0 + 256) * kW + h * kD + wt] = (uint16_t)(tc::pack16<F16>(o / tot, 0.f) & 0xffffu);
             }
         }
 
@@ -256,7 +256,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
                         const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), kScaleLog2, -mxs));
                         const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2, -mxs));
                         sum += p0 + p1;
-                        pk[j] = tc::pack_bf16(p0, p1);
+                        pk[j] = tc::pack16<F16>(p0, p1);
                     }
                     tmem_st_32x16(t_s + c * 16, pk);
                 };
@@ -314,8 +314,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
                         const float acc = __uint_as_float(dcol < 32 ? v0[dcol] : v1[dcol - 32]);
                         o[j] = (acc + p_last * X->v256[dcol]) * inv_l;
                     }
-                    dst[q] = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]), tc::pack_bf16(o[4], o[5]),
-                                        tc::pack_bf16(o[6], o[7]));
+                    dst[q] = make_uint4(tc::pack16<F16>(o[0], o[1]), tc::pack16<F16>(o[2], o[3]), tc::pack16<F16>(o[4], o[5]),
+                                        tc::pack16<F16>(o[6], o[7]));
                 }
             }
         }
@@ -330,21 +330,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfl
 
 }  // namespace
 
-int launch_attention_tc(const void* d_qkv, int batch, void* d_out, cudaStream_t stream) {
+int launch_attention_tc(const void* d_qkv, int batch, void* d_out, int f16, cudaStream_t stream) {
     FB_REQUIRE(d_qkv && d_out && batch >= 1, "fb_vit_attention: bad arguments");
     CUtensorMap tm;
     int rc = make_tmap_bf16_2d(&tm, d_qkv, (uint64_t)batch * kTok, 3 * kW, 3 * kW, 128, 64);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
+        FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
+        FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
         attr_set = true;
     }
     const int n_pairs = batch * 16;
     int grid = (n_pairs + 1) / 2;
     if (grid > sm_count()) grid = sm_count();
-    attention_tc_kernel<<<grid, kThreadsAttn, kSmemAttn, stream>>>(tm, reinterpret_cast<const __nv_bfloat16*>(d_qkv),
-                                                                 reinterpret_cast<__nv_bfloat16*>(d_out), n_pairs);
+    if (f16) attention_tc_kernel<true><<<grid, kThreadsAttn, kSmemAttn, stream>>>(tm, reinterpret_cast<const uint16_t*>(d_qkv),
+                                                                              reinterpret_cast<uint16_t*>(d_out), n_pairs);
+    else attention_tc_kernel<false><<<grid, kThreadsAttn, kSmemAttn, stream>>>(tm, reinterpret_cast<const uint16_t*>(d_qkv),
+                                                                            reinterpret_cast<uint16_t*>(d_out), n_pairs);
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -203,7 +203,7 @@ int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, v
 }
 
 int fb_vit_im2col(const float* d_clip_in, int batch, void* d_out_bf16, void* stream) {
-    int rc = launch_im2col_patch14(d_clip_in, batch, d_out_bf16, (cudaStream_t)stream);
+    int rc = launch_im2col_patch14(d_clip_in, batch, d_out_bf16, 0, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }
@@ -216,6 +216,12 @@ int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* ga
     return rc;
 }
 
+int fb_vit_attention_f16(const void* d_qkv_f16, int batch, void* d_out_f16, void* stream) {
+    int rc = launch_attention_tc(d_qkv_f16, batch, d_out_f16, 1, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
 int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
     int rc = launch_attention(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
@@ -223,7 +229,7 @@ int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, vo
 }
 
 int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
-    int rc = launch_attention_tc(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
+    int rc = launch_attention_tc(d_qkv_bf16, batch, d_out_bf16, 0, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }

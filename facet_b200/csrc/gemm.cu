@@ -51,11 +51,12 @@ struct GemmArgs {
     float* pair_sims;
     long long pair_cap;
     unsigned long long* pair_count;
+    int f16;              // operands (and 16-bit outputs) are fp16 instead of bf16
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -122,7 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+            const uint32_t idesc = tc::make_idesc16<F16>(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -233,8 +234,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<uint4*>(stg + lane * kEpiPitch + 16 * j) =
-                            make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                       tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                            make_uint4(tc::pack16<F16>(f[8 * j], f[8 * j + 1]), tc::pack16<F16>(f[8 * j + 2], f[8 * j + 3]),
+                                       tc::pack16<F16>(f[8 * j + 4], f[8 * j + 5]), tc::pack16<F16>(f[8 * j + 6], f[8 * j + 7]));
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -390,10 +391,12 @@ static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, l
     case MODE_: {                                                                                                      \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        gemm_bf16_kernel<MODE_><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                                    \
+        if (p.f16) gemm_bf16_kernel<MODE_, true><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                   \
+        else gemm_bf16_kernel<MODE_, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                        \
         break;                                                                                                         \
     }
     switch (p.mode) {
@@ -430,6 +433,8 @@ int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long 
     FB_REQUIRE(d_a && d_b && d_out, "fb_gemm_bf16: null pointer");
     FB_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % BK == 0, "fb_gemm_bf16: K must be a positive multiple of %d (got %d)", BK, K);
     FB_REQUIRE(N % 32 == 0, "fb_gemm_bf16: N must be a multiple of 32 (got %d)", N);
+    const int f16 = (mode & FB_GEMM_F16_FLAG) ? 1 : 0;
+    mode &= ~FB_GEMM_F16_FLAG;
     FB_REQUIRE(mode >= 0 && mode <= 3, "fb_gemm_bf16: unknown epilogue mode %d", mode);
     FB_REQUIRE(mode != FB_GEMM_BIAS_RESIDUAL_F32 || d_residual, "fb_gemm_bf16: residual pointer required");
     const int out_elt = (mode == FB_GEMM_BIAS_BF16 || mode == FB_GEMM_BIAS_GELU_BF16) ? 2 : 4;
@@ -438,7 +443,7 @@ int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long 
     FB_REQUIRE(!d_residual || ((reinterpret_cast<uintptr_t>(d_residual) & 15) == 0 && (ldr * 4) % 16 == 0), "fb_gemm_bf16: residual not aligned");
     GemmArgs p{};
     p.M = M; p.N = N; p.K = K; p.mode = mode; p.bias = d_bias; p.out = d_out; p.ldo = ldo;
-    p.residual = d_residual; p.ldr = ldr;
+    p.residual = d_residual; p.ldr = ldr; p.f16 = f16;
     return launch_gemm_common(d_a, lda, d_b, ldb, p, stream);
 }
 

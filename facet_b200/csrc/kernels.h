@@ -8,6 +8,7 @@
 #define FB_GEMM_BIAS_RESIDUAL_F32 2
 #define FB_GEMM_F32 3
 #define FB_GEMM_THRESHOLD_PAIRS 4
+#define FB_GEMM_F16_FLAG 16   /* OR into the mode: operands and 16-bit outputs are fp16 instead of bf16 */
 
 namespace fb {
 
@@ -44,12 +45,12 @@ int launch_cosine_recheck(const float* d_emb_f32, long long ld, int k, const int
                           long long cand_cap, float tau, int* d_pairs, float* d_sims, long long cap,
                           unsigned long long* d_count, cudaStream_t stream);
 int launch_f32_to_bf16(const float* d_in, void* d_out, long long n, cudaStream_t stream);
-int launch_im2col_patch14(const float* d_x, int batch, void* d_out, cudaStream_t stream);
+int launch_im2col_patch14(const float* d_x, int batch, void* d_out, int f16, cudaStream_t stream);
 int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
                      const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,
-                     cudaStream_t stream);
+                     cudaStream_t stream);   // out_bf16: 0 = fp32, 1 = bf16, 2 = fp16
 int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);      // mma.sync (legacy path)
-int launch_attention_tc(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);   // tcgen05
+int launch_attention_tc(const void* d_qkv, int batch, void* d_out, int f16, cudaStream_t stream);   // tcgen05
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -87,6 +88,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
+    return F16 ? make_idesc_f16(m, n, a_mn_major, b_mn_major) : make_idesc_bf16(m, n, a_mn_major, b_mn_major);
+}
 
 // Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes with the
 // 128-byte swizzle TMA produces (8-row groups of 1024 B): LBO = 1 (ignored), SBO = 1024 B,
@@ -113,6 +123,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) { return F16 ? pack_f16(a, b) : pack_bf16(a, b); }
+// the two 16-bit halves of a word as floats
+template <bool F16>
+__device__ __forceinline__ float lo16(uint32_t w) {
+    if (F16) return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+    return __uint_as_float(w << 16);
+}
+template <bool F16>
+__device__ __forceinline__ float hi16(uint32_t w) {
+    if (F16) return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+    return __uint_as_float(w & 0xffff0000u);
 }
 
 }  // namespace tc

@@ -10,6 +10,7 @@
 //                           MLP aesthetic head on the un-normalised features; tag similarities
 // The residual stream stays in fp32; GEMM inputs are bf16 (csrc/gemm.cu).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -26,8 +27,9 @@ constexpr int kPatchK = 588;      // 3 * 14 * 14
 constexpr int kPatchKPad = 640;
 
 // ---------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(256) im2col_patch14_kernel(const float* __restrict__ x, int batch,
-                                                             __nv_bfloat16* __restrict__ out) {
+                                                             uint32_t* __restrict__ out) {
     // out[(b*256 + py*16 + px)][k], k = c*196 + ky*14 + kx (conv weight [1024,3,14,14] flattened), zero padded to 640
     const long long total = (long long)batch * 256 * (kPatchKPad / 2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -46,15 +48,21 @@ __global__ void __launch_bounds__(256) im2col_patch14_kernel(const float* __rest
                 v[e] = __ldg(x + (((size_t)b * 3 + c) * 224 + y) * 224 + xx);
             }
         }
-        reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(v[0], v[1]);
+        if (F16) {
+            __half2 h2 = __floats2half2_rn(v[0], v[1]);
+            out[i] = *reinterpret_cast<uint32_t*>(&h2);
+        } else {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
+            out[i] = *reinterpret_cast<uint32_t*>(&b2);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over 1024 columns, one warp per row, eps = 1e-5 (two-pass, fp32).
 //   ASSEMBLE: the input row is built on the fly as (token 0 ? class_emb : patch_out[b, t-1]) + pos[t]
-//   OUT_BF16: bf16 output (GEMM operand) or fp32 output (residual stream)
-template <bool ASSEMBLE, bool OUT_BF16>
+//   OUT: 0 = fp32 output (residual stream), 1 = bf16, 2 = fp16 (GEMM operand)
+template <bool ASSEMBLE, int OUT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, long long ld_in, int rows,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const float* __restrict__ cls, const float* __restrict__ pos,
@@ -104,10 +112,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const float o1 = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
         const float o2 = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
         const float o3 = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
-        if (OUT_BF16) {
+        if (OUT == 1) {
             __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
             uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * ld_out + j * 128 + lane * 4) = pk;
+        } else if (OUT == 2) {
+            __half2 lo = __floats2half2_rn(o0, o1), hi = __floats2half2_rn(o2, o3);
+            uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (size_t)row * ld_out + j * 128 + lane * 4) = pk;
         } else {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * ld_out + j * 128 + lane * 4) =
                 make_float4(o0, o1, o2, o3);
@@ -362,12 +374,13 @@ __global__ void __launch_bounds__(768) vit_tail_kernel(const float* __restrict__
 
 }  // namespace
 
-int launch_im2col_patch14(const float* d_x, int batch, void* d_out, cudaStream_t stream) {
+int launch_im2col_patch14(const float* d_x, int batch, void* d_out, int f16, cudaStream_t stream) {
     FB_REQUIRE(d_x && d_out && batch >= 1, "fb_vit_im2col: bad arguments");
     const long long total = (long long)batch * 256 * (kPatchKPad / 2);
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 32) blocks = sm_count() * 32;
-    im2col_patch14_kernel<<<blocks, 256, 0, stream>>>(d_x, batch, reinterpret_cast<__nv_bfloat16*>(d_out));
+    if (f16) im2col_patch14_kernel<true><<<blocks, 256, 0, stream>>>(d_x, batch, reinterpret_cast<uint32_t*>(d_out));
+    else im2col_patch14_kernel<false><<<blocks, 256, 0, stream>>>(d_x, batch, reinterpret_cast<uint32_t*>(d_out));
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -379,11 +392,13 @@ int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* 
     const int blocks = (rows + 7) / 8;
     if (cls) {
         FB_REQUIRE(pos && !out_bf16, "fb_vit_layernorm: assembly mode writes the fp32 residual stream");
-        layernorm_kernel<true, false><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, cls, pos, d_out, ld_out);
-    } else if (out_bf16) {
-        layernorm_kernel<false, true><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, nullptr, nullptr, d_out, ld_out);
+        layernorm_kernel<true, 0><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, cls, pos, d_out, ld_out);
+    } else if (out_bf16 == 1) {
+        layernorm_kernel<false, 1><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, nullptr, nullptr, d_out, ld_out);
+    } else if (out_bf16 == 2) {
+        layernorm_kernel<false, 2><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, nullptr, nullptr, d_out, ld_out);
     } else {
-        layernorm_kernel<false, false><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, nullptr, nullptr, d_out, ld_out);
+        layernorm_kernel<false, 0><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, nullptr, nullptr, d_out, ld_out);
     }
     FB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -231,19 +231,20 @@ def gemm_bf16(a, b, mode: int = GEMM_F32, bias=None, residual=None, out=None):
     contiguous).  Returns bf16 (modes 0/1) or float32 (modes 2/3)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
-        raise TypeError("gemm_bf16 takes bf16 operands")
+    if a.dtype != b.dtype or a.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("gemm_bf16 takes two bf16 or two fp16 operands")
+    f16 = a.dtype == torch.float16
     if a.stride(-1) != 1 or b.stride(-1) != 1:
         raise ValueError("operands must be K-contiguous")
     m, k = a.shape
     n, kb = b.shape
     if k != kb:
         raise ValueError("K mismatch")
-    odt = torch.bfloat16 if mode in (GEMM_BIAS_BF16, GEMM_BIAS_GELU_BF16) else torch.float32
+    odt = a.dtype if mode in (GEMM_BIAS_BF16, GEMM_BIAS_GELU_BF16) else torch.float32
     if out is None:
         out = torch.empty((m, n), dtype=odt, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.check(lib.fb_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), m, n, k, int(mode),
+        _lib.check(lib.fb_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), m, n, k, int(mode) | (16 if f16 else 0),
                                     _ptr(bias) if bias is not None else None, _ptr(out), out.stride(0),
                                     _ptr(residual) if residual is not None else None,
                                     residual.stride(0) if residual is not None else 0, _lib.stream_ptr()), "fb_gemm_bf16")
@@ -251,15 +252,18 @@ def gemm_bf16(a, b, mode: int = GEMM_F32, bias=None, residual=None, out=None):
 
 
 def vit_layernorm(x, gamma, beta, out_bf16=True, class_emb=None, pos_emb=None, rows=None):
+    """out_bf16: False / 0 -> fp32, True / 1 -> bf16, 2 -> fp16."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     rows = int(rows if rows is not None else x.shape[0])
-    out = torch.empty((rows, 1024), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    out_bf16 = int(out_bf16)
+    odt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[out_bf16]
+    out = torch.empty((rows, 1024), dtype=odt, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.fb_vit_layernorm(_ptr(x), x.stride(0), rows, _ptr(gamma), _ptr(beta),
                                         _ptr(class_emb) if class_emb is not None else None,
                                         _ptr(pos_emb) if pos_emb is not None else None, _ptr(out), 1024,
-                                        int(bool(out_bf16)), _lib.stream_ptr()), "fb_vit_layernorm")
+                                        out_bf16, _lib.stream_ptr()), "fb_vit_layernorm")
     return out
 
 
@@ -268,8 +272,11 @@ def vit_attention(qkv, batch: int, legacy_mma: bool = False):
     mma.sync variant kept for A/B checks)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    out = torch.empty((batch * 257, 1024), dtype=torch.bfloat16, device=qkv.device)
-    fn = lib.fb_vit_attention_mma if legacy_mma else lib.fb_vit_attention
+    out = torch.empty((batch * 257, 1024), dtype=qkv.dtype, device=qkv.device)
+    if qkv.dtype == torch.float16:
+        fn = lib.fb_vit_attention_f16
+    else:
+        fn = lib.fb_vit_attention_mma if legacy_mma else lib.fb_vit_attention
     with torch.cuda.device(qkv.device):
         _lib.check(fn(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
     return out

@@ -151,6 +151,7 @@ int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, i
 #define FB_GEMM_BIAS_GELU_BF16 1
 #define FB_GEMM_BIAS_RESIDUAL_F32 2
 #define FB_GEMM_F32 3
+#define FB_GEMM_F16_FLAG 16   /* OR into mode: operands and 16-bit outputs are IEEE fp16 instead of bf16 */
 int fb_gemm_bf16(const void* d_a, int64_t lda, const void* d_b, int64_t ldb, int m, int n, int k, int mode,
                  const float* d_bias, void* d_out, int64_t ldo, const float* d_residual, int64_t ldr,
                  void* stream);
@@ -175,6 +176,8 @@ typedef struct fb_vit_weights {
     const float *head_w2, *head_b2;            /* Linear(256,1): [256], [1] */
     const float *tag_emb;                      /* [n_tags][768] L2-normalised text embeddings (tagger.py:73) or NULL */
     int n_tags;
+    int f16;                                   /* 0: 16-bit weights/activations are bf16; 1: IEEE fp16 (the reference runs
+                                                  `.half()` on CUDA, processing/scorer.py:515) */
     int n_layers;                              /* 24 */
     const fb_vit_layer *layers;                /* HOST array of n_layers entries */
 } fb_vit_weights;
@@ -193,8 +196,9 @@ int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, v
 int fb_vit_im2col(const float* d_clip_in, int batch, void* d_out_bf16, void* stream);
 int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* gamma, const float* beta,
                      const float* class_emb, const float* pos_emb, void* d_out, int64_t ld_out,
-                     int out_bf16, void* stream);
+                     int out_bf16 /* 0 fp32, 1 bf16, 2 fp16 */, void* stream);
 int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);      /* tcgen05 */
+int fb_vit_attention_f16(const void* d_qkv_f16, int batch, void* d_out_f16, void* stream);     /* tcgen05, fp16 operands */
 int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);  /* mma.sync variant, kept for A/B checks */
 
 #ifdef __cplusplus

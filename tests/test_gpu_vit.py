@@ -6,18 +6,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _rand_bf16(shape, seed, scale=1.0):
+def _rand_bf16(shape, seed, scale=1.0, dtype=None):
     import torch
     g = torch.Generator(device="cuda").manual_seed(seed)
-    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(dtype or torch.bfloat16)
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 256, 128), (1000, 768, 1024), (257 * 8, 3072, 1024),
                                    (2056, 1024, 4096), (129, 32, 640), (4096, 1024, 640)])
-def test_gemm_all_epilogues(m, n, k):
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_gemm_all_epilogues(m, n, k, dt):
     import torch
     from facet_b200 import ops
-    a, b = _rand_bf16((m, k), 1), _rand_bf16((n, k), 2, scale=k ** -0.5)
+    dtype = torch.float16 if dt == "fp16" else torch.bfloat16
+    a, b = _rand_bf16((m, k), 1, dtype=dtype), _rand_bf16((n, k), 2, scale=k ** -0.5, dtype=dtype)
     bias = torch.randn(n, device="cuda")
     res = torch.randn(m, n, device="cuda")
     ref = a.float() @ b.float().T
@@ -48,35 +50,39 @@ def test_layernorm_and_assembly():
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("legacy", [False, True])
-def test_attention_vs_torch(legacy):
+@pytest.mark.parametrize("variant", ["tcgen05-bf16", "tcgen05-fp16", "mma-bf16"])
+def test_attention_vs_torch(variant):
     import torch
     from facet_b200 import ops
     bsz = 3
-    qkv = _rand_bf16((bsz * 257, 3072), 5, scale=1.5)
-    got = ops.vit_attention(qkv, bsz, legacy_mma=legacy).float().reshape(bsz, 257, 16, 64)
+    qkv = _rand_bf16((bsz * 257, 3072), 5, scale=1.5, dtype=torch.float16 if variant.endswith("fp16") else None)
+    got = ops.vit_attention(qkv, bsz, legacy_mma=variant.startswith("mma")).float().reshape(bsz, 257, 16, 64)
     q, k, v = qkv.float().reshape(bsz, 257, 3, 16, 64).unbind(2)
     att = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125, dim=-1)
     ref = torch.einsum("bhqk,bkhd->bqhd", att, v)
     torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
 
 
-def test_vit_tower_vs_fp32_oracle():
+@pytest.mark.parametrize("dt,aest_tol", [("fp16", 0.01), ("bf16", 0.03)])
+def test_vit_tower_vs_fp32_oracle(dt, aest_tol):
+    """north_star tolerances: cosine >= 0.999 and aesthetic within 0.01 — met by the default fp16 mode (the
+    reference's own CUDA precision).  bf16 keeps the cosine bound; its 8-bit mantissa leaves ~0.004 mean /
+    ~0.013 max aesthetic noise on this random-init head, hence the looser bound for that variant."""
     import torch
     from facet_b200.models.clip_vit import ClipVitL14, random_state_dict
     from oracle import vit_torch
     sd = random_state_dict(0)
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(4, 3, 224, 224, generator=g)
+    x = torch.randn(8, 3, 224, 224, generator=g)
     tags = torch.nn.functional.normalize(torch.randn(240, 768, generator=torch.Generator().manual_seed(7)), dim=-1)
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     ref = vit_torch.score_batch(sd_gpu, x.cuda(), tags.cuda())       # fp32 oracle (TF32 off by default)
-    model = ClipVitL14(sd, tag_embeddings=tags.numpy())
+    model = ClipVitL14(sd, tag_embeddings=tags.numpy(), dtype=dt)
     out = model.encode(x.cuda())
     cos = torch.nn.functional.cosine_similarity(out["embedding"], ref["embedding"], dim=-1)
     assert float(cos.min()) >= 0.999, cos
     aest = ((out["aesthetic_raw"] + 1) * 5).clamp(0, 10)
-    assert float((aest - ref["aesthetic"]).abs().max()) <= 0.01, (aest, ref["aesthetic"])
+    assert float((aest - ref["aesthetic"]).abs().max()) <= aest_tol, (aest, ref["aesthetic"])
     assert float((out["tag_sims"] - ref["tag_sims"]).abs().max()) <= 5e-3
     nrm = out["embedding"].norm(dim=-1)
     torch.testing.assert_close(nrm, torch.ones_like(nrm), rtol=1e-5, atol=1e-5)
