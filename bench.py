@@ -212,6 +212,9 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry one JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
 
@@ -257,47 +260,43 @@ def main():
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- per-kernel device times of the same step (events around each stage, same stream) ---------------
-    def timed(fn, reps=3):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            r = fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps, r
-
-    ms_tech, _ = timed(lambda: ops.tech_stats_raw(pool))
-    ms_pre, clip_in = timed(lambda: ops.clip_preprocess(pool))
-    ms_vit, _ = timed(lambda: scorer.model.encode(clip_in))
+    # ---- per-kernel device times of the SAME steps: the library records a CUDA-event pair around each of
+    # its launches on the launching stream (fb_profile_*); K more steps, identical inputs -------------------
+    _lib.profile_enable(True)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(args.steps):
+        step()
+    pe1.record()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    ms_step_profiled = pe0.elapsed_time(pe1) / args.steps
+    per_step = {k: (v[0] / args.steps, v[1] // args.steps) for k, v in prof.items() if v[1]}
+    ms_tech, ms_pre = per_step["technical"][0], per_step["preprocess"][0]
+    ms_vit = sum(per_step[k][0] for k in ("im2col", "gemm", "layernorm", "attention", "vit_tail") if k in per_step)
+    gemm_ms, gemm_launches = per_step["gemm"]
     stages = {"technical_ms": ms_tech, "preprocess_ms": ms_pre, "vit_ms": ms_vit,
+              "kernel_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
+              "launches_per_step": {k: v[1] for k, v in per_step.items()},
+              "step_ms_with_event_pairs": ms_step_profiled,
               "technical_gbs": B * TECH_BYTES_PER_IMAGE / (ms_tech * 1e-3) / 1e9,
               "vit_tflops": B * GFLOP_PER_IMAGE * 1e9 / (ms_vit * 1e-3) / 1e12}
-    # the dominant kernel of the step: the tcgen05 GEMM (98 launches per ViT forward); timed per launch shape
-    M = B * 257
-    gemm_ms = 0.0
-    for (m, n, k, reps_in_fwd, mode) in [(B * 256, 1024, 640, 1, ops.GEMM_F32), (M, 3072, 1024, 24, ops.GEMM_BIAS_BF16),
-                                        (M, 1024, 1024, 24, ops.GEMM_BIAS_RESIDUAL_F32), (M, 4096, 1024, 24, ops.GEMM_BIAS_GELU_BF16),
-                                        (M, 1024, 4096, 24, ops.GEMM_BIAS_RESIDUAL_F32)]:
-        a = torch.randn(m, k, device=device).to(torch.float16)
-        w = (torch.randn(n, k, device=device) * k ** -0.5).to(torch.float16)
-        bias = torch.zeros(n, device=device)
-        f32_out = mode in (ops.GEMM_F32, ops.GEMM_BIAS_RESIDUAL_F32)
-        o = torch.zeros((m, n), device=device, dtype=torch.float32 if f32_out else torch.float16)
-        res = o if mode == ops.GEMM_BIAS_RESIDUAL_F32 else None      # in place, as the forward pass does
-        ms, _ = timed(lambda: ops.gemm_bf16(a, w, mode, bias=bias, residual=res, out=o), reps=5)
-        gemm_ms += ms * reps_in_fwd
-        del a, w, o
     peaks = measured_peaks()
     gemm_tflops = B * GEMM_GFLOP_PER_IMAGE * 1e9 / (gemm_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, 97 launches per step)",
+    # DRAM traffic of the GEMM launches of one layer at batch 128, from profiles/r1_gemm_ncu.txt (ncu --set full)
+    traffic_per_layer_b128 = (436.5 + 108.1 + 73.7 + 155.5 + 204.3 + 86.2 + 75.8 + 221.0) * 1e6
+    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05), {gemm_launches} launches per step",
                 "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                "share_of_step": gemm_ms / ms_step,
+                "frac": gemm_tflops / peaks["bf16_tflops"],
+                "traffic": (24 * traffic_per_layer_b128 * B / 128) if world >= 1 else None,
+                "traffic_note": "bytes per step, scaled from the ncu capture at batch 128 (24 layers x 4 launches)",
+                "algorithmic_flops_per_step": B * GEMM_GFLOP_PER_IMAGE * 1e9, "kernel_ms_per_step": gemm_ms,
+                "timing": "CUDA-event pairs around every launch of the kernel, on the launching stream, over K steps",
+                "peak_source": peaks["source"], "share_of_step": gemm_ms / ms_step_profiled,
                 "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
-                                     "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"]}}
+                                     "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"],
+                                     "algorithmic_bytes_per_step": B * TECH_BYTES_PER_IMAGE,
+                                     "traffic": 592.0e6 / 8 * B, "traffic_note": "ncu dram bytes read, 8-frame capture scaled"}}
 
     # ---- e2e: pinned host frames -> pipeline (H2D + kernels + D2H inside the timed region) ---------------
     e2e = None

@@ -23,6 +23,8 @@ _SIGNATURES = {
     "fb_last_error": (C.c_char_p, []),
     "fb_launch_count": (C.c_uint64, []),
     "fb_device_sm_count": (C.c_int, []),
+    "fb_profile_enable": (None, [C.c_int]),
+    "fb_profile_read": (C.c_int, [_P, _P, C.c_int]),
     "fb_tech_stats": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
     "fb_tech_derive": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_tech_stats_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
@@ -97,6 +99,23 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().fb_launch_count())
+
+
+PROFILE_CATEGORIES = ("technical", "hs_derive", "preprocess", "im2col", "gemm", "layernorm", "attention", "vit_tail",
+                      "cosine", "hamming", "other")
+
+
+def profile_enable(on: bool):
+    load().fb_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{category: (milliseconds, launches)} recorded since profile_enable(True); synchronises the device."""
+    n = len(PROFILE_CATEGORIES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    check(load().fb_profile_read(C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p), n), "fb_profile_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROFILE_CATEGORIES)}
 
 
 def require_cuda():

@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../../include/facet_b200.h"
 #include "common.cuh"
@@ -26,6 +28,35 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 void count_launch(int k) { g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
 
+// ---- event-pair profiler -----------------------------------------------------------------------------
+namespace {
+struct ProfState {
+    std::mutex mu;
+    bool on = false;
+    std::vector<cudaEvent_t> ev;     // pairs: [2*i] begin, [2*i+1] end
+    std::vector<int> cat;
+    size_t used = 0;
+} g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int c, cudaStream_t st) : slot(-1), stream(st) {
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (g_prof.used == g_prof.cat.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        g_prof.ev.push_back(a);
+        g_prof.ev.push_back(b);
+        g_prof.cat.push_back(c);
+    }
+    slot = (int)g_prof.used++;
+    g_prof.cat[slot] = c;
+    cudaEventRecord(g_prof.ev[2 * slot], stream);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+}
+
 int sm_count() {
     static int cached = 0;
     if (cached == 0) {
@@ -49,8 +80,34 @@ const char* fb_last_error(void) { return get_error(); }
 uint64_t fb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int fb_device_sm_count(void) { return sm_count(); }
 
+void fb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+}
+
+int fb_profile_read(double* ms_per_category, uint64_t* launches_per_category, int n_categories) {
+    FB_REQUIRE(ms_per_category && launches_per_category && n_categories >= PROF_NCAT, "fb_profile_read: need %d categories", (int)PROF_NCAT);
+    FB_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (int i = 0; i < n_categories; ++i) {
+        ms_per_category[i] = 0.0;
+        launches_per_category[i] = 0;
+    }
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
+            ms_per_category[g_prof.cat[i]] += ms;
+            launches_per_category[g_prof.cat[i]] += 1;
+        }
+    }
+    g_prof.used = 0;
+    return 0;
+}
+
 int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
                   uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, int force_generic, void* stream) {
+    ProfScope ps(PROF_TECH, (cudaStream_t)stream);
     int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
                                reinterpret_cast<long long*>(d_sums), force_generic, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
@@ -58,6 +115,7 @@ int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t
 }
 
 int fb_tech_derive(const uint32_t* d_hs_hist, int n, double* d_out, void* stream) {
+    ProfScope ps(PROF_DERIVE, (cudaStream_t)stream);
     int rc = launch_hs_derive(d_hs_hist, n, d_out, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
@@ -135,6 +193,7 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
                        int out_size, const int32_t* d_hp0, const int32_t* d_hcpad, int hgroups, int h_px_lo,
                        int h_span_px, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk, int row0, int rows,
                        const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out, void* stream) {
+    ProfScope ps(PROF_PREPROCESS, (cudaStream_t)stream);
     int rc = launch_clip_preprocess(d_images, n, height, width, (long long)image_stride, rgb_order, out_size, d_hp0,
                                     d_hcpad, hgroups, h_px_lo, h_span_px, d_vbounds, d_vcoef, vk, row0, rows, mean3, std3,
                                     d_tmp, d_out, (cudaStream_t)stream);
@@ -144,6 +203,7 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
 
 int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts, int32_t* d_pairs,
                      int64_t cap, uint64_t* d_count, void* stream) {
+    ProfScope ps(PROF_HAMMING, (cudaStream_t)stream);
     int rc = launch_hamming_pairs(reinterpret_cast<const unsigned long long*>(d_hashes), (long long)n, max_distance,
                                   part, nparts, d_pairs, (long long)cap,
                                   reinterpret_cast<unsigned long long*>(d_count), (cudaStream_t)stream);
@@ -164,6 +224,7 @@ int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint
 
 int fb_gemm_bf16(const void* d_a, int64_t lda, const void* d_b, int64_t ldb, int m, int n, int k, int mode,
                  const float* d_bias, void* d_out, int64_t ldo, const float* d_residual, int64_t ldr, void* stream) {
+    ProfScope ps(PROF_GEMM, (cudaStream_t)stream);
     int rc = launch_gemm_bf16(d_a, lda, d_b, ldb, m, n, k, mode, d_bias, d_out, ldo, d_residual, ldr, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
@@ -184,6 +245,7 @@ int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, i
     FB_CUDA_OK(cudaMemsetAsync(d_cand_count, 0, sizeof(uint64_t), st));
     FB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     if (rows <= 0 || n < 2) return 0;
+    ProfScope ps(PROF_COSINE, st);
     int rc = launch_cosine_candidates(d_emb_bf16, dim, (int)n, (int)row_offset, (int)rows, dim, tau - band, d_cand, d_cand_sims,
                                       (long long)cand_cap, reinterpret_cast<unsigned long long*>(d_cand_count), st);
     if (rc) return rc;

@@ -54,7 +54,23 @@ struct GemmArgs {
     int f16;              // operands (and 16-bit outputs) are fp16 instead of bf16
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact (erf) GELU, nn.GELU() of the reference tower.  erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
+// i.e. fp32 noise; checked against scipy over [-8, 8]): 2 MUFU + 9 FMA instead of erff's ~45 instructions.
+//   0.5 x (1 + erf(x / sqrt 2)) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2)
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float hx = 0.5f * x;
+    return fmaf(fabsf(hx), fmaf(-p, e, 1.0f), hx);
+}
 
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)

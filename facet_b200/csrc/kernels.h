@@ -55,6 +55,17 @@ int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream);
 void count_launch(int k);
+
+// Optional per-category CUDA-event timing of the library's launches (bench.py roofline): when enabled every
+// launch wrapper records an event pair on the launching stream; fb_profile_read() turns them into milliseconds.
+enum ProfCat { PROF_TECH = 0, PROF_DERIVE, PROF_PREPROCESS, PROF_IM2COL, PROF_GEMM, PROF_LAYERNORM, PROF_ATTENTION,
+               PROF_TAIL, PROF_COSINE, PROF_HAMMING, PROF_OTHER, PROF_NCAT };
+struct ProfScope {
+    ProfScope(int cat, cudaStream_t st);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
 size_t vit_workspace_bytes(int batch);
 
 }  // namespace fb

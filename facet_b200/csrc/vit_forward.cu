@@ -53,37 +53,40 @@ int vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void
     const int ln_out = f16 ? 2 : 1;
     static const bool legacy_attn = getenv("FB_ATTN_LEGACY") != nullptr;   // A/B switch: mma.sync attention
     int rc;
-#define STEP(call, n)          \
-    do {                       \
-        rc = (call);           \
-        if (rc) return rc;     \
-        count_launch(n);       \
+#define STEP_CAT(cat, call, n)          \
+    do {                                \
+        {                               \
+            ProfScope ps_(cat, st);     \
+            rc = (call);                \
+        }                               \
+        if (rc) return rc;              \
+        count_launch(n);                \
     } while (0)
     // patch embedding: im2col (aliases qkv) -> GEMM -> fp32 [B*256][1024] (aliases h)
-    STEP(launch_im2col_patch14(d_clip_in, batch, ws.qkv, f16, st), 1);
-    STEP(launch_gemm_bf16(ws.qkv, kPatchKPad, w->w_patch, kPatchKPad, batch * 256, kWidth, kPatchKPad, FB_GEMM_F32 | gflag, nullptr,
+    STEP_CAT(PROF_IM2COL, launch_im2col_patch14(d_clip_in, batch, ws.qkv, f16, st), 1);
+    STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.qkv, kPatchKPad, w->w_patch, kPatchKPad, batch * 256, kWidth, kPatchKPad, FB_GEMM_F32 | gflag, nullptr,
                           ws.h, kWidth, nullptr, 0, st), 1);
     // class token + positional embedding + ln_pre -> residual stream
-    STEP(launch_layernorm(reinterpret_cast<const float*>(ws.h), kWidth, M, w->ln_pre_g, w->ln_pre_b, w->class_emb,
+    STEP_CAT(PROF_LAYERNORM, launch_layernorm(reinterpret_cast<const float*>(ws.h), kWidth, M, w->ln_pre_g, w->ln_pre_b, w->class_emb,
                           w->pos_emb, ws.x, kWidth, 0, st), 1);
     for (int l = 0; l < w->n_layers; ++l) {
         const fb_vit_layer& L = w->layers[l];
-        STEP(launch_layernorm(ws.x, kWidth, M, L.ln1_g, L.ln1_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);
-        STEP(launch_gemm_bf16(ws.xn, kWidth, L.w_qkv, kWidth, M, 3 * kWidth, kWidth, FB_GEMM_BIAS_BF16 | gflag, L.b_qkv, ws.qkv,
+        STEP_CAT(PROF_LAYERNORM, launch_layernorm(ws.x, kWidth, M, L.ln1_g, L.ln1_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);
+        STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.xn, kWidth, L.w_qkv, kWidth, M, 3 * kWidth, kWidth, FB_GEMM_BIAS_BF16 | gflag, L.b_qkv, ws.qkv,
                               3 * kWidth, nullptr, 0, st), 1);
-        if (legacy_attn && !f16) STEP(launch_attention(ws.qkv, batch, ws.attn, st), 1);
-        else STEP(launch_attention_tc(ws.qkv, batch, ws.attn, f16, st), 1);
-        STEP(launch_gemm_bf16(ws.attn, kWidth, L.w_out, kWidth, M, kWidth, kWidth, FB_GEMM_BIAS_RESIDUAL_F32 | gflag, L.b_out, ws.x,
+        if (legacy_attn && !f16) STEP_CAT(PROF_ATTENTION, launch_attention(ws.qkv, batch, ws.attn, st), 1);
+        else STEP_CAT(PROF_ATTENTION, launch_attention_tc(ws.qkv, batch, ws.attn, f16, st), 1);
+        STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.attn, kWidth, L.w_out, kWidth, M, kWidth, kWidth, FB_GEMM_BIAS_RESIDUAL_F32 | gflag, L.b_out, ws.x,
                               kWidth, ws.x, kWidth, st), 1);
-        STEP(launch_layernorm(ws.x, kWidth, M, L.ln2_g, L.ln2_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);
-        STEP(launch_gemm_bf16(ws.xn, kWidth, L.w_fc, kWidth, M, kMlp, kWidth, FB_GEMM_BIAS_GELU_BF16 | gflag, L.b_fc, ws.h, kMlp,
+        STEP_CAT(PROF_LAYERNORM, launch_layernorm(ws.x, kWidth, M, L.ln2_g, L.ln2_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);
+        STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.xn, kWidth, L.w_fc, kWidth, M, kMlp, kWidth, FB_GEMM_BIAS_GELU_BF16 | gflag, L.b_fc, ws.h, kMlp,
                               nullptr, 0, st), 1);
-        STEP(launch_gemm_bf16(ws.h, kMlp, L.w_proj, kMlp, M, kWidth, kMlp, FB_GEMM_BIAS_RESIDUAL_F32 | gflag, L.b_proj, ws.x, kWidth,
+        STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.h, kMlp, L.w_proj, kMlp, M, kWidth, kMlp, FB_GEMM_BIAS_RESIDUAL_F32 | gflag, L.b_proj, ws.x, kWidth,
                               ws.x, kWidth, st), 1);
     }
-    STEP(launch_vit_tail(ws.x, batch, w->ln_post_g, w->ln_post_b, w->proj, w->head_w1, w->head_b1, w->head_w2, w->head_b2,
+    STEP_CAT(PROF_TAIL, launch_vit_tail(ws.x, batch, w->ln_post_g, w->ln_post_b, w->proj, w->head_w1, w->head_b1, w->head_w2, w->head_b2,
                          w->tag_emb, w->n_tags, d_features, d_embedding, d_aesthetic_raw, d_tag_sims, st), 1);
-#undef STEP
+#undef STEP_CAT
     return 0;
 }
 

@@ -29,6 +29,15 @@ const char* fb_last_error(void);
 uint64_t fb_launch_count(void);
 int fb_device_sm_count(void);
 
+/* Optional CUDA-event timing of the library's own launches, per kernel family, on the launching stream
+ * (used by bench.py for the roofline of the timed region).  Categories: 0 technical, 1 hs-derive,
+ * 2 preprocess, 3 im2col, 4 tcgen05 GEMM, 5 layernorm, 6 attention, 7 ViT tail, 8 cosine stage,
+ * 9 hamming/burst, 10 other.  fb_profile_read synchronises the device, fills the two arrays
+ * (>= FB_PROFILE_CATEGORIES entries) and resets the recording. */
+#define FB_PROFILE_CATEGORIES 11
+void fb_profile_enable(int on);
+int fb_profile_read(double* ms_per_category, uint64_t* launches_per_category, int n_categories);
+
 /* ---------------------------------------------------------------------------------------
  * Technical metrics — replaces analyzers/image_cache.py:22-32 (ImageCache: gray, hsv,
  * Laplacian variance) and the pixel passes of analyzers/technical.py:94 (H-S calcHist),
