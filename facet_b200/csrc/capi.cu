@@ -201,6 +201,16 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
     return rc;
 }
 
+int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+             const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
+             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, void* stream) {
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    int rc = launch_phash(d_images, n, height, width, (long long)image_stride, rgb_order, d_hbounds, d_hcoef, hk, d_vbounds,
+                          d_vcoef, vk, d_tmp, reinterpret_cast<unsigned long long*>(d_hashes), d_small, d_dct, (cudaStream_t)stream);
+    if (rc == 0) count_launch(2);
+    return rc;
+}
+
 int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts, int32_t* d_pairs,
                      int64_t cap, uint64_t* d_count, void* stream) {
     ProfScope ps(PROF_HAMMING, (cudaStream_t)stream);

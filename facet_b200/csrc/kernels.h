@@ -32,6 +32,9 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                            int h_span_px, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
                            const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
                            cudaStream_t stream);
+int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order, const int* d_hbounds,
+                 const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
+                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
 

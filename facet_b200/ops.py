@@ -315,3 +315,38 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
             if nc <= cap and m <= cap:
                 return pairs[:m], sims[:m]
             cap = max(nc, m)
+
+
+_PHASH_PLANS: dict = {}
+
+
+def phash(images, rgb_order: bool = False, debug: bool = False):
+    """64-bit perceptual hashes (imagehash.phash) of a same-shaped batch.  Returns a uint64 numpy array
+    (and, with debug=True, the 32x32 uint8 luma thumbnails and the 8x8 float64 DCT blocks)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    from .utils import resample as rs
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    key = (h, w, str(t.device))
+    if key not in _PHASH_PLANS:
+        hb, hc, hk, vb, vc, vk = rs.phash_plan(h, w)
+        _PHASH_PLANS[key] = tuple(torch.from_numpy(a).to(t.device) for a in (hb, hc, vb, vc)) + (hk, vk)
+    hb, hc, vb, vc, hk, vk = _PHASH_PLANS[key]
+    tmp = torch.empty((n, h, 32), dtype=torch.uint8, device=t.device)
+    hashes = torch.empty((n,), dtype=torch.int64, device=t.device)
+    small = torch.empty((n, 32, 32), dtype=torch.uint8, device=t.device) if debug else None
+    dct = torch.empty((n, 64), dtype=torch.float64, device=t.device) if debug else None
+    with torch.cuda.device(t.device):
+        _lib.check(lib.fb_phash(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hb), _ptr(hc), hk, _ptr(vb), _ptr(vc), vk,
+                                _ptr(tmp), _ptr(hashes), _ptr(small) if debug else None, _ptr(dct) if debug else None,
+                                _lib.stream_ptr()), "fb_phash")
+    out = hashes.cpu().numpy().view(np.uint64)
+    if debug:
+        return out, small.cpu().numpy(), dct.cpu().numpy().reshape(n, 8, 8)
+    return out
+
+
+def phash_hex(images, rgb_order: bool = False):
+    """str(imagehash.phash(img)) for each frame: 16 lowercase hex digits."""
+    return ["%016x" % int(v) for v in phash(images, rgb_order=rgb_order)]

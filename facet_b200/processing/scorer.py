@@ -90,12 +90,13 @@ class Facet:
         vit = self.model.encode(clip_in)
         return {"hist256": hist, "sums": sums, "derived": derived, **vit}
 
-    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5):
+    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True):
         """Full per-image pass for a same-shaped batch -> list of result dicts with the reference's
         metric keys (processing/batch_processor.py:298-355, the analyzer-derived subset)."""
         t = ops.to_device_u8(images)
         n, h, w, _ = t.shape
         dev = self.score_images_device(t, rgb_order=rgb_order)
+        hashes = ops.phash_hex(t, rgb_order=rgb_order) if with_phash else [None] * n      # batch_processor.py:216
         hist = dev["hist256"].cpu().numpy().view(np.uint32).astype(np.int64)
         sums = dev["sums"].cpu().numpy()
         der = dev["derived"].cpu().numpy()
@@ -130,6 +131,6 @@ class Facet:
                 "is_monochrome": mono["is_monochrome"], "mean_saturation": mono["mean_saturation"],
                 "dynamic_range_stops": dr["dynamic_range_stops"], "noise_sigma": nz["noise_sigma"],
                 "contrast_score": ct["contrast_score"],
-                "tags": tags, "quality_score": None, "scoring_model": "clip-mlp",
+                "tags": tags, "quality_score": None, "scoring_model": "clip-mlp", "phash": hashes[i],
             })
         return results

@@ -36,14 +36,29 @@ def _bicubic(x: np.ndarray) -> np.ndarray:
     return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
 
 
-def precompute_coeffs(in_size: int, out_size: int):
-    """Pillow precompute_coeffs + normalize_coeffs_8bpc for box (0, in_size), bicubic.
+def _lanczos(x: np.ndarray) -> np.ndarray:
+    """Pillow lanczos_filter (support 3): sinc(x) * sinc(x / 3) on [-3, 3)."""
+    def sinc(v):
+        out = np.ones_like(v)
+        nz = v != 0.0
+        out[nz] = np.sin(np.pi * v[nz]) / (np.pi * v[nz])
+        return out
+    x = np.asarray(x, dtype=np.float64)
+    return np.where((x >= -3.0) & (x < 3.0), sinc(x) * sinc(x / 3.0), 0.0)
+
+
+LANCZOS_SUPPORT = 3.0
+
+
+def precompute_coeffs(in_size: int, out_size: int, kernel: str = "bicubic"):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for box (0, in_size), bicubic or lanczos.
 
     Returns (bounds int32 [out,2] = first tap / tap count, coef int32 [out,ksize], ksize).
     """
+    filt, base_support = (_bicubic, BICUBIC_SUPPORT) if kernel == "bicubic" else (_lanczos, LANCZOS_SUPPORT)
     scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
     filterscale = max(scale, 1.0)
-    support = BICUBIC_SUPPORT * filterscale
+    support = base_support * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     ss = 1.0 / filterscale
     bounds = np.zeros((out_size, 2), np.int32)
@@ -55,7 +70,7 @@ def precompute_coeffs(in_size: int, out_size: int):
         xmax = int(center + support + 0.5)
         xmax = min(xmax, in_size)
         cnt = xmax - xmin
-        w = _bicubic((np.arange(cnt, dtype=np.float64) + xmin - center + 0.5) * ss)
+        w = filt((np.arange(cnt, dtype=np.float64) + xmin - center + 0.5) * ss)
         ww = 0.0
         for v in w:            # sequential double accumulation, as in C
             ww += float(v)
@@ -143,3 +158,12 @@ def resample_reference_numpy(img_rgb: np.ndarray, out: int = 224) -> np.ndarray:
         acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(p.vcoef[yo, :c].astype(np.int64), t64[f:f + c], axes=([0], [0]))
         res[yo] = np.clip(acc >> PRECISION_BITS, 0, 255)
     return res
+
+
+@lru_cache(maxsize=64)
+def phash_plan(height: int, width: int, size: int = 32):
+    """Lanczos tables of imagehash.phash's `resize((32, 32), ANTIALIAS)` for an HxW luma image:
+    (hbounds, hcoef, hk, vbounds, vcoef, vk)."""
+    hb, hc, hk = precompute_coeffs(width, size, "lanczos")
+    vb, vc, vk = precompute_coeffs(height, size, "lanczos")
+    return (np.ascontiguousarray(hb), np.ascontiguousarray(hc), hk, np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk)

@@ -107,6 +107,18 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
                        uint8_t* d_tmp, float* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Perceptual hash — replaces `imagehash.phash(pil_img)` (processing/batch_processor.py:216,
+ * processing/scorer.py:972, processing/multi_pass.py:449): Pillow convert('L') -> resize((32,32), LANCZOS)
+ * -> 2-D DCT-II -> top-left 8x8 > median, 64 bits row-major MSB first (str(ImageHash) = "%016x").
+ * Coefficient tables ([32][2] bounds + [32][k] int32 taps per axis, Pillow's Lanczos taps) come from
+ * facet_b200/utils/resample.py.  d_tmp scratch [n][height][32] uint8.  d_small ([n][32][32] uint8, the
+ * resized luma) and d_dct ([n][64] float64, the low-frequency block) are optional debug outputs. */
+int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+             const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
+             const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
+             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Duplicate / burst grouping — replaces the O(N^2) loop of utils/duplicate.py:94-119 and the
  * pairwise predicate of processing/scorer.py:1943-1968.
  *

@@ -1,0 +1,38 @@
+"""GPU parity of the perceptual hash against Pillow + scipy (the libraries imagehash.phash calls)."""
+import numpy as np
+import pytest
+
+from facet_b200.synth import synth_image_bgr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(683, 1024), (1024, 683), (97, 131), (400, 600), (33, 35), (2000, 3000)])
+def test_phash_matches_pillow_scipy(shape):
+    from facet_b200 import ops
+    from oracle import phash as op
+    h, w = shape
+    imgs = np.stack([synth_image_bgr(i, h, w) for i in range(6)])
+    hashes, small, dct = ops.phash(imgs, debug=True)
+    hexes = ops.phash_hex(imgs)
+    for i in range(len(imgs)):
+        ref_small, ref_low, ref_val = op.phash_parts(imgs[i])
+        assert np.array_equal(small[i], ref_small), "32x32 luma thumbnail must be bit-exact with Pillow"
+        np.testing.assert_allclose(dct[i], ref_low, rtol=1e-9, atol=1e-6)
+        # bits can only differ where a coefficient sits within float64 noise of the median
+        med = np.median(ref_low)
+        safe = np.abs(ref_low - med).flatten() > 1e-6
+        got_bits = np.array([(int(hashes[i]) >> (63 - k)) & 1 for k in range(64)])
+        want_bits = np.array([(ref_val >> (63 - k)) & 1 for k in range(64)])
+        assert np.array_equal(got_bits[safe], want_bits[safe])
+        if safe.all():
+            assert hexes[i] == op.phash_hex(imgs[i])
+    # RGB-order input gives the same hash
+    assert np.array_equal(ops.phash(np.ascontiguousarray(imgs[..., ::-1]), rgb_order=True), hashes)
+
+
+def test_phash_24mp():
+    from facet_b200 import ops
+    from oracle import phash as op
+    img = synth_image_bgr(4, 4000, 6000)
+    assert ops.phash_hex(img[None])[0] == op.phash_hex(img)
