@@ -32,7 +32,7 @@ _SIGNATURES = {
     "fb_roi_laplacian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "fb_clip_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
                                      _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int,
-                                     _P, _P, _P, _P, _P]),
+                                     _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_phash": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int,
                            _P, _P, _P, _P, _P]),
     "fb_hamming_pairs": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),

@@ -192,11 +192,12 @@ int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_orde
 int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
                        int out_size, const int32_t* d_hp0, const int32_t* d_hcpad, int hgroups, int h_px_lo,
                        int h_span_px, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk, int row0, int rows,
-                       const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out, void* stream) {
+                       const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
+                       const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0, void* stream) {
     ProfScope ps(PROF_PREPROCESS, (cudaStream_t)stream);
     int rc = launch_clip_preprocess(d_images, n, height, width, (long long)image_stride, rgb_order, out_size, d_hp0,
                                     d_hcpad, hgroups, h_px_lo, h_span_px, d_vbounds, d_vcoef, vk, row0, rows, mean3, std3,
-                                    d_tmp, d_out, (cudaStream_t)stream);
+                                    d_tmp, d_out, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, (cudaStream_t)stream);
     if (rc == 0) count_launch(2);
     return rc;
 }

@@ -195,7 +195,7 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                            int out_size, const int* d_hp0, const int* d_hcpad, int hgroups, int h_px_lo,
                            int h_span_px, const int* d_vbounds, const int* d_vcoef, int vk, int row0, int rows,
                            const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
-                           cudaStream_t stream) {
+                           const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream) {
     FB_REQUIRE(d_images && d_hp0 && d_hcpad && d_vbounds && d_vcoef && d_tmp && d_out && mean3 && std3,
                "fb_clip_preprocess: null pointer");
     FB_REQUIRE(n >= 1 && out_size >= 1 && out_size <= 1024, "fb_clip_preprocess: bad n/out_size");
@@ -209,10 +209,16 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
         FB_CUDA_OK(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dim3 gh((rows + kRowsPerBlock - 1) / kRowsPerBlock, n);
-    resample_h_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, out_size, d_hp0, d_hcpad, hgroups, row0, rows,
-                                                 h_px_lo, h_span_px, d_tmp);
-    FB_CUDA_OK(cudaGetLastError());
+    // horizontal pass: exact int8 tensor-core product when the layout allows it, CUDA cores otherwise
+    int tc = launch_resample_h_tc(d_images, n, H, W, image_stride, out_size, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, row0, rows,
+                                  d_tmp, stream);
+    if (tc < 0 || tc > 1) return tc;
+    if (tc == 1) {
+        dim3 gh((rows + kRowsPerBlock - 1) / kRowsPerBlock, n);
+        resample_h_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, out_size, d_hp0, d_hcpad, hgroups, row0, rows,
+                                                     h_px_lo, h_span_px, d_tmp);
+        FB_CUDA_OK(cudaGetLastError());
+    }
     dim3 gv(out_size, n);
     int threads = (out_size * 3 + 3) / 4;
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;

@@ -1,0 +1,236 @@
+// Horizontal pass of Pillow's 8-bit resampler as an exact int8 tensor-core product.
+//
+// Part of `scorer.preprocess` (processing/scorer.py:508-510).  For a block of 8 output columns the
+// pass is  tmp[row, xo, c] = clip8((2^21 + sum_x img[row, x, c] * k[xo, x]) >> 22), i.e. a matrix product
+// of the image rows (uint8, interleaved channels, K = byte offset inside the block's window) with a
+// banded coefficient matrix.  Coefficients are 22-bit fixed point, so they are split into signed base-128
+// limbs (int8): the product is evaluated exactly with tcgen05.mma.kind::i8 (u8 x s8 -> s32) and the limbs
+// are recombined in the epilogue.
+//   A  image bytes [n*H rows][W*3] uint8, K-major, TMA boxes of 128 rows x 128 bytes (128-byte swizzle)
+//   B  per column block j: [96][KW] int8, row = limb*24 + (xo-8j)*3 + c, K = byte - kb0[j]   (host table)
+//   D  [128 rows][96] int32 in TMEM (two buffers), epilogue: one thread per row, 24 output bytes
+// Persistent CTAs, 6 warps: TMA producer, MMA issuer, 4 epilogue warps; 6-stage mbarrier ring.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int RM = 128, RN = 96, RKB = 128, RSTAGES = 6;
+constexpr int kABytesR = RM * RKB;        // 16 KB
+constexpr int kBBytesR = RN * RKB;        // 12 KB
+constexpr int kStageR = kABytesR + kBBytesR;
+constexpr int kThreadsR = 192;
+constexpr int kSmemR = RSTAGES * kStageR + 1024 + 256;
+constexpr int kNB = 8;                    // output columns per block
+constexpr int kPrec = 32 - 8 - 2;
+
+struct ResampleTcArgs {
+    int n_img, H, row0, rows;             // rows [row0, row0+rows) of every image are produced
+    int out;                              // output columns (multiple of 8)
+    int kblocks;                          // KW / 128
+    int limbs;                            // 3 or 4
+    const int* kb0;                       // [out/8] first byte of each block's window (multiple of 16)
+    uint8_t* tmp;                         // [n][rows][out][3]
+};
+
+// kind::i8: D = s32 (c_format 2), A = unsigned 8 bit (0), B = signed 8 bit (1), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_u8s8(int m, int n) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsR, 1)
+resample_h_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_coef, ResampleTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RSTAGES * kStageR);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + RSTAGES;
+    uint64_t* tmem_full = bars + 2 * RSTAGES;
+    uint64_t* tmem_empty = bars + 2 * RSTAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RSTAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = p.out / kNB;
+    const int mtiles_img = (p.rows + RM - 1) / RM;
+    const int num_tiles = p.n_img * mtiles_img * nblk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RSTAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tmem_full[a], 1);
+            tc::mbar_init(&tmem_empty[a], 4);
+        }
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+        tc::tma_prefetch_desc(&tmap_img);
+        tc::tma_prefetch_desc(&tmap_coef);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (image, m-tile inside the image, column block); column block fastest: 28 blocks share the rows in L2
+    auto decode = [&](int tile, int& img, int& mt, int& blk) {
+        blk = tile % nblk;
+        const int t2 = tile / nblk;
+        mt = t2 % mtiles_img;
+        img = t2 / mtiles_img;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int img, mt, blk;
+                decode(tile, img, mt, blk);
+                const int grow = img * p.H + p.row0 + mt * RM;     // first global row of the tile
+                const int kb0 = __ldg(p.kb0 + blk);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageR;
+                    tc::mbar_expect_tx(&full_bar[stage], kStageR);
+                    tc::tma_load_2d(&tmap_img, &full_bar[stage], sa, kb0 + kb * RKB, grow);
+                    tc::tma_load_2d(&tmap_coef, &full_bar[stage], sa + kABytesR, kb * RKB, blk * RN);
+                    if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_u8s8(RM, RN);
+            int stage = 0, iter = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                tc::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 128;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * kStageR);
+                    const uint64_t da = tc::make_desc_k_sw128(sa);
+                    const uint64_t db = tc::make_desc_k_sw128(sa + kABytesR);
+#pragma unroll
+                    for (int k = 0; k < RKB / 32; ++k) umma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_commit(&empty_bar[stage]);
+                    if (++stage == RSTAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            int img, mt, blk;
+            decode(tile, img, mt, blk);
+            const int acc = iter & 1;
+            tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
+            uint32_t d0[32], d1[32], d2[32];
+            tc::tmem_ld_32x32(taddr, d0);
+            tc::tmem_ld_32x32(taddr + 32, d1);
+            tc::tmem_ld_32x32(taddr + 64, d2);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+            // columns: limb L occupies [24 L, 24 L + 24); 96 values = d0 | d1 | d2
+            auto col = [&](int c) -> uint32_t { return c < 32 ? d0[c] : (c < 64 ? d1[c - 32] : d2[c - 64]); };
+            const int r_in = mt * RM + quarter * 32 + lane;
+            if (r_in < p.rows) {
+                uint32_t packed[6];
+#pragma unroll
+                for (int w = 0; w < 6; ++w) packed[w] = 0u;
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    uint32_t v = col(i) + (col(24 + i) << 7) + (col(48 + i) << 14) + (1u << (kPrec - 1));
+                    if (p.limbs == 4) v += col(72 + i) << 21;
+                    int s = (int)v >> kPrec;
+                    s = s < 0 ? 0 : (s > 255 ? 255 : s);
+                    packed[i >> 2] |= (uint32_t)s << (8 * (i & 3));
+                }
+                uint8_t* dst = p.tmp + (((size_t)img * p.rows + r_in) * p.out + (size_t)blk * kNB) * 3;
+                uint2* d8 = reinterpret_cast<uint2*>(dst);
+                d8[0] = make_uint2(packed[0], packed[1]);
+                d8[1] = make_uint2(packed[2], packed[3]);
+                d8[2] = make_uint2(packed[4], packed[5]);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    FB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride};
+    cuuint32_t box[2] = {128, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(u8) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace
+
+// Returns 1 when the tensor-core path does not apply (caller falls back to the CUDA-core kernel), 0 on success.
+int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long image_stride, int out_size, const int8_t* d_coef,
+                         int kw, int limbs, const int* d_kb0, int row0, int rows, uint8_t* d_tmp, cudaStream_t stream) {
+    if (!d_coef || !d_kb0 || kw <= 0) return 1;
+    if ((W % 16) != 0 || (reinterpret_cast<uintptr_t>(d_images) & 15) != 0 || image_stride != (long long)H * W * 3) return 1;
+    if (out_size % kNB != 0 || (kw % RKB) != 0 || (limbs != 3 && limbs != 4)) return 1;
+    if ((reinterpret_cast<uintptr_t>(d_tmp) & 7) != 0) return 1;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_u8_2d(&ta, d_images, (uint64_t)n * H, (uint64_t)W * 3, (uint64_t)W * 3, RM);
+    if (rc) return rc;
+    rc = make_tmap_u8_2d(&tb, d_coef, (uint64_t)(out_size / kNB) * RN, (uint64_t)kw, (uint64_t)kw, RN);
+    if (rc) return rc;
+    ResampleTcArgs p;
+    p.n_img = n; p.H = H; p.row0 = row0; p.rows = rows; p.out = out_size; p.kblocks = kw / RKB; p.limbs = limbs;
+    p.kb0 = d_kb0; p.tmp = d_tmp;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemR));
+        attr_set = true;
+    }
+    const int tiles = n * ((rows + RM - 1) / RM) * (out_size / kNB);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    resample_h_tc_kernel<<<grid, kThreadsR, kSmemR, stream>>>(ta, tb, p);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fb

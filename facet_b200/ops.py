@@ -195,11 +195,14 @@ def _device_plan(height: int, width: int, out: int, device):
     if key not in _PLAN_CACHE:
         p = rs.plan(height, width, out)
         dev = {name: torch.from_numpy(getattr(p, name)).to(device) for name in ("hp0", "hcpad", "vbounds", "vcoef")}
+        dev["tc_coef"] = torch.from_numpy(p.tc_coef).to(device) if p.tc_coef is not None else None
+        dev["tc_kb0"] = torch.from_numpy(p.tc_kb0).to(device) if p.tc_kb0 is not None else None
         _PLAN_CACHE[key] = (p, dev)
     return _PLAN_CACHE[key]
 
 
-def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), rgb_order: bool = False):
+def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), rgb_order: bool = False,
+                    tensor_cores: bool = True):
     """Resize(out, bicubic, antialias) + CenterCrop + ToTensor + Normalize on the GPU.
 
     images: [n,H,W,3] uint8 (numpy or CUDA tensor; BGR unless rgb_order).  Returns a CUDA float32
@@ -212,6 +215,7 @@ def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5,
     p, dev = _device_plan(h, w, out_size, t.device)
     tmp = torch.empty((n, p.rows, out_size, 3), dtype=torch.uint8, device=t.device)
     out = torch.empty((n, 3, out_size, out_size), dtype=torch.float32, device=t.device)
+    use_tc = bool(tensor_cores) and dev["tc_coef"] is not None
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[float(v) for v in std])
     with torch.cuda.device(t.device):
@@ -219,6 +223,8 @@ def clip_preprocess(images, out_size: int = 224, mean=(0.5, 0.5, 0.5), std=(0.5,
                                           _ptr(dev["hp0"]), _ptr(dev["hcpad"]), p.hgroups, p.h_px_lo, p.h_span_px,
                                           _ptr(dev["vbounds"]), _ptr(dev["vcoef"]), p.vk, p.row0, p.rows,
                                           C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), _ptr(tmp), _ptr(out),
+                                          _ptr(dev["tc_coef"]) if use_tc else None, p.tc_kw if use_tc else 0,
+                                          p.tc_limbs if use_tc else 0, _ptr(dev["tc_kb0"]) if use_tc else None,
                                           _lib.stream_ptr()), "fb_clip_preprocess")
     return out
 

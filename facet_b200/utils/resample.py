@@ -108,6 +108,12 @@ class ResamplePlan:
     vk: int
     row0: int
     rows: int
+    # tensor-core form of the horizontal pass (csrc/resample_tc.cu): per block of 8 output columns an
+    # int8 matrix [96][tc_kw]: row = limb*24 + (xo - 8j)*3 + channel, column = byte - tc_kb0[j]
+    tc_coef: np.ndarray | None = None    # int8 [out/8 * 96, tc_kw]
+    tc_kb0: np.ndarray | None = None     # int32 [out/8]
+    tc_kw: int = 0
+    tc_limbs: int = 0
 
 
 @lru_cache(maxsize=64)
@@ -134,9 +140,50 @@ def plan(height: int, width: int, out: int = 224) -> ResamplePlan:
         hcpad[off:off + cnt, xo] = hc[xo, :cnt]
     px_lo = int(hp0.min()) // 16 * 16
     px_hi = -(-int((hp0 + 4 * hgroups).max()) // 16) * 16
+    tc_coef, tc_kb0, tc_kw, tc_limbs = _tc_tables(hb, hc, out)
     return ResamplePlan(height, width, out, np.ascontiguousarray(hb), np.ascontiguousarray(hc), hk,
                         np.ascontiguousarray(hp0), np.ascontiguousarray(hcpad), hgroups, px_lo, px_hi - px_lo,
-                        np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk, row0, row1 - row0)
+                        np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk, row0, row1 - row0,
+                        tc_coef, tc_kb0, tc_kw, tc_limbs)
+
+
+def split_limbs(c: np.ndarray, limbs: int) -> np.ndarray:
+    """Signed base-128 digits of int coefficients: c == sum_i d_i * 128**i, d_i in [-64, 63] except the top one."""
+    c = c.astype(np.int64).copy()
+    out = []
+    for i in range(limbs - 1):
+        d = ((c + 64) % 128) - 64
+        out.append(d)
+        c = (c - d) // 128
+    out.append(c)
+    return np.stack(out)
+
+
+def _tc_tables(hb, hc, out, nb: int = 8, n_rows: int = 96, channels: int = 3):
+    """Banded int8 coefficient matrices for the tcgen05 horizontal pass (None if the layout does not fit)."""
+    if out % nb:
+        return None, None, 0, 0
+    nblk = out // nb
+    first = hb[:, 0].astype(np.int64)
+    last = (hb[:, 0] + hb[:, 1]).astype(np.int64)
+    kb0 = np.array([int(first[nb * j]) * channels // 16 * 16 for j in range(nblk)], np.int32)
+    span = max(int(last[nb * j:nb * j + nb].max()) * channels - int(kb0[j]) for j in range(nblk))
+    kw = -(-span // 128) * 128
+    cmax = int(np.abs(hc).max())
+    limbs = 3 if cmax < 63 * 16384 else 4
+    if np.abs(split_limbs(hc, limbs)[-1]).max() > 127 or nb * channels * limbs > n_rows:
+        return None, None, 0, 0
+    digits = split_limbs(hc, limbs)                      # [limbs, out, ksize]
+    table = np.zeros((nblk, n_rows, kw), np.int8)
+    for j in range(nblk):
+        for xl in range(nb):
+            xo = nb * j + xl
+            f, cnt = int(hb[xo, 0]), int(hb[xo, 1])
+            for c in range(channels):
+                cols = (f + np.arange(cnt)) * channels + c - int(kb0[j])
+                for L in range(limbs):
+                    table[j, L * nb * channels + xl * channels + c, cols] = digits[L, xo, :cnt]
+    return np.ascontiguousarray(table.reshape(nblk * n_rows, kw)), kb0, kw, limbs
 
 
 def resample_reference_numpy(img_rgb: np.ndarray, out: int = 224) -> np.ndarray:

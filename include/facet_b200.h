@@ -96,6 +96,11 @@ int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_orde
  * d_tmp      scratch [n][rows][out][3] uint8 (horizontal pass output)
  * d_out      [n][3][out][out] float32, planes R,G,B, (x/255 - mean[c]) / std[c]
  * mean3/std3 are HOST pointers to 3 floats each.
+ * Optional tensor-core tables (NULL/0 to skip): the horizontal pass as an exact u8 x s8 -> s32
+ * tcgen05 product.  Per block j of 8 output columns, d_tc_coef holds an int8 matrix [96][tc_kw]
+ * (row = limb*24 + (xo-8j)*3 + channel, column = byte - d_tc_kb0[j]) of the signed base-128 limbs of
+ * the taps (tc_limbs = 3 or 4).  Used when width % 16 == 0 and the batch is contiguous; the CUDA-core
+ * kernel with d_hp0/d_hcpad is the general path.
  */
 int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
                        int rgb_order, int out_size,
@@ -104,7 +109,9 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
                        const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
                        int row0, int rows,
                        const float* mean3, const float* std3,
-                       uint8_t* d_tmp, float* d_out, void* stream);
+                       uint8_t* d_tmp, float* d_out,
+                       const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Perceptual hash — replaces `imagehash.phash(pil_img)` (processing/batch_processor.py:216,

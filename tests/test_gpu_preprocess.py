@@ -39,3 +39,20 @@ def test_preprocess_24mp():
     got = ops.clip_preprocess(bgr).cpu().numpy()[0]
     want = _torchvision_preprocess(np.ascontiguousarray(bgr[..., ::-1]), (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
     np.testing.assert_allclose(got, want, rtol=0, atol=3e-7)
+
+
+@pytest.mark.parametrize("shape", [(683, 1024), (400, 608), (4000, 6000), (1024, 1024)])
+def test_tensor_core_and_cuda_core_horizontal_pass_agree(shape):
+    """csrc/resample_tc.cu (u8 x s8 tcgen05 product with base-128 coefficient limbs) is exact: identical
+    output to the CUDA-core kernel and to torchvision."""
+    import torch
+    from facet_b200 import ops
+    from facet_b200.utils import resample as rs
+    h, w = shape
+    assert rs.plan(h, w).tc_coef is not None
+    bgr = np.stack([synth_image_bgr(30 + i, h, w) for i in range(3)])
+    a = ops.clip_preprocess(bgr, tensor_cores=True)
+    b = ops.clip_preprocess(bgr, tensor_cores=False)
+    assert torch.equal(a, b)
+    want = _torchvision_preprocess(np.ascontiguousarray(bgr[1][..., ::-1]), (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+    np.testing.assert_allclose(a[1].cpu().numpy(), want, rtol=0, atol=3e-7)

@@ -44,3 +44,30 @@ def test_bicubic_plan_matches_torchvision():
             cnt = int(p.hbounds[xo, 1])
             assert np.array_equal(p.hcpad[off:off + cnt, xo], p.hcoef[xo, :cnt])
             assert not p.hcpad[:off, xo].any() and not p.hcpad[off + cnt:, xo].any()
+
+
+def test_tensor_core_limb_tables_reproduce_taps():
+    """The banded int8 matrices of csrc/resample_tc.cu recombine to the exact 22-bit taps."""
+    rng = np.random.default_rng(0)
+    for (h, w) in [(4000, 6000), (683, 1024), (225, 304)]:
+        p = rs.plan(h, w)
+        assert p.tc_coef is not None and p.tc_kw % 128 == 0 and p.tc_limbs in (3, 4)
+        row = rng.integers(0, 256, w * 3).astype(np.int64)
+        tbl = p.tc_coef.reshape(p.out // 8, 96, p.tc_kw).astype(np.int64)
+        for j in (0, p.out // 16, p.out // 8 - 1):
+            lo = int(p.tc_kb0[j])
+            seg = np.zeros(p.tc_kw, np.int64)
+            hi = min(lo + p.tc_kw, w * 3)
+            seg[:hi - lo] = row[lo:hi]
+            d = tbl[j] @ seg
+            for xl in range(8):
+                xo = 8 * j + xl
+                f, c = p.hbounds[xo]
+                for ch in range(3):
+                    want = int(row[(f + np.arange(c)) * 3 + ch] @ p.hcoef[xo, :c].astype(np.int64))
+                    got = sum(int(d[L * 24 + xl * 3 + ch]) * 128 ** L for L in range(p.tc_limbs))
+                    assert want == got
+    c = np.array([0, 1, -1, 63, 64, -64, -65, 8191, -8192, 4194304, -4194304, 262143])
+    for limbs in (3, 4):
+        d = rs.split_limbs(c, limbs)
+        assert np.array_equal(sum(d[i] * 128 ** i for i in range(limbs)), c)
