@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of B synthetic 24 MP frames per GPU:
-technical metrics (csrc/tech_stats.cu) + CLIP preprocess (csrc/preprocess.cu) + ViT-L/14 tower,
+technical metrics (csrc/tech_stats.cu) + perceptual hash (csrc/phash.cu) + CLIP preprocess
+(csrc/preprocess.cu, csrc/resample_tc.cu) + ViT-L/14 tower,
 aesthetic head and tag similarities (csrc/gemm.cu, csrc/vit.cu) + the similarity stage on the
 step's embeddings (all-gather across ranks, cosine pairs, csrc/gemm.cu + csrc/similarity.cu).
 `value` is the whole-job rate with the frames already resident in HBM; `e2e` is the same pass
@@ -176,8 +177,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(batch, note=None):
-    cfg = {"workload": "full legacy scoring pass on synthetic 6000x4000 (24 MP) BGR frames: technical metrics + CLIP "
-                       "preprocess + ViT-L/14 224px + MLP aesthetic + tag similarities + cosine duplicate pairs "
+    cfg = {"workload": "full legacy scoring pass on synthetic 6000x4000 (24 MP) BGR frames: technical metrics + pHash + CLIP "
+                       "preprocess + ViT-L/14 224px + MLP aesthetic + tag similarities + Hamming and cosine duplicate pairs "
                        "(BASELINE.json configs[4], per-GPU share)",
            "image": [H, W, 3], "batch_per_gpu": batch, "parallelism": "data-parallel, one rank per GPU",
            "l2": "inputs larger than L2 (pool of batch x 72 MB frames per step)", "weights": "random-init ViT-L/14 (seed 0)",
@@ -225,9 +226,11 @@ def main():
     torch.cuda.synchronize()
 
     def step():
-        out = scorer.score_images_device(pool)
+        out = scorer.score_images_device(pool)                      # technical + pHash + preprocess + ViT/heads/tags
         emb = all_gather_embeddings(out["embedding"]) if world > 1 else out["embedding"]
         pairs, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)
+        hashes = all_gather_embeddings(out["phash"].view(-1, 1)).view(-1) if world > 1 else out["phash"]
+        ops.hamming_pairs(hashes, 6, part=rank, nparts=world)      # duplicate rule of utils/duplicate.py on the step's hashes
         return out, pairs
 
     def barrier():
@@ -273,9 +276,10 @@ def main():
     ms_step_profiled = pe0.elapsed_time(pe1) / args.steps
     per_step = {k: (v[0] / args.steps, v[1] // args.steps) for k, v in prof.items() if v[1]}
     ms_tech, ms_pre = per_step["technical"][0], per_step["preprocess"][0]
+    ms_phash = per_step.get("other", (0.0, 0))[0]
     ms_vit = sum(per_step[k][0] for k in ("im2col", "gemm", "layernorm", "attention", "vit_tail") if k in per_step)
     gemm_ms, gemm_launches = per_step["gemm"]
-    stages = {"technical_ms": ms_tech, "preprocess_ms": ms_pre, "vit_ms": ms_vit,
+    stages = {"technical_ms": ms_tech, "phash_ms": ms_phash, "preprocess_ms": ms_pre, "vit_ms": ms_vit,
               "kernel_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
               "launches_per_step": {k: v[1] for k, v in per_step.items()},
               "step_ms_with_event_pairs": ms_step_profiled,

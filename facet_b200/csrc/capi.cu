@@ -204,11 +204,13 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
 
 int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
-             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, void* stream) {
+             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma,
+             const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0, void* stream) {
     ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
     int rc = launch_phash(d_images, n, height, width, (long long)image_stride, rgb_order, d_hbounds, d_hcoef, hk, d_vbounds,
-                          d_vcoef, vk, d_tmp, reinterpret_cast<unsigned long long*>(d_hashes), d_small, d_dct, (cudaStream_t)stream);
-    if (rc == 0) count_launch(2);
+                          d_vcoef, vk, d_tmp, reinterpret_cast<unsigned long long*>(d_hashes), d_small, d_dct, d_luma,
+                          d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, (cudaStream_t)stream);
+    if (rc == 0) count_launch(d_luma ? 3 : 2);
     return rc;
 }
 

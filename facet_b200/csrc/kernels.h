@@ -33,10 +33,12 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                            const float* mean3, const float* std3, uint8_t* d_tmp, float* d_out,
                            const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
 int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long image_stride, int out_size, const int8_t* d_coef,
-                         int kw, int limbs, const int* d_kb0, int row0, int rows, uint8_t* d_tmp, cudaStream_t stream);
+                         int kw, int limbs, const int* d_kb0, int row0, int rows, uint8_t* d_tmp, int channels,
+                         cudaStream_t stream);
 int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order, const int* d_hbounds,
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
-                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, cudaStream_t stream);
+                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, const int8_t* d_tc_coef,
+                 int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
 

@@ -81,6 +81,29 @@ __global__ void __launch_bounds__(256) luma_hresample_kernel(const uint8_t* __re
     }
 }
 
+// Pillow luma plane [n][H][W] uint8 (input of the tensor-core horizontal pass): 16 pixels (48 bytes) per thread
+__global__ void __launch_bounds__(256) luma_plane_kernel(const uint8_t* __restrict__ img, long long total_px, int rgb_order,
+                                                         uint8_t* __restrict__ luma) {
+    const int wr = rgb_order ? 19595 : 7471, wb = rgb_order ? 7471 : 19595;
+    const long long groups = total_px / 16;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(img) + 3 * g;
+        const uint4 a = ldg_nc_v4(src), b = ldg_nc_v4(src + 1), c = ldg_nc_v4(src + 2);
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+            const int l0 = (wr * (int)(w0 & 255) + 38470 * (int)((w0 >> 8) & 255) + wb * (int)((w0 >> 16) & 255) + 0x8000) >> 16;
+            const int l1 = (wr * (int)(w0 >> 24) + 38470 * (int)(w1 & 255) + wb * (int)((w1 >> 8) & 255) + 0x8000) >> 16;
+            const int l2 = (wr * (int)((w1 >> 16) & 255) + 38470 * (int)(w1 >> 24) + wb * (int)(w2 & 255) + 0x8000) >> 16;
+            const int l3 = (wr * (int)((w2 >> 8) & 255) + 38470 * (int)((w2 >> 16) & 255) + wb * (int)(w2 >> 24) + 0x8000) >> 16;
+            o[q] = (uint32_t)l0 | ((uint32_t)l1 << 8) | ((uint32_t)l2 << 16) | ((uint32_t)l3 << 24);
+        }
+        reinterpret_cast<uint4*>(luma)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // one CTA (1024 threads = the 32 x 32 pixels) per image
 __global__ void __launch_bounds__(1024) phash_finish_kernel(const uint8_t* __restrict__ tmp, int H, const int* __restrict__ bounds,
                                                             const int* __restrict__ coef, int ksize,
@@ -152,19 +175,35 @@ __global__ void __launch_bounds__(1024) phash_finish_kernel(const uint8_t* __res
 
 int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order, const int* d_hbounds,
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
-                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, cudaStream_t stream) {
+                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, const int8_t* d_tc_coef,
+                 int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream) {
     FB_REQUIRE(d_images && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_hashes, "fb_phash: null pointer");
     FB_REQUIRE(n >= 1 && H >= 1 && W >= 1, "fb_phash: bad shape");
-    const size_t smem = (size_t)kRows * W;
-    FB_REQUIRE(smem <= 200 * 1024, "fb_phash: image width %d exceeds shared memory staging", W);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(luma_hresample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+    // tensor-core route: Pillow luma plane, then the horizontal Lanczos pass as an exact u8 x s8 product
+    int tc = 1;
+    const bool plane_ok = d_luma && d_tc_coef && d_tc_kb0 && (W % 16 == 0) && image_stride == (long long)H * W * 3 &&
+                          (reinterpret_cast<uintptr_t>(d_images) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_luma) & 15) == 0;
+    if (plane_ok) {
+        const long long total_px = (long long)n * H * W;
+        long long blocks = (total_px / 16 + 255) / 256;
+        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+        luma_plane_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_images, total_px, rgb_order, d_luma);
+        FB_CUDA_OK(cudaGetLastError());
+        tc = launch_resample_h_tc(d_luma, n, H, W, (long long)H * W, kOut, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, 0, H, d_tmp, 1, stream);
+        if (tc < 0 || tc > 1) return tc;
     }
-    dim3 gh((H + kRows - 1) / kRows, n);
-    luma_hresample_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, rgb_order, d_hbounds, d_hcoef, hk, d_tmp);
-    FB_CUDA_OK(cudaGetLastError());
+    if (tc == 1) {
+        const size_t smem = (size_t)kRows * W;
+        FB_REQUIRE(smem <= 200 * 1024, "fb_phash: image width %d exceeds shared memory staging", W);
+        static bool attr_set = false;
+        if (!attr_set) {
+            FB_CUDA_OK(cudaFuncSetAttribute(luma_hresample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        dim3 gh((H + kRows - 1) / kRows, n);
+        luma_hresample_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, rgb_order, d_hbounds, d_hcoef, hk, d_tmp);
+        FB_CUDA_OK(cudaGetLastError());
+    }
     phash_finish_kernel<<<n, 1024, 0, stream>>>(d_tmp, H, d_vbounds, d_vcoef, vk, d_hashes, d_small, d_dct);
     FB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -211,7 +211,7 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
     }
     // horizontal pass: exact int8 tensor-core product when the layout allows it, CUDA cores otherwise
     int tc = launch_resample_h_tc(d_images, n, H, W, image_stride, out_size, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, row0, rows,
-                                  d_tmp, stream);
+                                  d_tmp, 3, stream);
     if (tc < 0 || tc > 1) return tc;
     if (tc == 1) {
         dim3 gh((rows + kRowsPerBlock - 1) / kRowsPerBlock, n);

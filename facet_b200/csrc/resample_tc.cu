@@ -18,14 +18,17 @@ namespace fb {
 
 namespace {
 
-constexpr int RM = 128, RN = 96, RKB = 128, RSTAGES = 6;
+constexpr int RM = 128, RKB = 128, RSTAGES = 6;
 constexpr int kABytesR = RM * RKB;        // 16 KB
-constexpr int kBBytesR = RN * RKB;        // 12 KB
-constexpr int kStageR = kABytesR + kBBytesR;
 constexpr int kThreadsR = 192;
-constexpr int kSmemR = RSTAGES * kStageR + 1024 + 256;
 constexpr int kNB = 8;                    // output columns per block
 constexpr int kPrec = 32 - 8 - 2;
+template <int CH> struct RCfg {
+    static constexpr int RN = CH == 3 ? 96 : 32;          // coefficient rows per block: limb * (8*CH) + (xo-8j)*CH + c, padded
+    static constexpr int kBBytes = RN * RKB;
+    static constexpr int kStage = kABytesR + kBBytes;
+    static constexpr int kSmem = RSTAGES * kStage + 1024 + 256;
+};
 
 struct ResampleTcArgs {
     int n_img, H, row0, rows;             // rows [row0, row0+rows) of every image are produced
@@ -33,7 +36,7 @@ struct ResampleTcArgs {
     int kblocks;                          // KW / 128
     int limbs;                            // 3 or 4
     const int* kb0;                       // [out/8] first byte of each block's window (multiple of 16)
-    uint8_t* tmp;                         // [n][rows][out][3]
+    uint8_t* tmp;                         // [n][rows][out][CH]
 };
 
 // kind::i8: D = s32 (c_format 2), A = unsigned 8 bit (0), B = signed 8 bit (1), both K-major
@@ -47,8 +50,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+template <int CH>
 __global__ void __launch_bounds__(kThreadsR, 1)
 resample_h_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_coef, ResampleTcArgs p) {
+    constexpr int RN = RCfg<CH>::RN;
+    constexpr int kStageR = RCfg<CH>::kStage;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RSTAGES * kStageR);
@@ -143,34 +149,55 @@ resample_h_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_
             tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 128;
-            uint32_t d0[32], d1[32], d2[32];
-            tc::tmem_ld_32x32(taddr, d0);
-            tc::tmem_ld_32x32(taddr + 32, d1);
-            tc::tmem_ld_32x32(taddr + 64, d2);
-            tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
-            // columns: limb L occupies [24 L, 24 L + 24); 96 values = d0 | d1 | d2
-            auto col = [&](int c) -> uint32_t { return c < 32 ? d0[c] : (c < 64 ? d1[c - 32] : d2[c - 64]); };
             const int r_in = mt * RM + quarter * 32 + lane;
-            if (r_in < p.rows) {
-                uint32_t packed[6];
+            if (CH == 3) {
+                uint32_t d0[32], d1[32], d2[32];
+                tc::tmem_ld_32x32(taddr, d0);
+                tc::tmem_ld_32x32(taddr + 32, d1);
+                tc::tmem_ld_32x32(taddr + 64, d2);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                // columns: limb L occupies [24 L, 24 L + 24); 96 values = d0 | d1 | d2
+                auto col = [&](int c) -> uint32_t { return c < 32 ? d0[c] : (c < 64 ? d1[c - 32] : d2[c - 64]); };
+                if (r_in < p.rows) {
+                    uint32_t packed[6];
 #pragma unroll
-                for (int w = 0; w < 6; ++w) packed[w] = 0u;
+                    for (int w = 0; w < 6; ++w) packed[w] = 0u;
 #pragma unroll
-                for (int i = 0; i < 24; ++i) {
-                    uint32_t v = col(i) + (col(24 + i) << 7) + (col(48 + i) << 14) + (1u << (kPrec - 1));
-                    if (p.limbs == 4) v += col(72 + i) << 21;
-                    int s = (int)v >> kPrec;
-                    s = s < 0 ? 0 : (s > 255 ? 255 : s);
-                    packed[i >> 2] |= (uint32_t)s << (8 * (i & 3));
+                    for (int i = 0; i < 24; ++i) {
+                        uint32_t v = col(i) + (col(24 + i) << 7) + (col(48 + i) << 14) + (1u << (kPrec - 1));
+                        if (p.limbs == 4) v += col(72 + i) << 21;
+                        int s = (int)v >> kPrec;
+                        s = s < 0 ? 0 : (s > 255 ? 255 : s);
+                        packed[i >> 2] |= (uint32_t)s << (8 * (i & 3));
+                    }
+                    uint8_t* dst = p.tmp + (((size_t)img * p.rows + r_in) * p.out + (size_t)blk * kNB) * 3;
+                    uint2* d8 = reinterpret_cast<uint2*>(dst);
+                    d8[0] = make_uint2(packed[0], packed[1]);
+                    d8[1] = make_uint2(packed[2], packed[3]);
+                    d8[2] = make_uint2(packed[4], packed[5]);
                 }
-                uint8_t* dst = p.tmp + (((size_t)img * p.rows + r_in) * p.out + (size_t)blk * kNB) * 3;
-                uint2* d8 = reinterpret_cast<uint2*>(dst);
-                d8[0] = make_uint2(packed[0], packed[1]);
-                d8[1] = make_uint2(packed[2], packed[3]);
-                d8[2] = make_uint2(packed[4], packed[5]);
+            } else {
+                uint32_t d0[32];
+                tc::tmem_ld_32x32(taddr, d0);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                if (r_in < p.rows) {
+                    uint32_t packed[2] = {0u, 0u};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t v = d0[i] + (d0[8 + i] << 7) + (d0[16 + i] << 14) + (1u << (kPrec - 1));
+                        if (p.limbs == 4) v += d0[24 + i] << 21;
+                        int s = (int)v >> kPrec;
+                        s = s < 0 ? 0 : (s > 255 ? 255 : s);
+                        packed[i >> 2] |= (uint32_t)s << (8 * (i & 3));
+                    }
+                    *reinterpret_cast<uint2*>(p.tmp + ((size_t)img * p.rows + r_in) * p.out + (size_t)blk * kNB) = make_uint2(packed[0], packed[1]);
+                }
             }
         }
     }
@@ -207,14 +234,17 @@ int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 }  // namespace
 
 // Returns 1 when the tensor-core path does not apply (caller falls back to the CUDA-core kernel), 0 on success.
+// channels = 3: d_images is [n][H][W][3] interleaved; channels = 1: a [n][H][W] uint8 plane.
 int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long image_stride, int out_size, const int8_t* d_coef,
-                         int kw, int limbs, const int* d_kb0, int row0, int rows, uint8_t* d_tmp, cudaStream_t stream) {
+                         int kw, int limbs, const int* d_kb0, int row0, int rows, uint8_t* d_tmp, int channels,
+                         cudaStream_t stream) {
     if (!d_coef || !d_kb0 || kw <= 0) return 1;
-    if ((W % 16) != 0 || (reinterpret_cast<uintptr_t>(d_images) & 15) != 0 || image_stride != (long long)H * W * 3) return 1;
-    if (out_size % kNB != 0 || (kw % RKB) != 0 || (limbs != 3 && limbs != 4)) return 1;
+    if ((W % 16) != 0 || (reinterpret_cast<uintptr_t>(d_images) & 15) != 0 || image_stride != (long long)H * W * channels) return 1;
+    if (out_size % kNB != 0 || (kw % RKB) != 0 || (limbs != 3 && limbs != 4) || (channels != 1 && channels != 3)) return 1;
     if ((reinterpret_cast<uintptr_t>(d_tmp) & 7) != 0) return 1;
+    const int RN = channels == 3 ? RCfg<3>::RN : RCfg<1>::RN;
     CUtensorMap ta, tb;
-    int rc = make_tmap_u8_2d(&ta, d_images, (uint64_t)n * H, (uint64_t)W * 3, (uint64_t)W * 3, RM);
+    int rc = make_tmap_u8_2d(&ta, d_images, (uint64_t)n * H, (uint64_t)W * channels, (uint64_t)W * channels, RM);
     if (rc) return rc;
     rc = make_tmap_u8_2d(&tb, d_coef, (uint64_t)(out_size / kNB) * RN, (uint64_t)kw, (uint64_t)kw, RN);
     if (rc) return rc;
@@ -223,12 +253,14 @@ int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long
     p.kb0 = d_kb0; p.tmp = d_tmp;
     static bool attr_set = false;
     if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemR));
+        FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RCfg<3>::kSmem));
+        FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RCfg<1>::kSmem));
         attr_set = true;
     }
     const int tiles = n * ((rows + RM - 1) / RM) * (out_size / kNB);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    resample_h_tc_kernel<<<grid, kThreadsR, kSmemR, stream>>>(ta, tb, p);
+    if (channels == 3) resample_h_tc_kernel<3><<<grid, kThreadsR, RCfg<3>::kSmem, stream>>>(ta, tb, p);
+    else resample_h_tc_kernel<1><<<grid, kThreadsR, RCfg<1>::kSmem, stream>>>(ta, tb, p);
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -326,9 +326,10 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
 _PHASH_PLANS: dict = {}
 
 
-def phash(images, rgb_order: bool = False, debug: bool = False):
+def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bool = True, device_only: bool = False):
     """64-bit perceptual hashes (imagehash.phash) of a same-shaped batch.  Returns a uint64 numpy array
-    (and, with debug=True, the 32x32 uint8 luma thumbnails and the 8x8 float64 DCT blocks)."""
+    (and, with debug=True, the 32x32 uint8 luma thumbnails and the 8x8 float64 DCT blocks); with
+    device_only=True the CUDA int64 tensor is returned without synchronising."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     from .utils import resample as rs
@@ -337,8 +338,12 @@ def phash(images, rgb_order: bool = False, debug: bool = False):
     key = (h, w, str(t.device))
     if key not in _PHASH_PLANS:
         hb, hc, hk, vb, vc, vk = rs.phash_plan(h, w)
-        _PHASH_PLANS[key] = tuple(torch.from_numpy(a).to(t.device) for a in (hb, hc, vb, vc)) + (hk, vk)
-    hb, hc, vb, vc, hk, vk = _PHASH_PLANS[key]
+        tcc, tkb0, tkw, tlimbs = rs.phash_tc_tables(h, w)
+        tc_dev = (torch.from_numpy(tcc).to(t.device), torch.from_numpy(tkb0).to(t.device), tkw, tlimbs) if tcc is not None else None
+        _PHASH_PLANS[key] = tuple(torch.from_numpy(a).to(t.device) for a in (hb, hc, vb, vc)) + (hk, vk, tc_dev)
+    hb, hc, vb, vc, hk, vk, tc_dev = _PHASH_PLANS[key]
+    use_tc = bool(tensor_cores) and tc_dev is not None and w % 16 == 0
+    luma = torch.empty((n, h, w), dtype=torch.uint8, device=t.device) if use_tc else None
     tmp = torch.empty((n, h, 32), dtype=torch.uint8, device=t.device)
     hashes = torch.empty((n,), dtype=torch.int64, device=t.device)
     small = torch.empty((n, 32, 32), dtype=torch.uint8, device=t.device) if debug else None
@@ -346,7 +351,11 @@ def phash(images, rgb_order: bool = False, debug: bool = False):
     with torch.cuda.device(t.device):
         _lib.check(lib.fb_phash(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hb), _ptr(hc), hk, _ptr(vb), _ptr(vc), vk,
                                 _ptr(tmp), _ptr(hashes), _ptr(small) if debug else None, _ptr(dct) if debug else None,
+                                _ptr(luma) if use_tc else None, _ptr(tc_dev[0]) if use_tc else None,
+                                tc_dev[2] if use_tc else 0, tc_dev[3] if use_tc else 0, _ptr(tc_dev[1]) if use_tc else None,
                                 _lib.stream_ptr()), "fb_phash")
+    if device_only:
+        return hashes
     out = hashes.cpu().numpy().view(np.uint64)
     if debug:
         return out, small.cpu().numpy(), dct.cpu().numpy().reshape(n, 8, 8)

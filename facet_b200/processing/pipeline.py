@@ -54,8 +54,10 @@ class ScoringPipeline:
             self._free[slot].record(compute)
             outs.append(dev)
         cat = lambda key: torch.cat([o[key] for o in outs]).cpu().numpy() if outs[0][key] is not None else None
-        res = {key: cat(key) for key in ("hist256", "sums", "derived", "embedding", "aesthetic_raw", "tag_sims")}
+        res = {key: cat(key) for key in ("hist256", "sums", "derived", "embedding", "aesthetic_raw", "tag_sims", "phash")}
         res["hist256"] = res["hist256"].view(np.uint32)
+        if res["phash"] is not None:
+            res["phash"] = res["phash"].view(np.uint64)
         return res
 
     @staticmethod
@@ -64,4 +66,4 @@ class ScoringPipeline:
 
     @staticmethod
     def d2h_bytes(n, n_tags):
-        return int(n) * (256 * 4 + 4 * 8 + 4 * 8 + 768 * 4 + 4 + n_tags * 4)
+        return int(n) * (256 * 4 + 4 * 8 + 4 * 8 + 768 * 4 + 4 + n_tags * 4 + 8)

@@ -82,21 +82,23 @@ class Facet:
         return _aesthetic_from_raw(float(raw.flatten()[0]))
 
     # -- batched device-resident entry -------------------------------------------------------------------
-    def score_images_device(self, images, rgb_order=False):
-        """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, preprocess and ViT; returns device
-        tensors (nothing is copied to the host)."""
+    def score_images_device(self, images, rgb_order=False, with_phash=True):
+        """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;
+        returns device tensors (nothing is copied to the host)."""
         hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order)
+        hashes = ops.phash(images, rgb_order=rgb_order, device_only=True) if with_phash else None
         clip_in = ops.clip_preprocess(images, mean=self.mean, std=self.std, rgb_order=rgb_order)
         vit = self.model.encode(clip_in)
-        return {"hist256": hist, "sums": sums, "derived": derived, **vit}
+        return {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, **vit}
 
     def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True):
         """Full per-image pass for a same-shaped batch -> list of result dicts with the reference's
         metric keys (processing/batch_processor.py:298-355, the analyzer-derived subset)."""
         t = ops.to_device_u8(images)
         n, h, w, _ = t.shape
-        dev = self.score_images_device(t, rgb_order=rgb_order)
-        hashes = ops.phash_hex(t, rgb_order=rgb_order) if with_phash else [None] * n      # batch_processor.py:216
+        dev = self.score_images_device(t, rgb_order=rgb_order, with_phash=with_phash)
+        hashes = (["%016x" % int(v) for v in dev["phash"].cpu().numpy().view(np.uint64)]   # batch_processor.py:216
+                  if with_phash else [None] * n)
         hist = dev["hist256"].cpu().numpy().view(np.uint32).astype(np.int64)
         sums = dev["sums"].cpu().numpy()
         der = dev["derived"].cpu().numpy()

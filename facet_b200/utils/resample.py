@@ -214,3 +214,10 @@ def phash_plan(height: int, width: int, size: int = 32):
     hb, hc, hk = precompute_coeffs(width, size, "lanczos")
     vb, vc, vk = precompute_coeffs(height, size, "lanczos")
     return (np.ascontiguousarray(hb), np.ascontiguousarray(hc), hk, np.ascontiguousarray(vb), np.ascontiguousarray(vc), vk)
+
+
+@lru_cache(maxsize=64)
+def phash_tc_tables(height: int, width: int, size: int = 32):
+    """int8 limb tables of the horizontal Lanczos pass on the luma plane (one channel, 32 rows per block)."""
+    hb, hc, _ = precompute_coeffs(width, size, "lanczos")
+    return _tc_tables(hb, hc, size, nb=8, n_rows=32, channels=1)

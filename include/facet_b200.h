@@ -119,11 +119,17 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
  * -> 2-D DCT-II -> top-left 8x8 > median, 64 bits row-major MSB first (str(ImageHash) = "%016x").
  * Coefficient tables ([32][2] bounds + [32][k] int32 taps per axis, Pillow's Lanczos taps) come from
  * facet_b200/utils/resample.py.  d_tmp scratch [n][height][32] uint8.  d_small ([n][32][32] uint8, the
- * resized luma) and d_dct ([n][64] float64, the low-frequency block) are optional debug outputs. */
+ * resized luma) and d_dct ([n][64] float64, the low-frequency block) are optional debug outputs.
+ * Optional tensor-core route (width % 16 == 0, contiguous batch): d_luma scratch [n][height][width] uint8
+ * receives Pillow's luma plane and the horizontal Lanczos pass runs as a u8 x s8 tcgen05 product with
+ * the int8 limb tables d_tc_coef [4*32][tc_kw] / d_tc_kb0 [4] (same layout as fb_clip_preprocess, one
+ * channel); pass NULL/0 to use the CUDA-core kernel. */
 int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
              const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
-             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, void* stream);
+             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct,
+             uint8_t* d_luma, const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0,
+             void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Duplicate / burst grouping — replaces the O(N^2) loop of utils/duplicate.py:94-119 and the

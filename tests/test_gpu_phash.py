@@ -31,6 +31,15 @@ def test_phash_matches_pillow_scipy(shape):
     assert np.array_equal(ops.phash(np.ascontiguousarray(imgs[..., ::-1]), rgb_order=True), hashes)
 
 
+def test_phash_tensor_core_route_is_exact():
+    from facet_b200 import ops
+    for (h, w) in [(683, 1024), (400, 608), (2000, 3008)]:
+        imgs = np.stack([synth_image_bgr(40 + i, h, w) for i in range(3)])
+        a = ops.phash(imgs, debug=True, tensor_cores=True)
+        b = ops.phash(imgs, debug=True, tensor_cores=False)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
 def test_phash_24mp():
     from facet_b200 import ops
     from oracle import phash as op
