@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "250"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -214,9 +214,20 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry one JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=device)
+        # stdout must carry exactly one JSON line: send NCCL's start-up banner ("NCCL version ...", printed on
+        # stdout when the communicator is created) to stderr by redirecting fd 1 during initialisation
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
 
     B = args.batch
@@ -243,9 +254,11 @@ def main():
     barrier()
     # ---- timed region: K steps, CUDA events on the launching stream -------------------------------------
     launches0 = int(lib.fb_launch_count())
+    # one sampler per node (rank 0's GPU): concurrent nvidia-smi pollers slow every rank's launches
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

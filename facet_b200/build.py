@@ -35,7 +35,7 @@ def _digest() -> str:
     paths.append(os.path.join(os.path.dirname(HERE), "include", "facet_b200.h"))
     for p in paths:
         if os.path.isfile(p):
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())      # not the absolute path: the tree is relocated on the GPU box
             with open(p, "rb") as f:
                 h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -49,12 +49,30 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: facet_b200 needs the CUDA toolkit to build its kernels")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _up_to_date(digest: str) -> bool:
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as f:
-            if f.read().strip() == digest:
+            return f.read().strip() == digest
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    import fcntl
+    digest = _digest()
+    if not force and _up_to_date(digest):
+        return LIB
+    # several ranks may import the package at once: one builds, the others wait on the lock and re-check
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(digest):
                 return LIB
+            return _build_locked(digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest: str, verbose: bool) -> str:
     nvcc = nvcc_path()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -77,8 +95,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"nvcc failed on {src}\n")
     if failed:
         raise RuntimeError("building libfacet_b200.so failed")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB, *objs]
+    tmp_lib = LIB + ".tmp"
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", tmp_lib, *objs]
     subprocess.check_call(link)
+    os.replace(tmp_lib, LIB)            # atomic: a concurrent loader never sees a half-written file
     with open(STAMP, "w") as f:
         f.write(digest)
     return LIB
