@@ -84,7 +84,10 @@ def score_images_cpu(images_bgr, state_dict, tag_embeddings=None):
     """The reference's per-image pass on the CPU for a list of BGR frames (fp32 tower)."""
     import torch
     from . import vit_torch
+    from . import phash as _ph
     tech = [technical_metrics_cv(im) for im in images_bgr]
+    for t, im in zip(tech, images_bgr):
+        t["phash"] = _ph.phash_hex(im)                      # imagehash.phash, batch_processor.py:216
     clip_in = torch.stack([clip_preprocess_pil(im) for im in images_bgr])
     vit = vit_torch.score_batch(state_dict, clip_in, tag_embeddings)
     return tech, vit
