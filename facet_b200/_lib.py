@@ -26,6 +26,7 @@ _SIGNATURES = {
     "fb_profile_enable": (None, [C.c_int]),
     "fb_profile_read": (C.c_int, [_P, _P, C.c_int]),
     "fb_tech_stats": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "fb_tech_stats_luma": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
     "fb_tech_derive": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_tech_stats_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fb_gray_hsv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
@@ -34,7 +35,7 @@ _SIGNATURES = {
                                      _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int,
                                      _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_phash": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int,
-                           _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+                           _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "fb_hamming_pairs": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),
     "fb_burst_links": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_double, _P, _P, C.c_int64, _P, _P]),
 }

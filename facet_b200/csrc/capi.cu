@@ -105,11 +105,21 @@ int fb_profile_read(double* ms_per_category, uint64_t* launches_per_category, in
     return 0;
 }
 
+int fb_tech_stats_luma(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+                       uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, int force_generic, uint8_t* d_luma,
+                       void* stream) {
+    ProfScope ps(PROF_TECH, (cudaStream_t)stream);
+    int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
+                               reinterpret_cast<long long*>(d_sums), force_generic, d_luma, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
 int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
                   uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, int force_generic, void* stream) {
     ProfScope ps(PROF_TECH, (cudaStream_t)stream);
     int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
-                               reinterpret_cast<long long*>(d_sums), force_generic, (cudaStream_t)stream);
+                               reinterpret_cast<long long*>(d_sums), force_generic, nullptr, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }
@@ -204,13 +214,13 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
 
 int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
-             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma,
+             uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, int luma_ready,
              const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0, void* stream) {
     ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
     int rc = launch_phash(d_images, n, height, width, (long long)image_stride, rgb_order, d_hbounds, d_hcoef, hk, d_vbounds,
-                          d_vcoef, vk, d_tmp, reinterpret_cast<unsigned long long*>(d_hashes), d_small, d_dct, d_luma,
+                          d_vcoef, vk, d_tmp, reinterpret_cast<unsigned long long*>(d_hashes), d_small, d_dct, d_luma, luma_ready,
                           d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, (cudaStream_t)stream);
-    if (rc == 0) count_launch(d_luma ? 3 : 2);
+    if (rc == 0) count_launch(d_luma ? (luma_ready ? 2 : 3) : 2);
     return rc;
 }
 

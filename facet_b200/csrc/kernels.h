@@ -15,7 +15,7 @@ namespace fb {
 int tech_rows_per_unit(int n, int H, int W, int sms);
 int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
                       unsigned int* d_hist256, unsigned int* d_hs_hist, long long* d_sums, int force_generic,
-                      cudaStream_t stream);
+                      uint8_t* d_luma, cudaStream_t stream);
 int launch_gray_hsv(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t* d_gray, uint8_t* d_hsv,
                     cudaStream_t stream);
 int launch_hs_derive(const unsigned int* d_hs_hist, int n, double* d_out, cudaStream_t stream);
@@ -37,8 +37,8 @@ int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long
                          cudaStream_t stream);
 int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order, const int* d_hbounds,
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
-                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, const int8_t* d_tc_coef,
-                 int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
+                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, int luma_ready,
+                 const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
 

@@ -175,20 +175,23 @@ __global__ void __launch_bounds__(1024) phash_finish_kernel(const uint8_t* __res
 
 int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order, const int* d_hbounds,
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
-                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, const int8_t* d_tc_coef,
-                 int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream) {
+                 unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, int luma_ready,
+                 const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream) {
     FB_REQUIRE(d_images && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_hashes, "fb_phash: null pointer");
     FB_REQUIRE(n >= 1 && H >= 1 && W >= 1, "fb_phash: bad shape");
     // tensor-core route: Pillow luma plane, then the horizontal Lanczos pass as an exact u8 x s8 product
     int tc = 1;
     const bool plane_ok = d_luma && d_tc_coef && d_tc_kb0 && (W % 16 == 0) && image_stride == (long long)H * W * 3 &&
                           (reinterpret_cast<uintptr_t>(d_images) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_luma) & 15) == 0;
+    FB_REQUIRE(!luma_ready || plane_ok, "fb_phash: luma_ready needs the tensor-core route (width %% 16 == 0, tables, aligned plane)");
     if (plane_ok) {
-        const long long total_px = (long long)n * H * W;
-        long long blocks = (total_px / 16 + 255) / 256;
-        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-        luma_plane_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_images, total_px, rgb_order, d_luma);
-        FB_CUDA_OK(cudaGetLastError());
+        if (!luma_ready) {     // otherwise fb_tech_stats_luma already produced the plane in its pass over the frame
+            const long long total_px = (long long)n * H * W;
+            long long blocks = (total_px / 16 + 255) / 256;
+            if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+            luma_plane_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_images, total_px, rgb_order, d_luma);
+            FB_CUDA_OK(cudaGetLastError());
+        }
         tc = launch_resample_h_tc(d_luma, n, H, W, (long long)H * W, kOut, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, 0, H, d_tmp, 1, stream);
         if (tc < 0 || tc > 1) return tc;
     }

@@ -50,6 +50,8 @@ struct TechArgs {
     unsigned int* hs;
     unsigned long long* sums;
     int gray_round;   // 1 << 14, passed through the constant bank so IMAD can take it as an addend
+    uint8_t* luma;    // optional [n][H][W] Pillow luma plane (input of the pHash resampler), or nullptr
+    int luma_round;   // 1 << 15
 };
 
 __device__ __forceinline__ int sdiv_entry(int i) {   // round-half-even(255*4096 / i)
@@ -122,7 +124,7 @@ __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl,
     }
 }
 
-template <bool RGB, bool FULL>
+template <bool RGB, bool FULL, bool LUMA>
 __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* img, int tx, int uy,
                                              unsigned long long& out_l2, unsigned long long& out_n,
                                              long long& out_l) {
@@ -175,6 +177,7 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
         uint32_t w[12] = {cur.q0.x, cur.q0.y, cur.q0.z, cur.q0.w, cur.q1.x, cur.q1.y,
                           cur.q1.z, cur.q1.w, cur.q2.x, cur.q2.y, cur.q2.z, cur.q2.w};
         int gr[16];
+        uint32_t lum[4] = {0u, 0u, 0u, 0u};
         if (owned) {
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
@@ -184,6 +187,10 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
                 const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
                 const int b = RGB ? c2 : c0, g = c1, r = RGB ? c0 : c2;
                 gr[p] = (3735 * b + kRound + 19235 * g + 9798 * r) >> 15;
+                if (LUMA) {   // Pillow convert('L'): (19595 R + 38470 G + 7471 B + 2^15) >> 16
+                    const int l = (7471 * b + a.luma_round + 38470 * g + 19595 * r) >> 16;
+                    lum[p >> 2] |= (uint32_t)l << (8 * (p & 3));
+                }
                 // OpenCV RGB2HSV_b (hue range 180), branch-free
                 const int v = max(max(b, g), r);
                 const int d = v - min(min(b, g), r);
@@ -210,6 +217,10 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
                 const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
                 gr[p] = (3735 * (RGB ? c2 : c0) + kRound + 19235 * c1 + 9798 * (RGB ? c0 : c2)) >> 15;
             }
+        }
+        if (LUMA && owned && (FULL || active)) {
+            const int y = r0 - 1 + k;      // owned rows are never reflected
+            *reinterpret_cast<uint4*>(a.luma + ((size_t)(img - a.img) / 3) + (size_t)y * W + xl) = make_uint4(lum[0], lum[1], lum[2], lum[3]);
         }
         int gh;
         {
@@ -291,7 +302,7 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     }
 }
 
-template <bool RGB>
+template <bool RGB, bool LUMA>
 __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
     unsigned int* const smem = fb_smem;
     unsigned int* const s_hs = fb_smem;
@@ -331,8 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
             if (u >= seg_end) break;
             const int ul = (int)(u - img_first);
             const int tx = ul % a.tiles_x;
-            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
-            else process_unit<RGB, false>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
+            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true, LUMA>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
+            else process_unit<RGB, false, LUMA>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
         }
         acc_l2 = warp_sum_u64(acc_l2);
         acc_n = warp_sum_u64(acc_n);
@@ -404,6 +415,9 @@ __global__ void __launch_bounds__(256) tech_stats_generic_kernel(TechArgs a) {
                 g[dy + 1][dx + 1] = gray_of(RGB ? c2 : c0, c1, RGB ? c0 : c2);
                 if (dy == 0 && dx == 0) {
                     atomicAdd(g_hs + hs_bin_of(RGB ? c2 : c0, c1, RGB ? c0 : c2, s_sdiv, s_hdiv), 1u);
+                    if (a.luma)
+                        a.luma[(size_t)img_idx * W * H + i] =
+                            (uint8_t)((7471 * (RGB ? c2 : c0) + 38470 * c1 + 19595 * (RGB ? c0 : c2) + 0x8000) >> 16);
                 }
             }
         }
@@ -530,7 +544,7 @@ int tech_rows_per_unit(int n, int H, int W, int sms) {
 
 int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
                       unsigned int* d_hist256, unsigned int* d_hs_hist, long long* d_sums, int force_generic,
-                      cudaStream_t stream) {
+                      uint8_t* d_luma, cudaStream_t stream) {
     FB_REQUIRE(d_images && d_hist256 && d_hs_hist && d_sums, "fb_tech_stats: null pointer");
     FB_REQUIRE(n >= 1 && H >= 2 && W >= 2, "fb_tech_stats: need n>=1 and images of at least 2x2 (got n=%d %dx%d)", n, H, W);
     FB_REQUIRE(image_stride >= (long long)H * W * 3, "fb_tech_stats: image_stride smaller than one image");
@@ -548,6 +562,10 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     a.hs = d_hs_hist;
     a.sums = reinterpret_cast<unsigned long long*>(d_sums);
     a.gray_round = 1 << 14;
+    a.luma = d_luma;
+    a.luma_round = 1 << 15;
+    FB_REQUIRE(!d_luma || image_stride == (long long)H * W * 3, "fb_tech_stats: the luma plane needs a contiguous batch");
+    FB_REQUIRE(!d_luma || (reinterpret_cast<uintptr_t>(d_luma) & 15) == 0, "fb_tech_stats: luma plane must be 16-byte aligned");
     const bool aligned = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_images) & 15) == 0) &&
                          (image_stride % 16 == 0);
     const int sms = sm_count();
@@ -556,7 +574,8 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
         a.rows_per_unit = tech_rows_per_unit(n, H, W, sms);
         a.units_y = (H + a.rows_per_unit - 1) / a.rows_per_unit;
         const size_t smem = kSmemWords * sizeof(unsigned int);
-        auto kern = rgb_order ? tech_stats_kernel<true> : tech_stats_kernel<false>;
+        auto kern = d_luma ? (rgb_order ? tech_stats_kernel<true, true> : tech_stats_kernel<false, true>)
+                           : (rgb_order ? tech_stats_kernel<true, false> : tech_stats_kernel<false, false>);
         FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long total_units = (long long)a.tiles_x * a.units_y * n;
         int grid = (int)(total_units < sms ? total_units : sms);

@@ -43,9 +43,10 @@ def to_device_u8(images, device=None):
     return t
 
 
-def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False):
+def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False, luma_out=None):
     """Run the technical pass.  Returns CUDA tensors (hist256 u32->int32 view [n,256],
-    hs_hist int32 [n,180,256], sums int64 [n,4], derived float64 [n,4])."""
+    hs_hist int32 [n,180,256], sums int64 [n,4], derived float64 [n,4]).  luma_out: optional CUDA uint8
+    [n,H,W] tensor that receives Pillow's luma plane in the same pass (input of `phash(..., luma=...)`)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     t = to_device_u8(images)
@@ -59,8 +60,12 @@ def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False)
         sums = torch.empty((n, 4), dtype=torch.int64, device=dev)
         derived = torch.empty((n, 4), dtype=torch.float64, device=dev)
         st = _lib.stream_ptr()
-        _lib.check(lib.fb_tech_stats(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
-                                     _ptr(sums), int(bool(force_generic)), st), "fb_tech_stats")
+        if luma_out is not None:
+            _lib.check(lib.fb_tech_stats_luma(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
+                                              _ptr(sums), int(bool(force_generic)), _ptr(luma_out), st), "fb_tech_stats_luma")
+        else:
+            _lib.check(lib.fb_tech_stats(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
+                                         _ptr(sums), int(bool(force_generic)), st), "fb_tech_stats")
         _lib.check(lib.fb_tech_derive(_ptr(hs), n, _ptr(derived), st), "fb_tech_derive")
     return hist, hs, sums, derived
 
@@ -326,7 +331,14 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
 _PHASH_PLANS: dict = {}
 
 
-def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bool = True, device_only: bool = False):
+def phash_uses_luma_plane(h: int, w: int) -> bool:
+    """True when phash() takes the tensor-core route and can consume a luma plane from tech_stats_raw."""
+    from .utils import resample as rs
+    return w % 16 == 0 and rs.phash_tc_tables(h, w)[0] is not None
+
+
+def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bool = True, device_only: bool = False,
+          luma=None):
     """64-bit perceptual hashes (imagehash.phash) of a same-shaped batch.  Returns a uint64 numpy array
     (and, with debug=True, the 32x32 uint8 luma thumbnails and the 8x8 float64 DCT blocks); with
     device_only=True the CUDA int64 tensor is returned without synchronising."""
@@ -343,7 +355,11 @@ def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bo
         _PHASH_PLANS[key] = tuple(torch.from_numpy(a).to(t.device) for a in (hb, hc, vb, vc)) + (hk, vk, tc_dev)
     hb, hc, vb, vc, hk, vk, tc_dev = _PHASH_PLANS[key]
     use_tc = bool(tensor_cores) and tc_dev is not None and w % 16 == 0
-    luma = torch.empty((n, h, w), dtype=torch.uint8, device=t.device) if use_tc else None
+    luma_ready = luma is not None
+    if luma_ready and not use_tc:
+        raise ValueError("a precomputed luma plane needs the tensor-core route (width % 16 == 0)")
+    if use_tc and luma is None:
+        luma = torch.empty((n, h, w), dtype=torch.uint8, device=t.device)
     tmp = torch.empty((n, h, 32), dtype=torch.uint8, device=t.device)
     hashes = torch.empty((n,), dtype=torch.int64, device=t.device)
     small = torch.empty((n, 32, 32), dtype=torch.uint8, device=t.device) if debug else None
@@ -351,7 +367,7 @@ def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bo
     with torch.cuda.device(t.device):
         _lib.check(lib.fb_phash(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hb), _ptr(hc), hk, _ptr(vb), _ptr(vc), vk,
                                 _ptr(tmp), _ptr(hashes), _ptr(small) if debug else None, _ptr(dct) if debug else None,
-                                _ptr(luma) if use_tc else None, _ptr(tc_dev[0]) if use_tc else None,
+                                _ptr(luma) if use_tc else None, int(luma_ready), _ptr(tc_dev[0]) if use_tc else None,
                                 tc_dev[2] if use_tc else 0, tc_dev[3] if use_tc else 0, _ptr(tc_dev[1]) if use_tc else None,
                                 _lib.stream_ptr()), "fb_phash")
     if device_only:

@@ -85,8 +85,14 @@ class Facet:
     def score_images_device(self, images, rgb_order=False, with_phash=True):
         """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;
         returns device tensors (nothing is copied to the host)."""
-        hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order)
-        hashes = ops.phash(images, rgb_order=rgb_order, device_only=True) if with_phash else None
+        n, h, w, _ = images.shape
+        luma = None
+        if with_phash and ops.phash_uses_luma_plane(h, w):
+            # the technical pass also emits Pillow's luma plane, so the hash never re-reads the frame
+            import torch
+            luma = torch.empty((n, h, w), dtype=torch.uint8, device=images.device)
+        hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order, luma_out=luma)
+        hashes = ops.phash(images, rgb_order=rgb_order, device_only=True, luma=luma) if with_phash else None
         clip_in = ops.clip_preprocess(images, mean=self.mean, std=self.std, rgb_order=rgb_order)
         vit = self.model.encode(clip_in)
         return {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, **vit}

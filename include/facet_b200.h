@@ -57,6 +57,13 @@ int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t
                   int rgb_order, uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums,
                   int force_generic, void* stream);
 
+/* Same pass, additionally writing Pillow's luma plane (convert('L'): (19595 R + 38470 G + 7471 B + 2^15) >> 16)
+ * to d_luma [n][height][width] uint8 — the input of the perceptual hash's resampler (fb_phash with
+ * luma_ready = 1), so the frame is read from HBM once for both.  Needs a contiguous batch. */
+int fb_tech_stats_luma(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
+                       int rgb_order, uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums,
+                       int force_generic, uint8_t* d_luma, void* stream);
+
 /* Per-image reductions of the H-S histogram — technical.py:97-104 (entropy) and :237
  * (mean saturation).  d_out [n][4] float64 = { entropy_bits, sum_saturation, nonzero_bins,
  * total_count }. */
@@ -123,12 +130,14 @@ int fb_clip_preprocess(const uint8_t* d_images, int n, int height, int width, in
  * Optional tensor-core route (width % 16 == 0, contiguous batch): d_luma scratch [n][height][width] uint8
  * receives Pillow's luma plane and the horizontal Lanczos pass runs as a u8 x s8 tcgen05 product with
  * the int8 limb tables d_tc_coef [4*32][tc_kw] / d_tc_kb0 [4] (same layout as fb_clip_preprocess, one
- * channel); pass NULL/0 to use the CUDA-core kernel. */
+ * channel); pass NULL/0 to use the CUDA-core kernel.  luma_ready = 1: d_luma was already filled by
+ * fb_tech_stats_luma (the frame is then not read again). */
 int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
              const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
              uint8_t* d_tmp, uint64_t* d_hashes, uint8_t* d_small, double* d_dct,
-             uint8_t* d_luma, const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0,
+             uint8_t* d_luma, int luma_ready,
+             const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0,
              void* stream);
 
 /* ---------------------------------------------------------------------------------------

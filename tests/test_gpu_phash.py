@@ -40,6 +40,29 @@ def test_phash_tensor_core_route_is_exact():
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
 
 
+def test_luma_plane_from_technical_pass():
+    """fb_tech_stats_luma: same statistics, plus Pillow's luma plane that phash() can consume."""
+    import torch
+    from PIL import Image
+    from facet_b200 import ops
+    for (h, w, rgb) in [(200, 640, False), (683, 1024, True), (97, 131, False)]:
+        imgs = np.stack([synth_image_bgr(50 + i, h, w) for i in range(3)])
+        if rgb:
+            imgs = np.ascontiguousarray(imgs[..., ::-1])
+        t = ops.to_device_u8(imgs)
+        luma = torch.zeros((3, h, w), dtype=torch.uint8, device="cuda")
+        a = ops.tech_stats_raw(t, rgb_order=rgb, luma_out=luma)
+        b = ops.tech_stats_raw(t, rgb_order=rgb)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        for i in range(3):
+            rgb_img = imgs[i] if rgb else np.ascontiguousarray(imgs[i][..., ::-1])
+            want = np.asarray(Image.fromarray(rgb_img).convert("L"))
+            assert np.array_equal(luma[i].cpu().numpy(), want)
+        if ops.phash_uses_luma_plane(h, w):
+            assert np.array_equal(ops.phash(t, rgb_order=rgb, luma=luma), ops.phash(t, rgb_order=rgb))
+
+
 def test_phash_24mp():
     from facet_b200 import ops
     from oracle import phash as op
