@@ -1,0 +1,94 @@
+"""End-to-end checks of the host mirrors: Facet.score_images / BatchProcessor / ScoringPipeline vs the oracle."""
+import numpy as np
+import pytest
+
+from facet_b200.synth import synth_embeddings, synth_image_bgr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scorer():
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.processing.scorer import Facet
+    tags = synth_embeddings(24, seed=7, cluster_fraction=0.0)
+    names = [f"tag{i // 2}" for i in range(24)]
+    return Facet(random_state_dict(0), text_embeddings=tags, tag_names=names), tags, names
+
+
+def test_batch_processor_mixed_shapes_and_errors(scorer):
+    import torch
+    from facet_b200.processing.batch_processor import BatchProcessor
+    from oracle import cpu_port, technical_np as onp, vit_torch
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.models.tagger import select_tags
+    sc, tags, names = scorer
+    shapes = [(256, 384), (200, 320), (256, 384), (97, 131)]
+    items = [{"path": f"/x/img{i}.jpg", "img_cv": synth_image_bgr(i, h, w)} for i, (h, w) in enumerate(shapes)]
+    items.insert(2, {"path": "/x/broken.jpg", "error": "Failed to load image"})
+    items.append({"path": "/x/none.jpg", "img_cv": None})
+    bp = BatchProcessor(sc, batch_size=4)
+    res = list(bp.process_items(items))
+    assert [r.get("path") for r in res] == [it["path"] for it in items]
+    assert "error" in res[2] and "error" in res[-1]
+    sd = {k: v.cuda() for k, v in random_state_dict(0).items()}
+    for it, r in zip(items, res):
+        if "error" in r:
+            continue
+        img = it["img_cv"]
+        m = onp.all_metrics(img, mono_threshold=0.10)
+        assert r["histogram_data"] == m["histogram"]["histogram_bytes"]
+        assert r["is_monochrome"] == m["monochrome"]["is_monochrome"]
+        assert r["shadow_clipped"] == m["histogram"]["shadow_clipped"] and r["highlight_clipped"] == m["histogram"]["highlight_clipped"]
+        assert abs(r["raw_sharpness_variance"] - m["sharpness"]["raw_variance"]) <= 1e-9 * max(1.0, m["sharpness"]["raw_variance"])
+        assert r["noise_sigma"] == m["noise"]["noise_sigma"] and r["contrast_score"] == m["contrast"]["contrast_score"]
+        assert r["dynamic_range_stops"] == m["dynamic_range"]["dynamic_range_stops"]
+        from oracle import phash as oph
+        assert r["phash"] == oph.phash_hex(img)
+        clip_in = cpu_port.clip_preprocess_pil(img).unsqueeze(0).cuda()
+        ref = vit_torch.score_batch(sd, clip_in, torch.from_numpy(tags).cuda())
+        emb = np.frombuffer(r["clip_embedding"], np.float32)
+        assert len(r["clip_embedding"]) == 3072
+        assert float(np.dot(emb, ref["embedding"][0].cpu().numpy())) >= 0.999
+        assert abs(r["aesthetic"] - round(float(ref["aesthetic"][0]), 2)) <= 0.011
+        want_tags = select_tags(names, ref["tag_sims"][0].cpu().numpy(), 0.22, 5)
+        got_tags = r["tags"].split(",") if r["tags"] else []
+        sims = dict(zip(names, ref["tag_sims"][0].cpu().numpy()))
+        # identical unless a similarity sits within rounding distance of the threshold
+        if all(abs(float(v) - 0.22) > 2e-3 for v in sims.values()):
+            assert set(got_tags) == set(want_tags)
+    assert bp.metrics["images_failed"] == 2 and bp.metrics["images_processed"] == 4
+
+
+def test_host_pipeline_matches_direct_call(scorer):
+    import torch
+    from facet_b200.processing.pipeline import ScoringPipeline
+    sc, _, _ = scorer
+    frames = np.stack([synth_image_bgr(10 + i, 256, 384) for i in range(11)])
+    host = torch.from_numpy(frames).pin_memory()
+    pipe = ScoringPipeline(sc, chunk=4)
+    res = pipe.run_host(host)
+    direct = sc.score_images_device(torch.from_numpy(frames).cuda())
+    assert np.array_equal(res["hist256"], direct["hist256"].cpu().numpy().view(np.uint32))
+    assert np.array_equal(res["sums"], direct["sums"].cpu().numpy())
+    assert np.array_equal(res["phash"], direct["phash"].cpu().numpy().view(np.uint64))
+    np.testing.assert_allclose(res["embedding"], direct["embedding"].cpu().numpy(), rtol=0, atol=1e-6)
+    assert pipe.h2d_bytes(11, 256, 384) == frames.nbytes
+
+
+def test_tagger_and_single_image_twins(scorer):
+    from PIL import Image
+    sc, tags, names = scorer
+    img = synth_image_bgr(3, 300, 400)
+    pil = Image.fromarray(np.ascontiguousarray(img[..., ::-1]))
+    a, e, q, model = sc.get_aesthetic_and_quality(pil)
+    (a2, e2, _, _), = sc.get_aesthetic_and_quality_batch([pil])
+    assert model == "clip-mlp" and q is None and len(e) == 3072 and a == a2 and e == e2
+    got = sc.tagger.get_tags_from_embedding(e, threshold=-1.0, max_tags=3)
+    sims = np.frombuffer(e, np.float32) @ tags.T
+    best = {}
+    for n, s in zip(names, sims):
+        best[n] = max(best.get(n, -9), float(s))
+    want = [t for t, _ in sorted(best.items(), key=lambda kv: -kv[1])[:3]]
+    assert got == want
+    assert 0.0 <= sc.score_from_embedding(e) <= 10.0
