@@ -78,12 +78,17 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
+        path = os.environ.get("FACET_B200_LIB")     # kernel-variant experiments (scripts/variant_libs.sh)
+        if path:
+            build_if_missing = False
+        else:
+            path = LIB_PATH
         if build_if_missing:
             from . import build as _build
             _build.build()
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m facet_b200.build` (needs nvcc)")
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m facet_b200.build` (needs nvcc)")
+        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res

@@ -48,4 +48,10 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return r;
 }
 
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
 }  // namespace fb

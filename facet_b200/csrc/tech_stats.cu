@@ -29,13 +29,25 @@ namespace fb {
 namespace {
 
 constexpr int kHsBins = 180 * 256;
-constexpr int kThreads = 512;
+#ifndef FB_TECH_LANE_PX
+#define FB_TECH_LANE_PX 8
+#endif
+#ifndef FB_TECH_THREADS
+#define FB_TECH_THREADS 768
+#endif
+constexpr int kThreads = FB_TECH_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kLanePx = 16;
+constexpr int kLanePx = FB_TECH_LANE_PX;       // pixels per lane per row: 8 (3 x LDG.64) or 16 (3 x LDG.128)
+constexpr int kLaneWords = 3 * kLanePx / 4;
+constexpr int kPairs = kLanePx / 2;
+constexpr int kGroups = kLanePx / 4;
 constexpr int kTileW = 32 * kLanePx;   // 512 px per warp row
 constexpr int kH256Copies = 32;        // one luminance-histogram column per lane
-constexpr size_t kSmemWords = kHsBins + 256 * kH256Copies + 512 + 16;   // + work counter
-constexpr int kOffH256 = kHsBins;                       // word offsets inside the dynamic smem block
+constexpr int kHsStride = 257;          // shared-memory row stride of the H-S histogram: bank = (h + s) mod 32, so
+                                       // pixels of similar saturation and different hue do not collide
+constexpr int kHsSmemWords = 180 * kHsStride + 12;   // padded to a multiple of 16 words
+constexpr size_t kSmemWords = kHsSmemWords + 256 * kH256Copies + 512 + 16;   // + work counter
+constexpr int kOffH256 = kHsSmemWords;                  // word offsets inside the dynamic smem block
 constexpr int kOffSdiv = kOffH256 + 256 * kH256Copies;
 constexpr int kOffHdiv = kOffSdiv + 256;
 
@@ -98,23 +110,58 @@ __device__ __forceinline__ float add_f32_f16(uint16_t a, float c) {   // c + a
 }
 
 struct RowRegs {
-    uint4 q0, q1, q2;   // 48 bytes = 16 pixels
+    uint32_t w[kLaneWords];   // 3 * kLanePx bytes
     uint32_t h0, h1, h2;   // the 3 bytes of the one extra pixel lane 0 / lane 31 may need (kept raw:
                            // combining them here would stall on the load two rows early)
 };
 
 // histogram increment in shared memory (ptxas turns "+1" into the warp-aggregating
 // ATOMS.POPC.INC, which must not be predicated: FULL tiles call it unconditionally)
-__device__ __forceinline__ void smem_inc(uint32_t smem_base, int word) {
-    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_base + 4u * (uint32_t)word), "r"(1u) : "memory");
+__device__ __forceinline__ void smem_inc_addr(uint32_t addr) {
+    // no "memory" clobber: the increments only touch the histogram words, which nothing else reads or writes
+    // before the __syncthreads() that precedes the merge, so table reads may be scheduled across them
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(1u));
+}
+
+// 16-bit coefficient x 8-bit pixel dot products (IDP.2A): .lo uses bytes 0,1 of px, .hi bytes 2,3
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t coef, uint32_t px, uint32_t acc) {
+    uint32_t r;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(px), "r"(acc));
+    return r;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t coef, uint32_t px, uint32_t acc) {
+    uint32_t r;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(px), "r"(acc));
+    return r;
+}
+
+// Weighted channel sum of the 4 pixels held in three consecutive words (12 interleaved bytes):
+// out[p] = c0 + k0*ch0 + k1*ch1 + k2*ch2, two IDP.2A per pixel, no byte extraction.
+//   k01 = k0 | k1 << 16, k2_ = k2, k_0 = k0 << 16, k12 = k1 | k2 << 16
+__device__ __forceinline__ void dot4(uint32_t a, uint32_t b, uint32_t c, uint32_t k01, uint32_t k2_, uint32_t k_0,
+                                     uint32_t k12, uint32_t c0, uint32_t* out) {
+    out[0] = dp2a_hi(k2_, a, dp2a_lo(k01, a, c0));     // a0 a1 a2
+    out[1] = dp2a_lo(k12, b, dp2a_hi(k_0, a, c0));     // a3 b0 b1
+    out[2] = dp2a_lo(k2_, c, dp2a_hi(k01, b, c0));     // b2 b3 c0
+    out[3] = dp2a_hi(k12, c, dp2a_lo(k_0, c, c0));     // c1 c2 c3
 }
 
 template <bool RGB>
 __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl, bool need_halo, int hx) {
     const uint8_t* p = row + (size_t)xl * 3;
-    r.q0 = ldg_nc_v4(p);
-    r.q1 = ldg_nc_v4(p + 16);
-    r.q2 = ldg_nc_v4(p + 32);
+    if (kLanePx == 16) {
+#pragma unroll
+        for (int i = 0; i < kLaneWords / 4; ++i) {
+            const uint4 q = ldg_nc_v4(p + 16 * i);
+            r.w[4 * i] = q.x, r.w[4 * i + 1] = q.y, r.w[4 * i + 2] = q.z, r.w[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kLaneWords / 2; ++i) {
+            const uint2 q = ldg_nc_v2(p + 8 * i);
+            r.w[2 * i] = q.x, r.w[2 * i + 1] = q.y;
+        }
+    }
     r.h0 = r.h1 = r.h2 = 0;
     if (need_halo) {
         const uint8_t* h = row + (size_t)hx * 3;
@@ -124,26 +171,239 @@ __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl,
     }
 }
 
+// Per-lane constants of one unit.
+struct LaneCtx {
+    bool active, left_own, right_own, halo_left, halo_right;
+    uint32_t h256_addr;   // shared address of this lane's luminance column, minus 0x6400 * 128
+    uint32_t hs_addr;     // shared address of the H-S histogram
+    uint32_t hs_unbias;   // minus the two float magic numbers (0x4B000000 * 4 + 0x4B400000 * 4 * kHsStride)
+    uint32_t k64;         // 0x64646464 kept in a register (PRMT source of the fp16 exponent byte)
+    uint8_t* luma_row0;   // LUMA: address of (row 0, xl) in the luma plane
+    int W;
+};
+
+// Running sums of a warp: sum L^2, sum |N| (exact integers) and the telescoped sum of L as an integer-valued
+// float (flushed into an integer at the end of every unit, |value| < 2^24).
+struct WarpAcc {
+    unsigned long long l2, n;
+    long long l;
+    float lf;
+};
+
+// OpenCV RGB2HSV_b (hue range 180) of two pixels held as biased fp16 pairs (bits 0x6400 | value).  All
+// packed steps are exact in fp16 (|values| <= 1275).  Outputs: the table offsets of v and d for both pixels
+// (fp16 bit patterns 0x6400 + 4 v), d and the hue numerator as fp16 pairs.
+struct HsvPair {
+    uint32_t v4, d4;
+    __half2 d, hr;
+};
+
+template <bool RGB>
+__device__ __forceinline__ HsvPair hsv_pair(uint32_t x0, uint32_t x1, uint32_t x2) {
+    const __half2 B = bits_h2(RGB ? x2 : x0), G = bits_h2(x1), R = bits_h2(RGB ? x0 : x2);
+    const __half2 v = __hmax2(__hmax2(B, G), R);
+    const __half2 mn = __hmin2(__hmin2(B, G), R);
+    HsvPair o;
+    o.d = __hsub2(v, mn);
+    const __half2 gb = __hsub2(G, B), br = __hsub2(B, R), rg = __hsub2(R, G);
+    const __half2 two = __float2half2_rn(2.f), four = __float2half2_rn(4.f);
+    const uint32_t cg = h2_bits(__hfma2(o.d, two, br));
+    const uint32_t cb = h2_bits(__hfma2(o.d, four, rg));
+    const uint32_t m_r = __heq2_mask(v, R), m_g = __heq2_mask(v, G);
+    const uint32_t t = (m_g & cg) | (~m_g & cb);
+    o.hr = bits_h2((m_r & h2_bits(gb)) | (~m_r & t));
+    // table offsets straight from the fp16 bit patterns: 1024 + 4 v has bits 0x6400 + 4 v
+    o.v4 = h2_bits(__hfma2(v, four, __float2half2_rn(-3072.f)));
+    o.d4 = h2_bits(__hfma2(o.d, four, __float2half2_rn(1024.f)));
+    return o;
+}
+
+// The two fixed-point products of RGB2HSV_b run as round-down fp32 FMAs on tables pre-scaled by 2^-12:
+//   floor((d * sdiv[v] + 2048) / 4096) = floor(RD(d * sdiv[v] / 4096 + 0.5))
+// One H-S histogram increment per pixel; NP pairs per call so that their 4 NP table reads are in flight
+// together.
+template <bool FULL, int NP>
+__device__ __forceinline__ void hsv_bins(const HsvPair (&hp)[NP], const LaneCtx& ln) {
+    const char* tab = reinterpret_cast<const char*>(fb_smem);
+    float sdf[2 * NP], hdf[2 * NP];
+#pragma unroll
+    for (int i = 0; i < 2 * NP; ++i) {
+        const uint32_t v4 = hp[i >> 1].v4, d4 = hp[i >> 1].d4;
+        const uint32_t iv = (i & 1) ? (v4 >> 16) : (v4 & 0xffffu);
+        const uint32_t id = (i & 1) ? (d4 >> 16) : (d4 & 0xffffu);
+        sdf[i] = *reinterpret_cast<const float*>(tab + iv + (4 * kOffSdiv - 0x6400));
+        hdf[i] = *reinterpret_cast<const float*>(tab + id + (4 * kOffHdiv - 0x6400));
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * NP; ++i) {
+        const __half2 d = hp[i >> 1].d, hr = hp[i >> 1].hr;
+        const float df = (i & 1) ? __high2float(d) : __low2float(d);
+        const float hf = (i & 1) ? __high2float(hr) : __low2float(hr);
+        const uint32_t sb = __float_as_uint(__fadd_rd(__fmaf_rd(df, sdf[i], 0.5f), 8388608.f));     // 0x4B000000 + s
+        const uint32_t hb = __float_as_uint(__fadd_rd(__fmaf_rd(hf, hdf[i], 0.5f), 12582912.f));    // 0x4B400000 + h
+        // byte offset of the bin, negative (wrapped) when h < 0: the smaller of (a, a + 180 rows) is h mod 180
+        const uint32_t a0 = sb * 4u + hb * (4u * kHsStride) + ln.hs_unbias;
+        const uint32_t off = __viaddmin_u32(a0, 180u * 4u * kHsStride, a0);
+        if (FULL || ln.active) smem_inc_addr(off + ln.hs_addr);
+    }
+}
+
+// One image row of the lane's 16-pixel span.  Stencil state carried between rows (exact fp16 pairs):
+//   g_p = gray of the previous row, p1 = g[y-2] - 2 g[y-1], d_p = dxx of the previous row, q1 = dxx[y-2] - 2 dxx[y-1]
+//   hist : the row is owned by this unit -> histograms (and the luma plane)
+//   sten : the state holds rows y-2, y-1 -> Laplacian / Immerkaer response of row y-1
+//   vsign: +1 / -1 on the two rows where the vertical telescoped sum picks up g_p - g_c, else 0
 template <bool RGB, bool FULL, bool LUMA>
-__device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* img, int tx, int uy,
-                                             unsigned long long& out_l2, unsigned long long& out_n,
-                                             long long& out_l) {
+__device__ __forceinline__ void row_step(const RowRegs& cur, const LaneCtx& ln, bool hist, bool sten, float vsign, int y,
+                                         const __half2 (&g_p)[kPairs], __half2 (&g_c)[kPairs],
+                                         const __half2 (&d_p)[kPairs], __half2 (&d_c)[kPairs], __half2 (&p1)[kPairs],
+                                         __half2 (&q1)[kPairs], WarpAcc& acc) {
+    const uint32_t (&w)[kLaneWords] = cur.w;
+    // gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15, computed with doubled coefficients so that the high
+    // half of the accumulator is the fp16 bit pattern of 1024 + gray
+    constexpr uint32_t kB = 2 * 3735, kG = 2 * 19235, kR = 2 * 9798;
+    constexpr uint32_t k0 = RGB ? kR : kB, k2 = RGB ? kB : kR;
+    uint32_t ga[kLanePx];
+#pragma unroll
+    for (int q = 0; q < kGroups; ++q)
+        dot4(w[3 * q], w[3 * q + 1], w[3 * q + 2], k0 | (kG << 16), k2, k0 << 16, kG | (k2 << 16), 0x64008000u, ga + 4 * q);
+
+    // gray pairs as fp16 (the accumulators die here)
+    const __half2 k1024 = __half2half2(__ushort_as_half(0x6400));
+    if (hist) {
+#pragma unroll
+        for (int p = 0; p < kLanePx; ++p) {
+            uint32_t addr;     // (0x6400 + gray) * 128 + lane column; kept as SHF + IMAD (one per pipe)
+            asm volatile("{.reg .b32 t; shr.u32 t, %1, 16; mad.lo.u32 %0, t, 128, %2;}" : "=r"(addr) : "r"(ga[p]), "r"(ln.h256_addr));
+            if (FULL || ln.active) smem_inc_addr(addr);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) g_c[j] = __hsub2(bits_h2(__byte_perm(ga[2 * j], ga[2 * j + 1], 0x7632)), k1024);
+
+    if (hist) {
+        const uint32_t k64 = ln.k64;
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) {
+            HsvPair hp[2];
+            const uint32_t wa = w[3 * q], wb = w[3 * q + 1], wc = w[3 * q + 2];
+            // channel pairs of pixels (0,1) and (2,3) of the group as biased fp16 pairs (0x64 in the odd bytes)
+            const uint32_t p0 = __byte_perm(wa, k64, 0x4340);                              // a0 a3
+            const uint32_t p1_ = __byte_perm(__byte_perm(wa, k64, 0x4441), wb, 0x1410);    // a1 b0
+            const uint32_t p2 = __byte_perm(__byte_perm(wa, k64, 0x4442), wb, 0x1510);     // a2 b1
+            hp[0] = hsv_pair<RGB>(p0, p1_, p2);
+            const uint32_t r0 = __byte_perm(__byte_perm(wb, k64, 0x4442), wc, 0x1510);     // b2 c1
+            const uint32_t r1 = __byte_perm(__byte_perm(wb, k64, 0x4443), wc, 0x1610);     // b3 c2
+            const uint32_t r2 = __byte_perm(wc, k64, 0x4340);                              // c0 c3
+            hp[1] = hsv_pair<RGB>(r0, r1, r2);
+            hsv_bins<FULL, 2>(hp, ln);
+        }
+        if (LUMA) {   // Pillow convert('L'): (19595 R + 38470 G + 7471 B + 2^15) >> 16
+            constexpr uint32_t l0 = RGB ? 19595u : 7471u, l2 = RGB ? 7471u : 19595u;
+            uint32_t lw[kGroups];
+#pragma unroll
+            for (int q = 0; q < kGroups; ++q) {
+                uint32_t la[4];
+                dot4(w[3 * q], w[3 * q + 1], w[3 * q + 2], l0 | (38470u << 16), l2, l0 << 16, 38470u | (l2 << 16), 0x8000u, la);
+                lw[q] = __byte_perm(__byte_perm(la[0], la[1], 0x0062), __byte_perm(la[2], la[3], 0x0062), 0x5410);
+            }
+            if (FULL || ln.active) {
+                if (kLanePx == 16) *reinterpret_cast<uint4*>(ln.luma_row0 + (size_t)y * ln.W) = make_uint4(lw[0], lw[1], lw[kGroups - 2], lw[kGroups - 1]);
+                else *reinterpret_cast<uint2*>(ln.luma_row0 + (size_t)y * ln.W) = make_uint2(lw[0], lw[1]);
+            }
+        }
+    }
+
+    int gh;
+    {
+        const int c0 = (int)cur.h0, c1 = (int)cur.h1, c2 = (int)cur.h2;
+        gh = gray_of(RGB ? c2 : c0, c1, RGB ? c0 : c2);
+    }
+    const uint32_t halo_h2 = h2_bits(u16x2_to_half2((uint32_t)gh | ((uint32_t)gh << 16)));
+
+    // neighbours across lanes (both halves of the shuffled register are valid gray values)
+    uint32_t from_left = __shfl_up_sync(0xffffffffu, h2_bits(g_c[kPairs - 1]), 1);     // .hi = last gray of lane-1
+    uint32_t from_right = __shfl_down_sync(0xffffffffu, h2_bits(g_c[0]), 1);  // .lo = g[0] of lane+1
+    if (ln.left_own) from_left = h2_bits(g_c[0]);                 // .hi = own g[1]
+    if (ln.halo_left) from_left = halo_h2;
+    if (ln.right_own) from_right = h2_bits(g_c[kPairs - 1]);      // .lo = own last-but-one gray
+    if (ln.halo_right) from_right = halo_h2;
+
+    // shifted pairs S_j = (g[2j-1], g[2j]), j = 0..kPairs
+    uint32_t S[kPairs + 1];
+    S[0] = __byte_perm(from_left, h2_bits(g_c[0]), 0x5432);
+#pragma unroll
+    for (int j = 1; j < kPairs; ++j) S[j] = __byte_perm(h2_bits(g_c[j - 1]), h2_bits(g_c[j]), 0x5432);
+    S[kPairs] = __byte_perm(h2_bits(g_c[kPairs - 1]), from_right, 0x5432);
+
+    const __half2 kMinus2 = __float2half2_rn(-2.f);
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) d_c[j] = __hfma2(g_c[j], kMinus2, __hadd2(bits_h2(S[j]), bits_h2(S[j + 1])));
+
+    if (hist) {
+        // sum_x dxx over the lane's span telescopes to (gl - g0) + (gr - g15)
+        __half2 t = __hsub2(bits_h2(S[0]), bits_h2(S[kPairs]));      // (gl - g_last, g0 - gr)
+        float s = add_f32_f16((uint16_t)(h2_bits(t) & 0xffffu), 0.f);
+        s = add_f32_f16((uint16_t)((h2_bits(t) >> 16) ^ 0x8000u), s);
+        if (FULL || ln.active) acc.lf += s;
+    }
+    if (vsign != 0.f) {
+        // sum_y dyy telescopes to (g[r0-1]-g[r0]) + (g[r1]-g[r1-1]) per column
+        __half2 t = __float2half2_rn(0.f);
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) t = __hadd2(t, __hsub2(g_p[j], g_c[j]));
+        if (FULL || ln.active) acc.lf += vsign * (__low2float(t) + __high2float(t));
+    }
+    if (sten) {
+        float l2a = 0.f, l2b = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+            const uint32_t lb = h2_bits(__hadd2(__hadd2(d_p[j], p1[j]), g_c[j]));      // dxx + dyy of row y-1
+            const uint32_t nn = h2_bits(__habs2(__hadd2(q1[j], d_c[j])));              // |dyy(dxx)| of row y-1
+            l2a = fma_f32_f16((uint16_t)(lb & 0xffffu), l2a);
+            l2b = fma_f32_f16((uint16_t)(lb >> 16), l2b);
+            na = add_f32_f16((uint16_t)(nn & 0xffffu), na);
+            nb = add_f32_f16((uint16_t)(nn >> 16), nb);
+        }
+        // 16 * 1020^2 < 2^24 and 16 * 2040 < 2^24: both row sums are exact in fp32
+        if (FULL || ln.active) {
+            acc.l2 += (unsigned long long)__float2uint_rn(l2a + l2b);
+            acc.n += (unsigned long long)__float2uint_rn(na + nb);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+        p1[j] = __hfma2(g_c[j], kMinus2, g_p[j]);
+        q1[j] = __hfma2(d_c[j], kMinus2, d_p[j]);
+    }
+}
+
+template <bool RGB, bool FULL, bool LUMA>
+__device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* img, int tx, int uy, WarpAcc& acc) {
     const int lane = (int)lane_id();
     const int W = a.W, H = a.H;
     const int r0 = uy * a.rows_per_unit;
     const int r1 = min(H, r0 + a.rows_per_unit);
     const int rb = r1 - r0;
     const int x0 = tx * kTileW + lane * kLanePx;
-    const bool active = x0 < W;
-    const int xl = active ? x0 : (W - kLanePx);
+    LaneCtx ln;
+    ln.active = x0 < W;
+    const int xl = ln.active ? x0 : (W - kLanePx);
     // left / right neighbour of the lane's 16-pixel span
-    const bool left_own = (xl == 0);                 // reflect-101: x=-1 -> x=1
-    const bool right_own = (xl + kLanePx == W);      // x=W -> x=W-2
-    const bool halo_left = (lane == 0) && !left_own;
-    const bool halo_right = (lane == 31) && !right_own;
-    const bool need_halo = halo_left || halo_right;
-    const int hx = halo_left ? (xl - 1) : (xl + kLanePx);
+    ln.left_own = (xl == 0);                 // reflect-101: x=-1 -> x=1
+    ln.right_own = (xl + kLanePx == W);      // x=W -> x=W-2
+    ln.halo_left = (lane == 0) && !ln.left_own;
+    ln.halo_right = (lane == 31) && !ln.right_own;
+    const bool need_halo = ln.halo_left || ln.halo_right;
+    const int hx = ln.halo_left ? (xl - 1) : (xl + kLanePx);
     const size_t row_bytes = (size_t)W * 3;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fb_smem);
+    ln.h256_addr = smem_base + 4u * (uint32_t)(kOffH256 + lane) - 0x6400u * 128u;
+    ln.hs_addr = smem_base;
+    ln.hs_unbias = 0u - 4u * 0x4B000000u - (4u * kHsStride) * 0x4B400000u;
+    asm volatile("mov.b32 %0, 0x64646464;" : "=r"(ln.k64));
+    ln.W = W;
+    ln.luma_row0 = LUMA ? (a.luma + ((size_t)(img - a.img) / 3) + xl) : nullptr;
 
     auto row_ptr = [&](int k) -> const uint8_t* {     // k-th row of the walk: r0-1 .. r1
         int y = r0 - 1 + k;
@@ -152,154 +412,30 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
         return img + (size_t)y * row_bytes;
     };
 
-    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fb_smem);
-    const int kRound = a.gray_round;
     const int nrows = rb + 2;
-    RowRegs cur, nx1, nx2;
-    load_row<RGB>(cur, row_ptr(0), xl, need_halo, hx);
-    load_row<RGB>(nx1, row_ptr(1), xl, need_halo, hx);
+    RowRegs LA, LB;
+    load_row<RGB>(LA, row_ptr(0), xl, need_halo, hx);
 
-    __half2 g_pp[8], g_p[8], d_pp[8], d_p[8];
+    __half2 GA[kPairs], GB[kPairs], DA[kPairs], DB[kPairs], P1[kPairs], Q1[kPairs];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        g_pp[j] = g_p[j] = d_pp[j] = d_p[j] = __float2half2_rn(0.f);
+    for (int j = 0; j < kPairs; ++j) GA[j] = GB[j] = DA[j] = DB[j] = P1[j] = Q1[j] = __float2half2_rn(0.f);
+    acc.lf = 0.f;
+
+    // row k: prefetches row k+1, histograms if 1 <= k <= rb, stencil output of row k-1 if k >= 2.  Two rows
+    // per trip so that the (previous, current) register sets alternate by renaming instead of by moves.
+#define FB_ROW(K, CUR, NXT, GP, GC, DP, DC)                                                                   \
+    if ((K) < nrows) {                                                                                        \
+        if ((K) + 1 < nrows) load_row<RGB>(NXT, row_ptr((K) + 1), xl, need_halo, hx);                         \
+        row_step<RGB, FULL, LUMA>(CUR, ln, (K) >= 1 && (K) <= rb, (K) >= 2,                                   \
+                                  (K) == 1 ? 1.f : ((K) == rb + 1 ? -1.f : 0.f), r0 - 1 + (K), GP, GC, DP, DC, \
+                                  P1, Q1, acc);                                                               \
     }
-    float acc_lh = 0.f, acc_lh2 = 0.f;      // horizontal telescoped part of sum(L)
-    float acc_lv = 0.f;                     // vertical telescoped part
-    unsigned long long acc_l2 = 0ull;
-    unsigned int acc_n = 0u;
-    const __half2 kMinus2 = __float2half2_rn(-2.f);
-
-    for (int k = 0; k < nrows; ++k) {
-        if (k + 2 < nrows) load_row<RGB>(nx2, row_ptr(k + 2), xl, need_halo, hx);
-        const bool owned = (k >= 1) && (k <= rb);
-
-        uint32_t w[12] = {cur.q0.x, cur.q0.y, cur.q0.z, cur.q0.w, cur.q1.x, cur.q1.y,
-                          cur.q1.z, cur.q1.w, cur.q2.x, cur.q2.y, cur.q2.z, cur.q2.w};
-        int gr[16];
-        uint32_t lum[4] = {0u, 0u, 0u, 0u};
-        if (owned) {
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                const int o = 3 * p;
-                const int c0 = (int)__byte_perm(w[o >> 2], 0u, 0x4440 + (o & 3));
-                const int c1 = (int)__byte_perm(w[(o + 1) >> 2], 0u, 0x4440 + ((o + 1) & 3));
-                const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
-                const int b = RGB ? c2 : c0, g = c1, r = RGB ? c0 : c2;
-                gr[p] = (3735 * b + kRound + 19235 * g + 9798 * r) >> 15;
-                if (LUMA) {   // Pillow convert('L'): (19595 R + 38470 G + 7471 B + 2^15) >> 16
-                    const int l = (7471 * b + a.luma_round + 38470 * g + 19595 * r) >> 16;
-                    lum[p >> 2] |= (uint32_t)l << (8 * (p & 3));
-                }
-                // OpenCV RGB2HSV_b (hue range 180), branch-free
-                const int v = max(max(b, g), r);
-                const int d = v - min(min(b, g), r);
-                const int sd = (int)fb_smem[kOffSdiv + v];
-                const int hd = (int)fb_smem[kOffHdiv + d];
-                const bool vr = (v == r), vg = (v == g);
-                const int x = vr ? g : (vg ? b : r);
-                const int y = vr ? b : (vg ? r : g);
-                const int off = vr ? 0 : (vg ? 2 * d : 4 * d);
-                const int sat = (d * sd + 2048) >> 12;
-                int hue = ((x - y + off) * hd + 2048) >> 12;
-                hue += (hue >> 31) & 180;
-                if (FULL || active) {
-                    smem_inc(smem_base, hue * 256 + sat);
-                    smem_inc(smem_base, kOffH256 + gr[p] * kH256Copies + lane);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                const int o = 3 * p;
-                const int c0 = (int)__byte_perm(w[o >> 2], 0u, 0x4440 + (o & 3));
-                const int c1 = (int)__byte_perm(w[(o + 1) >> 2], 0u, 0x4440 + ((o + 1) & 3));
-                const int c2 = (int)__byte_perm(w[(o + 2) >> 2], 0u, 0x4440 + ((o + 2) & 3));
-                gr[p] = (3735 * (RGB ? c2 : c0) + kRound + 19235 * c1 + 9798 * (RGB ? c0 : c2)) >> 15;
-            }
-        }
-        if (LUMA && owned && (FULL || active)) {
-            const int y = r0 - 1 + k;      // owned rows are never reflected
-            *reinterpret_cast<uint4*>(a.luma + ((size_t)(img - a.img) / 3) + (size_t)y * W + xl) = make_uint4(lum[0], lum[1], lum[2], lum[3]);
-        }
-        int gh;
-        {
-            const int c0 = (int)cur.h0, c1 = (int)cur.h1, c2 = (int)cur.h2;
-            gh = gray_of(RGB ? c2 : c0, c1, RGB ? c0 : c2);
-        }
-
-        __half2 g_c[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            g_c[j] = u16x2_to_half2(__byte_perm((uint32_t)gr[2 * j], (uint32_t)gr[2 * j + 1], 0x5410));
-        const uint32_t halo_h2 = h2_bits(u16x2_to_half2((uint32_t)gh | ((uint32_t)gh << 16)));
-
-        // neighbours across lanes (both halves of the shuffled register are valid gray values)
-        uint32_t from_left = __shfl_up_sync(0xffffffffu, h2_bits(g_c[7]), 1);     // .hi = g[15] of lane-1
-        uint32_t from_right = __shfl_down_sync(0xffffffffu, h2_bits(g_c[0]), 1);  // .lo = g[0] of lane+1
-        if (left_own) from_left = h2_bits(g_c[0]);                 // .hi = own g[1]
-        if (halo_left) from_left = halo_h2;
-        if (right_own) from_right = h2_bits(g_c[7]);               // .lo = own g[14]
-        if (halo_right) from_right = halo_h2;
-
-        // shifted pairs S_j = (g[2j-1], g[2j]), j = 0..8
-        uint32_t S[9];
-        S[0] = __byte_perm(from_left, h2_bits(g_c[0]), 0x5432);
-#pragma unroll
-        for (int j = 1; j < 8; ++j) S[j] = __byte_perm(h2_bits(g_c[j - 1]), h2_bits(g_c[j]), 0x5432);
-        S[8] = __byte_perm(h2_bits(g_c[7]), from_right, 0x5432);
-
-        __half2 d_c[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            d_c[j] = __hfma2(g_c[j], kMinus2, __hadd2(bits_h2(S[j]), bits_h2(S[j + 1])));
-
-        if (owned) {
-            // sum_x dxx over the lane's span telescopes to (gl - g0) + (gr - g15)
-            __half2 t = __hsub2(bits_h2(S[0]), bits_h2(S[8]));      // (gl - g15, g0 - gr)
-            acc_lh = add_f32_f16((uint16_t)(h2_bits(t) & 0xffffu), acc_lh);
-            acc_lh2 = add_f32_f16((uint16_t)(h2_bits(t) >> 16), acc_lh2);
-        }
-        if (k == 1 || k == rb + 1) {
-            // sum_y dyy telescopes to (g[r0-1]-g[r0]) + (g[r1]-g[r1-1]) per column
-            __half2 t = __float2half2_rn(0.f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t = __hadd2(t, __hsub2(g_p[j], g_c[j]));
-            float s = __low2float(t) + __high2float(t);
-            acc_lv += (k == 1) ? s : -s;
-        }
-        if (k >= 2) {
-            float row_l2 = 0.f, row_n = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                __half2 dyy = __hfma2(g_p[j], kMinus2, __hadd2(g_pp[j], g_c[j]));
-                __half2 L = __hadd2(d_p[j], dyy);
-                __half2 N = __habs2(__hfma2(d_p[j], kMinus2, __hadd2(d_pp[j], d_c[j])));
-                uint32_t lb = h2_bits(L), nb = h2_bits(N);
-                row_l2 = fma_f32_f16((uint16_t)(lb & 0xffffu), row_l2);
-                row_l2 = fma_f32_f16((uint16_t)(lb >> 16), row_l2);
-                row_n = add_f32_f16((uint16_t)(nb & 0xffffu), row_n);
-                row_n = add_f32_f16((uint16_t)(nb >> 16), row_n);
-            }
-            // 16 * 1020^2 < 2^24 and 16 * 2040 < 2^24: both row sums are exact in fp32
-            acc_l2 += (unsigned long long)__float2uint_rn(row_l2);
-            acc_n += __float2uint_rn(row_n);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            g_pp[j] = g_p[j];
-            g_p[j] = g_c[j];
-            d_pp[j] = d_p[j];
-            d_p[j] = d_c[j];
-        }
-        cur = nx1;
-        nx1 = nx2;
+    for (int k = 0; k < nrows; k += 2) {
+        FB_ROW(k, LA, LB, GA, GB, DA, DB)
+        FB_ROW(k + 1, LB, LA, GB, GA, DB, DA)
     }
-    if (active) {
-        out_l2 += acc_l2;
-        out_n += acc_n;
-        out_l += (long long)__float2int_rn(acc_lh - acc_lh2) + (long long)__float2int_rn(acc_lv);
-    }
+#undef FB_ROW
+    acc.l += (long long)__float2int_rn(acc.lf);
 }
 
 template <bool RGB, bool LUMA>
@@ -312,11 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
     unsigned int* const s_next = fb_smem + kOffHdiv + 256;       // next unclaimed unit of the current segment
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    for (int i = tid; i < kHsBins + 256 * kH256Copies; i += kThreads) smem[i] = 0u;
+    for (int i = tid; i < kHsSmemWords + 256 * kH256Copies; i += kThreads) smem[i] = 0u;
     if (tid < 256) {
-        s_sdiv[tid] = (unsigned int)sdiv_entry(tid);
-        s_hdiv[tid] = (unsigned int)hdiv_entry(tid);
+        // fixed-point reciprocals pre-scaled by 2^-12 (exact in fp32: integers below 2^21)
+        s_sdiv[tid] = __float_as_uint((float)sdiv_entry(tid) * (1.f / 4096.f));
+        s_hdiv[tid] = __float_as_uint((float)hdiv_entry(tid) * (1.f / 4096.f));
     }
     if (tid == 0) *s_next = 0u;
     __syncthreads();
@@ -332,8 +468,10 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         const long long seg_end = min(u_end, img_first + upi);
         const uint8_t* img = a.img + (size_t)img_idx * a.img_stride;
 
-        unsigned long long acc_l2 = 0ull, acc_n = 0ull;
-        long long acc_l = 0;
+        WarpAcc acc;
+        acc.l2 = acc.n = 0ull;
+        acc.l = 0;
+        acc.lf = 0.f;
         // warps claim units of the segment dynamically (s_next is reset between segments)
         for (;;) {
             long long u = 0;
@@ -342,12 +480,12 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
             if (u >= seg_end) break;
             const int ul = (int)(u - img_first);
             const int tx = ul % a.tiles_x;
-            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true, LUMA>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
-            else process_unit<RGB, false, LUMA>(a, img, tx, ul / a.tiles_x, acc_l2, acc_n, acc_l);
+            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true, LUMA>(a, img, tx, ul / a.tiles_x, acc);
+            else process_unit<RGB, false, LUMA>(a, img, tx, ul / a.tiles_x, acc);
         }
-        acc_l2 = warp_sum_u64(acc_l2);
-        acc_n = warp_sum_u64(acc_n);
-        unsigned long long l_bits = warp_sum_u64((unsigned long long)acc_l);
+        const unsigned long long acc_l2 = warp_sum_u64(acc.l2);
+        const unsigned long long acc_n = warp_sum_u64(acc.n);
+        const unsigned long long l_bits = warp_sum_u64((unsigned long long)acc.l);
         if ((tid & 31) == 0) {
             unsigned long long* s = a.sums + (size_t)img_idx * 4;
             atomicAdd(s + 0, l_bits);
@@ -359,10 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         if (tid == 0) *s_next = 0u;
         unsigned int* g_hs = a.hs + (size_t)img_idx * kHsBins;
         for (int i = tid; i < kHsBins; i += kThreads) {
-            unsigned int c = s_hs[i];
+            const int si = (i >> 8) * kHsStride + (i & 255);
+            unsigned int c = s_hs[si];
             if (c) {
                 atomicAdd(g_hs + i, c);
-                s_hs[i] = 0u;
+                s_hs[si] = 0u;
             }
         }
         if (tid < 256) {
@@ -530,14 +669,16 @@ int launch_gray_hsv(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t
 }
 
 int tech_rows_per_unit(int n, int H, int W, int sms) {
-    // aim for >= 8 units per warp so the static round-robin balances, cap the halo overhead at ~4 %
+    // aim for >= 32 units per warp: warps claim units dynamically and wait for each other at the end of an
+    // image segment, so the tail is about one unit per segment; the two halo rows of a unit only cost the gray
+    // conversion (about 1.5 % at 32 rows)
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const long long want = (long long)sms * kWarps * 8;
+    const long long want = (long long)sms * kWarps * 32;
     long long units_y = (want + (long long)n * tiles_x - 1) / ((long long)n * tiles_x);
     if (units_y < 1) units_y = 1;
     int rows = (int)((H + units_y - 1) / units_y);
-    if (rows < 48) rows = 48;
-    if (rows > 512) rows = 512;
+    if (rows < 32) rows = 32;
+    if (rows > 128) rows = 128;
     if (rows > H) rows = H;
     return rows;
 }
@@ -566,8 +707,9 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     a.luma_round = 1 << 15;
     FB_REQUIRE(!d_luma || image_stride == (long long)H * W * 3, "fb_tech_stats: the luma plane needs a contiguous batch");
     FB_REQUIRE(!d_luma || (reinterpret_cast<uintptr_t>(d_luma) & 15) == 0, "fb_tech_stats: luma plane must be 16-byte aligned");
-    const bool aligned = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_images) & 15) == 0) &&
-                         (image_stride % 16 == 0);
+    constexpr int kAlign = kLanePx == 16 ? 16 : 8;     // vector width of the row loads
+    const bool aligned = (W % kLanePx == 0) && ((reinterpret_cast<uintptr_t>(d_images) & (kAlign - 1)) == 0) &&
+                         (image_stride % kAlign == 0) && (W >= kLanePx);
     const int sms = sm_count();
     if (aligned && !force_generic) {
         a.tiles_x = (W + kTileW - 1) / kTileW;
