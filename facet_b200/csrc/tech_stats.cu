@@ -109,18 +109,30 @@ __device__ __forceinline__ float add_f32_f16(uint16_t a, float c) {   // c + a
     return r;
 }
 
+// Shared-window address of the dynamic shared memory block.  On sm_100 the first KiB of the window is reserved
+// for the system, so a kernel without static shared memory sees its dynamic block at 0x400; the launcher
+// verifies this once with a probe kernel (and falls back to the generic kernel if it ever differs), which
+// lets every histogram / table access use a compile-time offset instead of an address add.
+constexpr uint32_t kSmemBase = 0x400;
+
 struct RowRegs {
     uint32_t w[kLaneWords];   // 3 * kLanePx bytes
-    uint32_t h0, h1, h2;   // the 3 bytes of the one extra pixel lane 0 / lane 31 may need (kept raw:
-                           // combining them here would stall on the load two rows early)
+    uint32_t halo;            // the aligned word that holds the one extra pixel lane 0 / lane 31 may need
 };
 
-// histogram increment in shared memory (ptxas turns "+1" into the warp-aggregating
-// ATOMS.POPC.INC, which must not be predicated: FULL tiles call it unconditionally)
-__device__ __forceinline__ void smem_inc_addr(uint32_t addr) {
-    // no "memory" clobber: the increments only touch the histogram words, which nothing else reads or writes
-    // before the __syncthreads() that precedes the merge, so table reads may be scheduled across them
-    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(1u));
+// histogram increment in shared memory at [addr + OFF] (ptxas turns "+1" into the warp-aggregating
+// ATOMS.POPC.INC, which must not be predicated: FULL tiles call it unconditionally).  No "memory" clobber:
+// the increments only touch histogram words, which nothing else reads or writes before the __syncthreads()
+// that precedes the merge, so table reads may be scheduled across them.
+template <uint32_t OFF>
+__device__ __forceinline__ void smem_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "r"(1u));
+}
+template <uint32_t OFF>
+__device__ __forceinline__ float smem_ld_f32(uint32_t addr) {
+    float r;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(addr), "n"(OFF));
+    return r;
 }
 
 // 16-bit coefficient x 8-bit pixel dot products (IDP.2A): .lo uses bytes 0,1 of px, .hi bytes 2,3
@@ -146,9 +158,20 @@ __device__ __forceinline__ void dot4(uint32_t a, uint32_t b, uint32_t c, uint32_
     out[3] = dp2a_hi(k12, c, dp2a_lo(k_0, c, c0));     // c1 c2 c3
 }
 
-template <bool RGB>
-__device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl, bool need_halo, int hx) {
-    const uint8_t* p = row + (size_t)xl * 3;
+// Per-lane constants of one unit.
+struct LaneCtx {
+    bool active, left_own, right_own, halo_left, halo_right;
+    uint32_t h256_off;    // byte offset of this lane's luminance column, minus 0x6400 * 128
+    uint32_t k64;         // 0x64646464 kept in a register (PRMT source of the fp16 exponent byte)
+    uint32_t hs_unbias;   // minus the two float magic numbers (0x4B000000 * 4 + 0x4B400000 * 4 * kHsStride)
+    int halo_delta;       // byte distance from the lane's first pixel to the aligned word with the halo pixel
+    uint8_t* luma_lane;   // LUMA: address of (row 0, xl) in the luma plane
+    int W;
+};
+
+template <bool NEED_HALO_CHECK = true>
+__device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* img, uint32_t off, bool need_halo, int halo_delta) {
+    const uint8_t* p = img + off;
     if (kLanePx == 16) {
 #pragma unroll
         for (int i = 0; i < kLaneWords / 4; ++i) {
@@ -162,32 +185,18 @@ __device__ __forceinline__ void load_row(RowRegs& r, const uint8_t* row, int xl,
             r.w[2 * i] = q.x, r.w[2 * i + 1] = q.y;
         }
     }
-    r.h0 = r.h1 = r.h2 = 0;
-    if (need_halo) {
-        const uint8_t* h = row + (size_t)hx * 3;
-        r.h0 = __ldg(h);
-        r.h1 = __ldg(h + 1);
-        r.h2 = __ldg(h + 2);
-    }
+    r.halo = 0u;
+    if (need_halo) r.halo = __ldg(reinterpret_cast<const unsigned int*>(p + halo_delta));
 }
 
-// Per-lane constants of one unit.
-struct LaneCtx {
-    bool active, left_own, right_own, halo_left, halo_right;
-    uint32_t h256_addr;   // shared address of this lane's luminance column, minus 0x6400 * 128
-    uint32_t hs_addr;     // shared address of the H-S histogram
-    uint32_t hs_unbias;   // minus the two float magic numbers (0x4B000000 * 4 + 0x4B400000 * 4 * kHsStride)
-    uint32_t k64;         // 0x64646464 kept in a register (PRMT source of the fp16 exponent byte)
-    uint8_t* luma_row0;   // LUMA: address of (row 0, xl) in the luma plane
-    int W;
-};
-
-// Running sums of a warp: sum L^2, sum |N| (exact integers) and the telescoped sum of L as an integer-valued
-// float (flushed into an integer at the end of every unit, |value| < 2^24).
+// Running sums of a warp: sum L^2, sum |N| (exact integers) and the telescoped sum of L.
 struct WarpAcc {
     unsigned long long l2, n;
     long long l;
-    float lf;
+    // per unit: integer-valued floats / a 32-bit integer, flushed into the 64-bit sums at the end of the unit
+    // (128 rows x 16 px: sum L < 2^24, sum |N| < 2^24 exactly representable; sum L^2 < 2^32)
+    float lf, nf;
+    unsigned int l2u;
 };
 
 // OpenCV RGB2HSV_b (hue range 180) of two pixels held as biased fp16 pairs (bits 0x6400 | value).  All
@@ -218,68 +227,107 @@ __device__ __forceinline__ HsvPair hsv_pair(uint32_t x0, uint32_t x1, uint32_t x
     return o;
 }
 
-// The two fixed-point products of RGB2HSV_b run as round-down fp32 FMAs on tables pre-scaled by 2^-12:
-//   floor((d * sdiv[v] + 2048) / 4096) = floor(RD(d * sdiv[v] / 4096 + 0.5))
+// The two fixed-point products of RGB2HSV_b run as one round-down packed fp32 FMA (FFMA2) on tables
+// pre-scaled by 2^-12, followed by a round-down add of 2^23 / 1.5 * 2^23 that leaves the integers in the
+// low mantissa bits:   floor((d * sdiv[v] + 2048) / 4096) = floor(RD(d * sdiv[v] / 4096 + 0.5))
+__device__ __forceinline__ void fixed_products(float d, float hr, float sdf, float hdf, uint32_t& sb, uint32_t& hb) {
+    asm("{.reg .b64 a, b, c, m;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 b, {%4, %5};\n\t"
+        "mov.b64 c, {%6, %6};\n\t"
+        "mov.b64 m, {%7, %8};\n\t"
+        "fma.rm.f32x2 a, a, b, c;\n\t"
+        "add.rm.f32x2 a, a, m;\n\t"
+        "mov.b64 {%0, %1}, a;}"
+        : "=r"(sb), "=r"(hb)
+        : "f"(d), "f"(hr), "f"(sdf), "f"(hdf), "f"(0.5f), "f"(8388608.f), "f"(12582912.f));
+}
+
 // One H-S histogram increment per pixel; NP pairs per call so that their 4 NP table reads are in flight
 // together.
 template <bool FULL, int NP>
 __device__ __forceinline__ void hsv_bins(const HsvPair (&hp)[NP], const LaneCtx& ln) {
-    const char* tab = reinterpret_cast<const char*>(fb_smem);
     float sdf[2 * NP], hdf[2 * NP];
 #pragma unroll
     for (int i = 0; i < 2 * NP; ++i) {
         const uint32_t v4 = hp[i >> 1].v4, d4 = hp[i >> 1].d4;
         const uint32_t iv = (i & 1) ? (v4 >> 16) : (v4 & 0xffffu);
         const uint32_t id = (i & 1) ? (d4 >> 16) : (d4 & 0xffffu);
-        sdf[i] = *reinterpret_cast<const float*>(tab + iv + (4 * kOffSdiv - 0x6400));
-        hdf[i] = *reinterpret_cast<const float*>(tab + id + (4 * kOffHdiv - 0x6400));
+        sdf[i] = smem_ld_f32<kSmemBase + 4 * kOffSdiv - 0x6400>(iv);
+        hdf[i] = smem_ld_f32<kSmemBase + 4 * kOffHdiv - 0x6400>(id);
     }
 #pragma unroll
     for (int i = 0; i < 2 * NP; ++i) {
         const __half2 d = hp[i >> 1].d, hr = hp[i >> 1].hr;
         const float df = (i & 1) ? __high2float(d) : __low2float(d);
         const float hf = (i & 1) ? __high2float(hr) : __low2float(hr);
-        const uint32_t sb = __float_as_uint(__fadd_rd(__fmaf_rd(df, sdf[i], 0.5f), 8388608.f));     // 0x4B000000 + s
-        const uint32_t hb = __float_as_uint(__fadd_rd(__fmaf_rd(hf, hdf[i], 0.5f), 12582912.f));    // 0x4B400000 + h
+        uint32_t sb, hb;      // 0x4B000000 + s, 0x4B400000 + h
+        fixed_products(df, hf, sdf[i], hdf[i], sb, hb);
         // byte offset of the bin, negative (wrapped) when h < 0: the smaller of (a, a + 180 rows) is h mod 180
-        const uint32_t a0 = sb * 4u + hb * (4u * kHsStride) + ln.hs_unbias;
-        const uint32_t off = __viaddmin_u32(a0, 180u * 4u * kHsStride, a0);
-        if (FULL || ln.active) smem_inc_addr(off + ln.hs_addr);
+        // (IMAD + LEA + VIADDMNMX; written as PTX so that the three steps are not re-associated into four)
+        uint32_t off;
+        asm("{.reg .b32 t, u;\n\t"
+            "mad.lo.u32 t, %2, %4, %3;\n\t"
+            "shl.b32 u, %1, 2;\n\t"
+            "add.u32 t, t, u;\n\t"
+            "add.u32 u, t, %5;\n\t"
+            "min.u32 %0, t, u;}"
+            : "=r"(off) : "r"(sb), "r"(hb), "r"(ln.hs_unbias), "n"(4 * kHsStride), "n"(180 * 4 * kHsStride));
+        if (FULL || ln.active) smem_inc<kSmemBase>(off);
     }
 }
 
-// One image row of the lane's 16-pixel span.  Stencil state carried between rows (exact fp16 pairs):
-//   g_p = gray of the previous row, p1 = g[y-2] - 2 g[y-1], d_p = dxx of the previous row, q1 = dxx[y-2] - 2 dxx[y-1]
-//   hist : the row is owned by this unit -> histograms (and the luma plane)
-//   sten : the state holds rows y-2, y-1 -> Laplacian / Immerkaer response of row y-1
-//   vsign: +1 / -1 on the two rows where the vertical telescoped sum picks up g_p - g_c, else 0
-template <bool RGB, bool FULL, bool LUMA>
-__device__ __forceinline__ void row_step(const RowRegs& cur, const LaneCtx& ln, bool hist, bool sten, float vsign, int y,
+enum RowMode { ROW_FIRST = 0, ROW_SECOND = 1, ROW_STEADY = 2, ROW_LAST = 3 };
+
+// One image row of the lane's pixel span.  Stencil state carried between rows (exact fp16 pairs; gray keeps
+// its +1024 bias, which cancels in every difference):
+//   g_p = gray of the previous row, p1 = g[y-2] - 2 g[y-1] - 1024, d_p = dxx of the previous row,
+//   q1 = dxx[y-2] - 2 dxx[y-1]
+// MODE: FIRST  = halo row above the unit (gray only)
+//       SECOND = first owned row: histograms, vertical telescoped sum picks up g_p - g_c
+//       STEADY = owned row: histograms + Laplacian / Immerkaer response of the previous row
+//       LAST   = halo row below the unit: stencil of the last owned row, vertical sum picks up -(g_p - g_c)
+template <bool RGB, bool FULL, bool LUMA, int MODE>
+__device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const uint8_t* img, uint32_t next_off,
+                                         bool need_halo, const LaneCtx& ln, int y,
                                          const __half2 (&g_p)[kPairs], __half2 (&g_c)[kPairs],
                                          const __half2 (&d_p)[kPairs], __half2 (&d_c)[kPairs], __half2 (&p1)[kPairs],
                                          __half2 (&q1)[kPairs], WarpAcc& acc) {
+    constexpr bool hist = (MODE == ROW_SECOND || MODE == ROW_STEADY);
+    constexpr bool sten = (MODE == ROW_STEADY || MODE == ROW_LAST);
+#ifdef FB_TECH_PREFETCH_EARLY
+    if (MODE != ROW_LAST) load_row(nxt, img, next_off, need_halo, ln.halo_delta);
+#endif
     const uint32_t (&w)[kLaneWords] = cur.w;
     // gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15, computed with doubled coefficients so that the high
     // half of the accumulator is the fp16 bit pattern of 1024 + gray
     constexpr uint32_t kB = 2 * 3735, kG = 2 * 19235, kR = 2 * 9798;
     constexpr uint32_t k0 = RGB ? kR : kB, k2 = RGB ? kB : kR;
+    constexpr uint32_t k01 = k0 | (kG << 16), k2_ = k2, k_0 = k0 << 16, k12 = kG | (k2 << 16);
     uint32_t ga[kLanePx];
 #pragma unroll
-    for (int q = 0; q < kGroups; ++q)
-        dot4(w[3 * q], w[3 * q + 1], w[3 * q + 2], k0 | (kG << 16), k2, k0 << 16, kG | (k2 << 16), 0x64008000u, ga + 4 * q);
+    for (int q = 0; q < kGroups; ++q) dot4(w[3 * q], w[3 * q + 1], w[3 * q + 2], k01, k2_, k_0, k12, 0x64008000u, ga + 4 * q);
+    // the halo pixel sits in bytes 1..3 (left: word before the span) or 0..2 (right: word after it)
+    const uint32_t gha = ln.halo_left ? dp2a_hi(k12, cur.halo, dp2a_lo(k_0, cur.halo, 0x64008000u))
+                                      : dp2a_hi(k2_, cur.halo, dp2a_lo(k01, cur.halo, 0x64008000u));
+    const uint32_t halo_h2 = __byte_perm(gha, 0u, 0x3232);
+    // prefetch the next row only now: issued before the first read of this row's registers, the new loads
+    // would share a scoreboard with the loads that read waits for, and the read would wait for them too
+#ifndef FB_TECH_PREFETCH_EARLY
+    if (MODE != ROW_LAST) load_row(nxt, img, next_off, need_halo, ln.halo_delta);
+#endif
 
-    // gray pairs as fp16 (the accumulators die here)
-    const __half2 k1024 = __half2half2(__ushort_as_half(0x6400));
     if (hist) {
 #pragma unroll
         for (int p = 0; p < kLanePx; ++p) {
             uint32_t addr;     // (0x6400 + gray) * 128 + lane column; kept as SHF + IMAD (one per pipe)
-            asm volatile("{.reg .b32 t; shr.u32 t, %1, 16; mad.lo.u32 %0, t, 128, %2;}" : "=r"(addr) : "r"(ga[p]), "r"(ln.h256_addr));
-            if (FULL || ln.active) smem_inc_addr(addr);
+            asm volatile("{.reg .b32 t; shr.u32 t, %1, 16; mad.lo.u32 %0, t, 128, %2;}" : "=r"(addr) : "r"(ga[p]), "r"(ln.h256_off));
+            if (FULL || ln.active) smem_inc<kSmemBase + 4 * kOffH256>(addr);
         }
     }
+    // gray pairs as biased fp16 (the accumulators die here)
 #pragma unroll
-    for (int j = 0; j < kPairs; ++j) g_c[j] = __hsub2(bits_h2(__byte_perm(ga[2 * j], ga[2 * j + 1], 0x7632)), k1024);
+    for (int j = 0; j < kPairs; ++j) g_c[j] = bits_h2(__byte_perm(ga[2 * j], ga[2 * j + 1], 0x7632));
 
     if (hist) {
         const uint32_t k64 = ln.k64;
@@ -308,18 +356,11 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, const LaneCtx& ln, 
                 lw[q] = __byte_perm(__byte_perm(la[0], la[1], 0x0062), __byte_perm(la[2], la[3], 0x0062), 0x5410);
             }
             if (FULL || ln.active) {
-                if (kLanePx == 16) *reinterpret_cast<uint4*>(ln.luma_row0 + (size_t)y * ln.W) = make_uint4(lw[0], lw[1], lw[kGroups - 2], lw[kGroups - 1]);
-                else *reinterpret_cast<uint2*>(ln.luma_row0 + (size_t)y * ln.W) = make_uint2(lw[0], lw[1]);
+                if (kLanePx == 16) *reinterpret_cast<uint4*>(ln.luma_lane + (size_t)y * ln.W) = make_uint4(lw[0], lw[1], lw[kGroups - 2], lw[kGroups - 1]);
+                else *reinterpret_cast<uint2*>(ln.luma_lane + (size_t)y * ln.W) = make_uint2(lw[0], lw[1]);
             }
         }
     }
-
-    int gh;
-    {
-        const int c0 = (int)cur.h0, c1 = (int)cur.h1, c2 = (int)cur.h2;
-        gh = gray_of(RGB ? c2 : c0, c1, RGB ? c0 : c2);
-    }
-    const uint32_t halo_h2 = h2_bits(u16x2_to_half2((uint32_t)gh | ((uint32_t)gh << 16)));
 
     // neighbours across lanes (both halves of the shuffled register are valid gray values)
     uint32_t from_left = __shfl_up_sync(0xffffffffu, h2_bits(g_c[kPairs - 1]), 1);     // .hi = last gray of lane-1
@@ -336,23 +377,25 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, const LaneCtx& ln, 
     for (int j = 1; j < kPairs; ++j) S[j] = __byte_perm(h2_bits(g_c[j - 1]), h2_bits(g_c[j]), 0x5432);
     S[kPairs] = __byte_perm(h2_bits(g_c[kPairs - 1]), from_right, 0x5432);
 
+    // dxx = g[x-1] - 2 g[x] + g[x+1]; with biased gray (1024 + g) the fma leaves a - 2 g - 1024, exact below 2048
     const __half2 kMinus2 = __float2half2_rn(-2.f);
 #pragma unroll
-    for (int j = 0; j < kPairs; ++j) d_c[j] = __hfma2(g_c[j], kMinus2, __hadd2(bits_h2(S[j]), bits_h2(S[j + 1])));
+    for (int j = 0; j < kPairs; ++j) d_c[j] = __hadd2(__hfma2(g_c[j], kMinus2, bits_h2(S[j])), bits_h2(S[j + 1]));
 
     if (hist) {
-        // sum_x dxx over the lane's span telescopes to (gl - g0) + (gr - g15)
+        // sum_x dxx over the lane's span telescopes to (gl - g0) + (gr - g_last)
         __half2 t = __hsub2(bits_h2(S[0]), bits_h2(S[kPairs]));      // (gl - g_last, g0 - gr)
         float s = add_f32_f16((uint16_t)(h2_bits(t) & 0xffffu), 0.f);
         s = add_f32_f16((uint16_t)((h2_bits(t) >> 16) ^ 0x8000u), s);
         if (FULL || ln.active) acc.lf += s;
     }
-    if (vsign != 0.f) {
+    if (MODE == ROW_SECOND || MODE == ROW_LAST) {
         // sum_y dyy telescopes to (g[r0-1]-g[r0]) + (g[r1]-g[r1-1]) per column
         __half2 t = __float2half2_rn(0.f);
 #pragma unroll
         for (int j = 0; j < kPairs; ++j) t = __hadd2(t, __hsub2(g_p[j], g_c[j]));
-        if (FULL || ln.active) acc.lf += vsign * (__low2float(t) + __high2float(t));
+        const float s = __low2float(t) + __high2float(t);
+        if (FULL || ln.active) acc.lf += (MODE == ROW_SECOND) ? s : -s;
     }
     if (sten) {
         float l2a = 0.f, l2b = 0.f, na = 0.f, nb = 0.f;
@@ -367,14 +410,16 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, const LaneCtx& ln, 
         }
         // 16 * 1020^2 < 2^24 and 16 * 2040 < 2^24: both row sums are exact in fp32
         if (FULL || ln.active) {
-            acc.l2 += (unsigned long long)__float2uint_rn(l2a + l2b);
-            acc.n += (unsigned long long)__float2uint_rn(na + nb);
+            acc.l2u += __float2uint_rn(l2a + l2b);
+            acc.nf += na + nb;
         }
     }
+    if (MODE != ROW_LAST) {
 #pragma unroll
-    for (int j = 0; j < kPairs; ++j) {
-        p1[j] = __hfma2(g_c[j], kMinus2, g_p[j]);
-        q1[j] = __hfma2(d_c[j], kMinus2, d_p[j]);
+        for (int j = 0; j < kPairs; ++j) {
+            p1[j] = __hfma2(g_c[j], kMinus2, g_p[j]);      // g_p - 2 g_c - 1024
+            q1[j] = __hfma2(d_c[j], kMinus2, d_p[j]);
+        }
     }
 }
 
@@ -383,59 +428,65 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     const int lane = (int)lane_id();
     const int W = a.W, H = a.H;
     const int r0 = uy * a.rows_per_unit;
-    const int r1 = min(H, r0 + a.rows_per_unit);
-    const int rb = r1 - r0;
+    const int rb = min(H, r0 + a.rows_per_unit) - r0;
     const int x0 = tx * kTileW + lane * kLanePx;
     LaneCtx ln;
     ln.active = x0 < W;
     const int xl = ln.active ? x0 : (W - kLanePx);
-    // left / right neighbour of the lane's 16-pixel span
+    // left / right neighbour of the lane's span
     ln.left_own = (xl == 0);                 // reflect-101: x=-1 -> x=1
     ln.right_own = (xl + kLanePx == W);      // x=W -> x=W-2
     ln.halo_left = (lane == 0) && !ln.left_own;
     ln.halo_right = (lane == 31) && !ln.right_own;
     const bool need_halo = ln.halo_left || ln.halo_right;
-    const int hx = ln.halo_left ? (xl - 1) : (xl + kLanePx);
-    const size_t row_bytes = (size_t)W * 3;
-    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(fb_smem);
-    ln.h256_addr = smem_base + 4u * (uint32_t)(kOffH256 + lane) - 0x6400u * 128u;
-    ln.hs_addr = smem_base;
-    ln.hs_unbias = 0u - 4u * 0x4B000000u - (4u * kHsStride) * 0x4B400000u;
+    ln.halo_delta = ln.halo_left ? -4 : 3 * kLanePx;
+    ln.h256_off = 4u * (uint32_t)lane - 0x6400u * 128u;
     asm volatile("mov.b32 %0, 0x64646464;" : "=r"(ln.k64));
+    asm volatile("mov.b32 %0, %1;" : "=r"(ln.hs_unbias) : "n"(0u - 4u * 0x4B000000u - (4u * kHsStride) * 0x4B400000u));
     ln.W = W;
-    ln.luma_row0 = LUMA ? (a.luma + ((size_t)(img - a.img) / 3) + xl) : nullptr;
+    ln.luma_lane = LUMA ? (a.luma + ((size_t)(img - a.img) / 3) + xl) : nullptr;
 
-    auto row_ptr = [&](int k) -> const uint8_t* {     // k-th row of the walk: r0-1 .. r1
+    const uint32_t row_bytes = (uint32_t)W * 3u;
+    const uint32_t lane_off = (uint32_t)xl * 3u;
+    auto row_off = [&](int k) -> uint32_t {     // byte offset of the lane's span in the k-th row of the walk: r0-1 .. r1
         int y = r0 - 1 + k;
         y = (y < 0) ? 1 : y;
         y = (y >= H) ? (H - 2) : y;
-        return img + (size_t)y * row_bytes;
+        return (uint32_t)y * row_bytes + lane_off;
     };
 
-    const int nrows = rb + 2;
     RowRegs LA, LB;
-    load_row<RGB>(LA, row_ptr(0), xl, need_halo, hx);
-
     __half2 GA[kPairs], GB[kPairs], DA[kPairs], DB[kPairs], P1[kPairs], Q1[kPairs];
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) GA[j] = GB[j] = DA[j] = DB[j] = P1[j] = Q1[j] = __float2half2_rn(0.f);
-    acc.lf = 0.f;
+    acc.lf = acc.nf = 0.f;
+    acc.l2u = 0u;
 
-    // row k: prefetches row k+1, histograms if 1 <= k <= rb, stencil output of row k-1 if k >= 2.  Two rows
-    // per trip so that the (previous, current) register sets alternate by renaming instead of by moves.
-#define FB_ROW(K, CUR, NXT, GP, GC, DP, DC)                                                                   \
-    if ((K) < nrows) {                                                                                        \
-        if ((K) + 1 < nrows) load_row<RGB>(NXT, row_ptr((K) + 1), xl, need_halo, hx);                         \
-        row_step<RGB, FULL, LUMA>(CUR, ln, (K) >= 1 && (K) <= rb, (K) >= 2,                                   \
-                                  (K) == 1 ? 1.f : ((K) == rb + 1 ? -1.f : 0.f), r0 - 1 + (K), GP, GC, DP, DC, \
-                                  P1, Q1, acc);                                                               \
+    // rows k = 0 .. rb+1 of the walk; row k prefetches row k+1.  Rows alternate between two register sets so
+    // that (previous, current) swap by renaming instead of by moves.
+    load_row(LA, img, row_off(0), need_halo, ln.halo_delta);
+    row_step<RGB, FULL, LUMA, ROW_FIRST>(LA, LB, img, row_off(1), need_halo, ln, r0 - 1, GB, GA, DB, DA, P1, Q1, acc);
+    row_step<RGB, FULL, LUMA, ROW_SECOND>(LB, LA, img, row_off(2), need_halo, ln, r0, GA, GB, DA, DB, P1, Q1, acc);
+    bool odd_tail = false;
+    int k = 2;
+    for (; k <= rb; k += 2) {
+        row_step<RGB, FULL, LUMA, ROW_STEADY>(LA, LB, img, row_off(k + 1), need_halo, ln, r0 - 1 + k, GB, GA, DB, DA, P1, Q1, acc);
+        if (k + 1 > rb) {
+            odd_tail = true;
+            break;
+        }
+        row_step<RGB, FULL, LUMA, ROW_STEADY>(LB, LA, img, row_off(k + 2), need_halo, ln, r0 + k, GA, GB, DA, DB, P1, Q1, acc);
     }
-    for (int k = 0; k < nrows; k += 2) {
-        FB_ROW(k, LA, LB, GA, GB, DA, DB)
-        FB_ROW(k + 1, LB, LA, GB, GA, DB, DA)
-    }
-#undef FB_ROW
+    if (odd_tail) row_step<RGB, FULL, LUMA, ROW_LAST>(LB, LA, img, 0u, need_halo, ln, r0 + rb, GA, GB, DA, DB, P1, Q1, acc);
+    else row_step<RGB, FULL, LUMA, ROW_LAST>(LA, LB, img, 0u, need_halo, ln, r0 + rb, GB, GA, DB, DA, P1, Q1, acc);
+
     acc.l += (long long)__float2int_rn(acc.lf);
+    acc.n += (unsigned long long)__float2uint_rn(acc.nf);
+    acc.l2 += (unsigned long long)acc.l2u;
+}
+
+__global__ void smem_base_probe_kernel(unsigned int* out) {
+    if (threadIdx.x == 0) *out = (unsigned int)__cvta_generic_to_shared(fb_smem);
 }
 
 template <bool RGB, bool LUMA>
@@ -471,7 +522,6 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
         WarpAcc acc;
         acc.l2 = acc.n = 0ull;
         acc.l = 0;
-        acc.lf = 0.f;
         // warps claim units of the segment dynamically (s_next is reset between segments)
         for (;;) {
             long long u = 0;
@@ -711,7 +761,23 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     const bool aligned = (W % kLanePx == 0) && ((reinterpret_cast<uintptr_t>(d_images) & (kAlign - 1)) == 0) &&
                          (image_stride % kAlign == 0) && (W >= kLanePx);
     const int sms = sm_count();
-    if (aligned && !force_generic) {
+    // the fast kernel addresses shared memory with compile-time offsets from kSmemBase: check once that the
+    // dynamic block really starts there on this driver
+    static int smem_base_ok = -1;
+    if (smem_base_ok < 0) {
+        unsigned int* d_probe = nullptr;
+        unsigned int h_probe = 0;
+        FB_CUDA_OK(cudaMalloc(&d_probe, sizeof(unsigned int)));
+        smem_base_probe_kernel<<<1, 32, 1024, stream>>>(d_probe);
+        FB_CUDA_OK(cudaMemcpyAsync(&h_probe, d_probe, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        FB_CUDA_OK(cudaStreamSynchronize(stream));
+        FB_CUDA_OK(cudaFree(d_probe));
+        smem_base_ok = (h_probe == kSmemBase) ? 1 : 0;
+        if (!smem_base_ok)
+            fprintf(stderr, "facet_b200: dynamic shared memory starts at 0x%x, not 0x%x: the technical pass uses its "
+                            "generic (slow) kernel\n", h_probe, kSmemBase);
+    }
+    if (aligned && !force_generic && smem_base_ok) {
         a.tiles_x = (W + kTileW - 1) / kTileW;
         a.rows_per_unit = tech_rows_per_unit(n, H, W, sms);
         a.units_y = (H + a.rows_per_unit - 1) / a.rows_per_unit;
