@@ -95,6 +95,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // similarity mode only needs tiles that contain an element with col > global row
     constexpr bool tri = (MODE == FB_GEMM_THRESHOLD_PAIRS);
 #define FB_TILE_SKIPPED(m0_, n0_) (tri && ((n0_) + BN <= (m0_) + p.row_offset + 1))
+    // Tile order.  Plain GEMMs walk row-major (their B operand is a weight matrix that stays in L2).  The
+    // similarity scan has a B operand far larger than L2, so its tiles are walked in groups of kGroupM tile
+    // rows, column by column: the CTAs running at any moment share kGroupM A tiles and every B tile is used
+    // kGroupM times while it is hot in L2 (HBM traffic per tile / kGroupM).
+    constexpr int kGroupM = 16;
+#define FB_TILE_COORDS(tile_, m0_, n0_)                                             \
+    int m0_, n0_;                                                                   \
+    if (tri) {                                                                      \
+        const int per_group_ = kGroupM * tiles_n;                                   \
+        const int g_ = (tile_) / per_group_;                                        \
+        const int w_ = (tile_) - g_ * per_group_;                                   \
+        const int gm_ = min(kGroupM, tiles_m - g_ * kGroupM);                       \
+        m0_ = (g_ * kGroupM + w_ % gm_) * BM;                                       \
+        n0_ = (w_ / gm_) * BN;                                                      \
+    } else {                                                                        \
+        m0_ = ((tile_) / tiles_n) * BM;                                             \
+        n0_ = ((tile_) % tiles_n) * BN;                                             \
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -124,7 +142,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                FB_TILE_COORDS(tile, m0, n0)
                 if (FB_TILE_SKIPPED(m0, n0)) continue;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -144,7 +162,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int iter = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                if (FB_TILE_SKIPPED((tile / tiles_n) * BM, (tile % tiles_n) * BN)) continue;
+                FB_TILE_COORDS(tile, m0, n0)
+                if (FB_TILE_SKIPPED(m0, n0)) continue;
                 const int acc = iter & 1;
                 tc::mbar_wait(&tmem_empty[acc], ((iter >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
@@ -177,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr bool bf16_out = (MODE == FB_GEMM_BIAS_BF16 || MODE == FB_GEMM_BIAS_GELU_BF16);
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            FB_TILE_COORDS(tile, m0, n0)
             if (FB_TILE_SKIPPED(m0, n0)) continue;
             const int acc = iter & 1;
             const int rbase = m0 + quarter * 32;
@@ -212,7 +231,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int col0 = ncol0 + c * 32;
                 if (MODE == FB_GEMM_THRESHOLD_PAIRS) {
                     const int grow = p.row_offset + row;
-                    if (row_ok && col0 + 31 > grow) {
+                    // candidates are rare: one max over the lane's 32 values decides whether to look at them at all
+                    float vmax = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) vmax = fmaxf(vmax, __uint_as_float(v[j]));
+                    if (row_ok && col0 + 31 > grow && vmax >= p.tau) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float sim = __uint_as_float(v[j]);
