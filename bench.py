@@ -313,7 +313,9 @@ def main():
                 "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
                                      "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"],
                                      "algorithmic_bytes_per_step": B * TECH_BYTES_PER_IMAGE,
-                                     "traffic": 592.0e6 / 8 * B, "traffic_note": "ncu dram bytes read, 8-frame capture scaled"}}
+                                     "traffic": (610.1e6 + 144.9e6) / 8 * B,
+                                     "traffic_note": "ncu dram bytes read + written (frames + the luma plane the pass also emits "
+                                                     "for the pHash), 8-frame capture of profiles/r1_tech_stats_ncu_v2.txt scaled"}}
 
     # ---- e2e: pinned host frames -> pipeline (H2D + kernels + D2H inside the timed region) ---------------
     e2e = None

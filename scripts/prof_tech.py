@@ -9,8 +9,10 @@ from facet_b200 import ops  # noqa: E402
 from time_tech import make_frames  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "photo"
+with_luma = len(sys.argv) > 2 and sys.argv[2] == "luma"
 fr = make_frames(kind, 8)
+luma = torch.empty(fr.shape[:3], dtype=torch.uint8, device=fr.device) if with_luma else None
 for _ in range(3):
-    ops.tech_stats_raw(fr)
+    ops.tech_stats_raw(fr, luma_out=luma)
 torch.cuda.synchronize()
 print("ok")
