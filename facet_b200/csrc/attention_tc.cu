@@ -1,17 +1,21 @@
 // Attention of the ViT-L/14 tower on tcgen05: softmax(Q K^T / 8) V per (image, head), 257 tokens, d = 64.
 // (what open_clip's nn.MultiheadAttention does inside `encode_image`, processing/scorer.py:662.)
 //
-// Persistent kernel, one CTA per SM, 256 threads = two independent warpgroups; each warpgroup walks
+// Persistent kernel, one CTA per SM, 512 threads = two independent groups of 8 warps; each group walks
 // its own queue of (image, head) pairs with its own shared-memory tiles and its own 256 TMEM
-// columns, so the tensor-core / TMA phases of one warpgroup overlap the softmax of the other.
+// columns, so the tensor-core / TMA phases of one group overlap the softmax of the other.  Inside a
+// group two threads share a query row (warps w and w+4 address the same 32 TMEM lanes): one takes the
+// scores of keys 0..127, the other those of keys 128..255; row maximum and sum are exchanged through
+// shared memory.
 // Per (image, head), for the two 128-row query tiles t = 0, 1:
 //   TMA      Q (2 x 128 rows), K and V (256 rows each) from the fused qkv buffer, 128-byte swizzle;
 //            the next pair's Q/K (V) loads are issued as soon as the last MMA reading them retires
 //   tcgen05  S = Q_t K^T           M=128, N=256, K=64, fp32 accumulator in TMEM columns [0,256)
-//   softmax  one thread per query row (tcgen05.ld), exact fp32 max / exp2 / sum; P is written back
-//            to TMEM as packed bf16 over the S columns it has already consumed (tcgen05.st)
+//   softmax  two threads per query row (tcgen05.ld), exact fp32 max / exp2 / sum; P is written back
+//            to TMEM as packed 16-bit pairs over S columns its writer has already consumed
+//            (tcgen05.st): keys 0..127 -> columns [0,64), keys 128..255 -> columns [128,192)
 //   tcgen05  O = P V               A operand from TMEM, V as an MN-major B operand straight from
-//            the TMA tile; M=128, N=64, K=256; accumulator in TMEM columns [128,192)
+//            the TMA tile; M=128, N=64, K=256; accumulator in TMEM columns [64,128)
 //   the 257th token is handled on the CUDA cores: as a key (one extra score per row folded into the
 //   softmax, one rank-1 update in the epilogue) and as a query (one row against all 257 keys)
 #include <cuda_bf16.h>
@@ -25,7 +29,8 @@ namespace fb {
 namespace {
 
 constexpr int kTok = 257, kW = 1024, kD = 64;
-constexpr int kThreadsAttn = 256;
+constexpr int kThreadsAttn = 512;
+constexpr int kWgThreads = 256;
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
 
 // per-warpgroup shared memory map (bytes)
@@ -33,14 +38,17 @@ constexpr int kOffQ = 0;                 // 2 x [128][64] bf16, 128B swizzle
 constexpr int kOffK = 32768;             // [256][64]
 constexpr int kOffV = 65536;             // [256][64]
 constexpr int kOffX = 98304;             // scalars, exchange arrays, barriers
-constexpr int kWgBytes = 98304 + 4096;
+constexpr int kWgBytes = 98304 + 8192;
 constexpr int kSmemAttn = 2 * kWgBytes + 1024;
 
 struct XArea {
     float q256[64], k256[64], v256[64];
     float cls_p[264];
-    float cls_red[8];
-    float cls_o[2][64];
+    float cls_red[16];
+    float cls_o[4][64];
+    float s256[2][128];      // score of query row r of tile t against key 256
+    float xmax[2][128];      // row maximum / sum of each column half
+    float xsum[2][128];
     uint64_t bar_qk, bar_v, bar_s, bar_pv;
 };
 
@@ -91,7 +99,7 @@ __device__ __forceinline__ float ex2_fast(float x) {      // MUFU.EX2, flush-to-
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
 
 template <bool F16>
 __global__ void __launch_bounds__(kThreadsAttn, 1)
@@ -99,10 +107,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
                     uint16_t* __restrict__ out, int n_pairs) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tmem_slot;
-    uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared pointer (a round trip through an integer would
+    // make every later access a generic LD/ST instead of LDS/STS)
+    uint8_t* smem0 = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wg = warp >> 2;                       // warpgroup 0 / 1
-    const int wt = tid & 127;                       // thread within the warpgroup == query row within a tile
+    const int wg = warp >> 3;                       // group 0 / 1
+    const int wt = tid & 255;                       // thread within the group
+    const int row = wt & 127;                       // query row within a tile
+    const int half = wt >> 7;                       // which 128 keys of the row this thread owns
     uint8_t* smem = smem0 + wg * kWgBytes;
     XArea* X = reinterpret_cast<XArea*>(smem + kOffX);
 
@@ -119,10 +131,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot + wg * 256;                               // this warpgroup's 256 columns
+    const uint32_t tmem = tmem_slot + wg * 256;                               // this group's 256 columns
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;             // TMEM lanes this warp may touch
-    const uint32_t t_s = tmem + lane_base;                                    // S: columns [0,256); P aliases [0,128)
-    const uint32_t t_o = tmem + lane_base + 128;                              // O: columns [128,192)
+    const uint32_t t_s = tmem + lane_base + half * 128;                       // this thread's 128 S columns
+    const uint32_t t_p = tmem + lane_base + half * 128;                       // P of keys [128 half, +128): 64 columns
+    const uint32_t t_o = tmem + lane_base + 64 + half * 32;                   // O: columns [64,128), 32 per thread
     const uint32_t idesc_s = tc::make_idesc16<F16>(128, 256);
     const uint32_t idesc_o = tc::make_idesc16<F16>(128, 64, 0, 1);
 
@@ -168,30 +181,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
             tc::umma_commit(&X->bar_s);
         }
-        // scores of this thread's row (both tiles) against key 256; CUDA cores, overlaps the MMA
-        const float s256_0 = dot64_row<F16>(smem + kOffQ, wt, X->k256);
-        const float s256_1 = dot64_row<F16>(smem + kOffQ + 16384, wt, X->k256);
+        // score of query row `row` of tile `half` against key 256; CUDA cores, overlaps the MMA
+        X->s256[half][row] = dot64_row<F16>(smem + kOffQ + half * 16384, row, X->k256);
 
-        // ---- query row 256 against all 257 keys ----
+        // ---- query row 256 against all 257 keys (thread = key) ----
         tc::mbar_wait(&X->bar_v, ph_load);
         {
             const float sa = dot64_row<F16>(smem + kOffK, wt, X->q256);
-            const float sb = dot64_row<F16>(smem + kOffK, wt + 128, X->q256);
             float s_last = -INFINITY;
             if (wt == 0) {
                 s_last = 0.f;
                 for (int d = 0; d < 64; ++d) s_last = fmaf(X->q256[d], X->k256[d], s_last);
             }
-            float mx = fmaxf(fmaxf(sa, sb), s_last);
+            float mx = fmaxf(sa, s_last);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) X->cls_red[warp & 3] = mx;
+            if (lane == 0) X->cls_red[warp & 7] = mx;
             wg_sync(wg);
-            mx = fmaxf(fmaxf(X->cls_red[0], X->cls_red[1]), fmaxf(X->cls_red[2], X->cls_red[3]));
-            const float pa = ex2_fast((sa - mx) * kScaleLog2), pb = ex2_fast((sb - mx) * kScaleLog2);
+            mx = fmaxf(fmaxf(fmaxf(X->cls_red[0], X->cls_red[1]), fmaxf(X->cls_red[2], X->cls_red[3])),
+                       fmaxf(fmaxf(X->cls_red[4], X->cls_red[5]), fmaxf(X->cls_red[6], X->cls_red[7])));
+            const float pa = ex2_fast((sa - mx) * kScaleLog2);
             X->cls_p[wt] = pa;
-            X->cls_p[wt + 128] = pb;
-            float sum = pa + pb;
+            float sum = pa;
             if (wt == 0) {
                 const float pl = ex2_fast((s_last - mx) * kScaleLog2);
                 X->cls_p[256] = pl;
@@ -199,21 +210,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) X->cls_red[4 + (warp & 3)] = sum;
+            if (lane == 0) X->cls_red[8 + (warp & 7)] = sum;
             wg_sync(wg);
-            // o[d] = sum_j p_j V[j][d]: thread = (d, half of the keys)
+            // o[d] = sum_j p_j V[j][d]: thread = (d, quarter of the keys)
             const int d = wt & 63, part = wt >> 6;
             float acc = 0.f;
 #pragma unroll 8
-            for (int j = part * 128; j < part * 128 + 128; ++j) {
+            for (int j = part * 64; j < part * 64 + 64; ++j) {
                 const uint32_t w = reinterpret_cast<const uint32_t*>(sw_chunk(smem + kOffV, j, d >> 3))[(d & 7) >> 1];
                 acc = fmaf(X->cls_p[j], (d & 1) ? tc::hi16<F16>(w) : tc::lo16<F16>(w), acc);
             }
             X->cls_o[part][d] = acc;
             wg_sync(wg);
             if (wt < 64) {
-                const float tot = (X->cls_red[4] + X->cls_red[5]) + (X->cls_red[6] + X->cls_red[7]);
-                const float o = X->cls_o[0][wt] + X->cls_o[1][wt] + X->cls_p[256] * X->v256[wt];
+                const float tot = ((X->cls_red[8] + X->cls_red[9]) + (X->cls_red[10] + X->cls_red[11])) +
+                                  ((X->cls_red[12] + X->cls_red[13]) + (X->cls_red[14] + X->cls_red[15]));
+                const float o = (X->cls_o[0][wt] + X->cls_o[1][wt]) + (X->cls_o[2][wt] + X->cls_o[3][wt]) + X->cls_p[256] * X->v256[wt];
                 out[(tok0 + 256) * kW + h * kD + wt] = (uint16_t)(tc::pack16<F16>(o / tot, 0.f) & 0xffffu);
             }
         }
@@ -225,28 +237,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             ph_s ^= 1;
             tc::tc_fence_after();
             if (t == 1 && wt == 0 && next < n_pairs) issue_qk(next);     // Q and K are dead once S_1 is complete
-            const float s256 = t == 0 ? s256_0 : s256_1;
-            // pass 1: row maximum over the 256 keys in TMEM and key 256 (TMEM loads double-buffered)
-            float mx = s256;
+            const float s256 = X->s256[t][row];
+            // pass 1: maximum over this thread's 128 keys (four independent chains), key 256 folded into half 0
+            float mx;
             {
                 uint32_t va[32], vb[32];
+                float m0 = half == 0 ? s256 : -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                 tc::tmem_ld_32x32(t_s, va);
 #pragma unroll 1
-                for (int c = 0; c < 8; c += 2) {
+                for (int c = 0; c < 4; c += 2) {
                     tc::tmem_ld_wait();
                     tc::tmem_ld_32x32(t_s + (c + 1) * 32, vb);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+                    for (int j = 0; j < 32; j += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(va[j]));
+                        m1 = fmaxf(m1, __uint_as_float(va[j + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(va[j + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(va[j + 3]));
+                    }
                     tc::tmem_ld_wait();
-                    if (c + 2 < 8) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
+                    if (c + 2 < 4) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                    for (int j = 0; j < 32; j += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(vb[j]));
+                        m1 = fmaxf(m1, __uint_as_float(vb[j + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(vb[j + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(vb[j + 3]));
+                    }
                 }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             }
-            // pass 2: p = exp2((s - m) / 8 * log2 e); P (bf16 pairs) overwrites S columns already consumed
+            X->xmax[half][row] = mx;
+            wg_sync(wg);
+            mx = fmaxf(X->xmax[0][row], X->xmax[1][row]);
+            // pass 2: p = exp2((s - m) / 8 * log2 e); P (16-bit pairs) overwrites S columns this thread has consumed
             const float mxs = mx * kScaleLog2;
             const float p_last = ex2_fast(fmaf(s256, kScaleLog2, -mxs));
-            float sum = p_last;
+            float sum0 = half == 0 ? p_last : 0.f, sum1 = 0.f;
             {
                 uint32_t va[32], vb[32];
                 auto emit = [&](const uint32_t (&v)[32], int c) {
@@ -255,44 +282,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
                     for (int j = 0; j < 16; ++j) {
                         const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), kScaleLog2, -mxs));
                         const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2, -mxs));
-                        sum += p0 + p1;
+                        sum0 += p0;
+                        sum1 += p1;
                         pk[j] = tc::pack16<F16>(p0, p1);
                     }
-                    tmem_st_32x16(t_s + c * 16, pk);
+                    tmem_st_32x16(t_p + c * 16, pk);
                 };
                 tc::tmem_ld_32x32(t_s, va);
 #pragma unroll 1
-                for (int c = 0; c < 8; c += 2) {
+                for (int c = 0; c < 4; c += 2) {
                     tc::tmem_ld_wait();
                     tc::tmem_ld_32x32(t_s + (c + 1) * 32, vb);
                     emit(va, c);
                     tc::tmem_ld_wait();
-                    if (c + 2 < 8) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
+                    if (c + 2 < 4) tc::tmem_ld_32x32(t_s + (c + 2) * 32, va);
                     emit(vb, c + 1);
                 }
             }
+            X->xsum[half][row] = sum0 + sum1;
             tmem_st_wait();
-            const float inv_l = 1.0f / sum;
             tc::tc_fence_before();
             wg_sync(wg);
+            const float inv_l = 1.0f / (X->xsum[0][row] + X->xsum[1][row]);
             if (wt == 0) {
                 tc::tc_fence_after();
                 // O = P V : 16 UMMAs of K = 16 keys (8 TMEM columns of P, 16 rows of V each)
                 const uint32_t vbase = tc::smem_u32(smem + kOffV);
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    umma_bf16_ts(tmem + 128, tmem + 8 * i, make_desc_mn_sw128(vbase + i * 2048), idesc_o, i != 0);
+                    umma_bf16_ts(tmem + 64, tmem + (i < 8 ? 8 * i : 128 + 8 * (i - 8)), make_desc_mn_sw128(vbase + i * 2048), idesc_o, i != 0);
                 tc::umma_commit(&X->bar_pv);
             }
             tc::mbar_wait(&X->bar_pv, ph_pv);
             ph_pv ^= 1;
             tc::tc_fence_after();
             if (t == 1 && wt == 0 && next < n_pairs) issue_v(next);      // V is dead once O_1 is complete
-            // epilogue: O row + rank-1 contribution of key 256, normalised, bf16
+            // epilogue: this thread's 32 columns of the O row + rank-1 contribution of key 256, normalised, 16-bit
             {
-                uint32_t v0[32], v1[32];
+                uint32_t v0[32];
                 tc::tmem_ld_32x32(t_o, v0);
-                tc::tmem_ld_32x32(t_o + 32, v1);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
                 wg_sync(wg);                       // every row of O is in registers: the accumulator columns may be reused
@@ -304,15 +332,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
                     for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     tc::umma_commit(&X->bar_s);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(out + (tok0 + t * 128 + wt) * kW + h * kD);
+                uint4* dst = reinterpret_cast<uint4*>(out + (tok0 + t * 128 + row) * kW + h * kD + half * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float o[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int dcol = 8 * q + j;
-                        const float acc = __uint_as_float(dcol < 32 ? v0[dcol] : v1[dcol - 32]);
-                        o[j] = (acc + p_last * X->v256[dcol]) * inv_l;
+                        o[j] = (__uint_as_float(v0[dcol]) + p_last * X->v256[half * 32 + dcol]) * inv_l;
                     }
                     dst[q] = make_uint4(tc::pack16<F16>(o[0], o[1]), tc::pack16<F16>(o[2], o[3]), tc::pack16<F16>(o[4], o[5]),
                                         tc::pack16<F16>(o[6], o[7]));
@@ -320,7 +347,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             }
         }
         ph_load ^= 1;
-        wg_sync(wg);        // X arrays (q256 / k256 / v256 / cls_*) are rewritten by the next pair
+        wg_sync(wg);        // X arrays (q256 / k256 / v256 / cls_* / s256) are rewritten by the next pair
     }
     tc::tc_fence_before();
     __syncthreads();

@@ -76,7 +76,9 @@ template <int MODE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared pointer (a round trip through an integer would
+    // make every later access a generic LD/ST instead of LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t* epi_stage = smem + STAGES * kStageBytes;
     uint8_t* epi_bias = epi_stage + kEpiStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kEpiStageBytes + kEpiBiasBytes);

@@ -56,7 +56,9 @@ resample_h_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_
     constexpr int RN = RCfg<CH>::RN;
     constexpr int kStageR = RCfg<CH>::kStage;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared pointer (a round trip through an integer would
+    // make every later access a generic LD/ST instead of LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RSTAGES * kStageR);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + RSTAGES;
