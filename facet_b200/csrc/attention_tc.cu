@@ -280,8 +280,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), kScaleLog2, -mxs));
-                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2, -mxs));
+                        const float x0 = fmaf(__uint_as_float(v[2 * j]), kScaleLog2, -mxs);
+                        const float x1 = fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2, -mxs);
+                        const float p0 = ex2_fast(x0), p1 = ex2_fast(x1);
                         sum0 += p0;
                         sum1 += p1;
                         pk[j] = tc::pack16<F16>(p0, p1);
