@@ -18,7 +18,8 @@ def _check_stats(st, ref):
     assert st.sum_abs_noise == ref["sum_abs_noise"]
 
 
-@pytest.mark.parametrize("shape", [(64, 64), (128, 192), (96, 512), (50, 1040), (683, 1024), (300, 1552)])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 192), (96, 512), (50, 1040), (683, 1024), (300, 1552),
+                                   (2, 8), (3, 16), (5, 264), (130, 8), (257, 776)])
 def test_fast_kernel_bit_exact_vs_oracle(shape):
     from facet_b200 import ops
     from oracle import technical_np as onp
