@@ -1,8 +1,8 @@
 """BASELINE.json configs[3]: all-pairs cosine similarity over N 768-d embeddings (planted near-duplicate clusters),
 sharded by rows across the ranks of one node; embeddings are all-gathered with NCCL when world > 1.
 
-    python scripts/bench_similarity.py --n 1000000            (1 GPU: the whole upper triangle)
-    torchrun --nproc-per-node 8 ... scripts/bench_similarity.py --n 1000000
+    python scripts/bench_similarity.py --embeddings 1000000            (1 GPU: the whole upper triangle)
+    torchrun --nproc-per-node 8 ... scripts/bench_similarity.py --embeddings 1000000
 
 Prints one JSON line: pairs/s over the N(N-1)/2 upper triangle, TFLOP/s on N(N-1)*768 flops, pair count.
 """
@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--embeddings", dest="n", type=int, default=1_000_000)
     ap.add_argument("--tau", type=float, default=0.90)
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
