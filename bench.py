@@ -263,6 +263,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from facet_b200.processing.pipeline import bind_to_gpu_numa_node
+    orig_affinity = os.sched_getaffinity(0)
+    numa_node = bind_to_gpu_numa_node(local_rank)      # pinned e2e buffers local to the GPU's PCIe root
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry one JSON line only
         # stdout must carry exactly one JSON line: send NCCL's start-up banner ("NCCL version ...", printed on
@@ -409,6 +412,7 @@ def main():
         frames_per_step = eb * reps
         e2e = {"value": world * frames_per_step / (ms_e * 1e-3), "unit": "images/s", "steps": n_e2e,
                "frames_per_step_per_gpu": frames_per_step,
+               "numa_node_rank0": numa_node,
                "h2d_bytes_per_step": pipe.h2d_bytes(frames_per_step, H, W) + frames_per_step * (768 * 4 + 8),
                "d2h_bytes_per_step": pipe.d2h_bytes(frames_per_step, 240) + d2h}
         del host
@@ -416,6 +420,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -----------------
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, orig_affinity)      # the CPU arm may use every host core again
         from oracle import cpu_port
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

@@ -14,6 +14,36 @@ import numpy as np
 from .. import _lib, ops
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers
+    allocated afterwards are local to the GPU's PCIe root (one process per GPU: without this, half of the
+    ranks of an 8-GPU box stream their frames across the socket interconnect).  Returns the node id or None
+    when the topology cannot be read; never raises."""
+    import os
+    try:
+        torch = _lib.require_cuda()
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class ScoringPipeline:
     def __init__(self, scorer, chunk: int = 8):
         torch = _lib.require_cuda()
