@@ -224,6 +224,15 @@ int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t imag
     return rc;
 }
 
+int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int fx, int fy, int red_h, int red_w,
+                 const uint32_t* mult4, const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, const int32_t* d_vbounds,
+                 const int32_t* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp,
+                 uint8_t* d_out, void* stream) {
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    return launch_thumbnail(d_images, n, height, width, (long long)image_stride, fx, fy, red_h, red_w, mult4, d_hbounds, d_hcoef, hk,
+                            d_vbounds, d_vcoef, vk, out_h, out_w, swap_rb, d_reduced, d_tmp, d_out, (cudaStream_t)stream);
+}
+
 int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts, int32_t* d_pairs,
                      int64_t cap, uint64_t* d_count, void* stream) {
     ProfScope ps(PROF_HAMMING, (cudaStream_t)stream);

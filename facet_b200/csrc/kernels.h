@@ -39,6 +39,10 @@ int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_s
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
                  unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, int luma_ready,
                  const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
+int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
+                     const unsigned int* mult4, const int* d_hbounds, const int* d_hcoef, int hk, const int* d_vbounds,
+                     const int* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp,
+                     uint8_t* d_out, cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
 

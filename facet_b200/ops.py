@@ -328,6 +328,41 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
             cap = max(nc, m)
 
 
+_THUMB_PLANS: dict = {}
+
+
+def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = True):
+    """Pillow `Image.thumbnail((size, size), LANCZOS)` of a same-shaped batch, bit-exact (the pixel work of
+    utils/image_transforms.py:32-50).  images: uint8 [n,H,W,3] (BGR unless rgb_order).  Returns a CUDA uint8
+    tensor [n,h,w,3] in RGB order when to_rgb (what PIL would hold), else in the input's channel order."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    from .utils import thumbnail as th
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    swap = bool(to_rgb) and not rgb_order
+    p = th.plan(h, w, size)
+    if p is None:                                   # Pillow leaves images that already fit unchanged
+        return t.flip(-1).contiguous() if swap else t.clone()
+    key = (h, w, size, str(t.device))
+    if key not in _THUMB_PLANS:
+        mult = np.array([th.reduce_multiplier(max(1, a * b)) for a, b in
+                         ((p.fx, p.fy), (w % p.fx or p.fx, p.fy), (p.fx, h % p.fy or p.fy), (w % p.fx or p.fx, h % p.fy or p.fy))],
+                        dtype=np.uint32)
+        _THUMB_PLANS[key] = (mult,) + tuple(torch.from_numpy(np.ascontiguousarray(a)).to(t.device)
+                                            for a in (p.hbounds, p.hcoef, p.vbounds, p.vcoef))
+    mult, hb, hc, vb, vc = _THUMB_PLANS[key]
+    with torch.cuda.device(t.device):
+        reduced = torch.empty((n, p.red_h, p.red_w, 3), dtype=torch.uint8, device=t.device) if (p.fx > 1 or p.fy > 1) else None
+        tmp = torch.empty((n, p.red_h, p.out_w, 3), dtype=torch.uint8, device=t.device)
+        out = torch.empty((n, p.out_h, p.out_w, 3), dtype=torch.uint8, device=t.device)
+        _lib.check(lib.fb_thumbnail(_ptr(t), n, h, w, h * w * 3, p.fx, p.fy, p.red_h, p.red_w, mult.ctypes.data,
+                                    _ptr(hb), _ptr(hc), p.hk, _ptr(vb), _ptr(vc), p.vk, p.out_h, p.out_w, int(swap),
+                                    _ptr(reduced) if reduced is not None else None, _ptr(tmp), _ptr(out), _lib.stream_ptr()),
+                   "fb_thumbnail")
+    return out
+
+
 _PHASH_PLANS: dict = {}
 
 

@@ -50,13 +50,16 @@ def _lanczos(x: np.ndarray) -> np.ndarray:
 LANCZOS_SUPPORT = 3.0
 
 
-def precompute_coeffs(in_size: int, out_size: int, kernel: str = "bicubic"):
-    """Pillow precompute_coeffs + normalize_coeffs_8bpc for box (0, in_size), bicubic or lanczos.
+def precompute_coeffs(in_size: int, out_size: int, kernel: str = "bicubic", in0: float = 0.0, in1: float | None = None):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the box (in0, in1) of an axis of in_size pixels
+    (default: the whole axis), bicubic or lanczos.  The box ends are C floats, as in ImagingResample.
 
     Returns (bounds int32 [out,2] = first tap / tap count, coef int32 [out,ksize], ksize).
     """
     filt, base_support = (_bicubic, BICUBIC_SUPPORT) if kernel == "bicubic" else (_lanczos, LANCZOS_SUPPORT)
-    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    in0 = float(np.float32(in0))
+    in1 = float(np.float32(in_size if in1 is None else in1))
+    scale = (in1 - in0) / out_size
     filterscale = max(scale, 1.0)
     support = base_support * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
@@ -64,7 +67,7 @@ def precompute_coeffs(in_size: int, out_size: int, kernel: str = "bicubic"):
     bounds = np.zeros((out_size, 2), np.int32)
     kk = np.zeros((out_size, ksize), np.float64)
     for xx in range(out_size):
-        center = 0.0 + (xx + 0.5) * scale
+        center = in0 + (xx + 0.5) * scale
         xmin = int(center - support + 0.5)
         xmin = max(xmin, 0)
         xmax = int(center + support + 0.5)

@@ -140,6 +140,21 @@ int fb_phash(const uint8_t* d_images, int n, int height, int width, int64_t imag
              const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int32_t* d_tc_kb0,
              void* stream);
 
+/* Photo thumbnail — the pixel work of utils/image_transforms.py:32-50 `generate_photo_thumbnail`
+ * (`thumb.thumbnail((size, size), Image.Resampling.LANCZOS)`, called when a photo row is saved,
+ * processing/scorer.py:1681-1686).  Pillow's algorithm, bit-exact: box reduction by (fx, fy) =
+ * int(scale / reducing_gap) with ((sum + n/2) * mult) >> 24 (mult4 = multipliers of the full, right-edge,
+ * bottom-edge and corner boxes), then the two-pass 8-bit Lanczos resampler on the reduced image with the
+ * 22-bit taps of facet_b200/utils/thumbnail.py (d_hbounds [out_w][2], d_hcoef [out_w][hk], d_vbounds
+ * [out_h][2], d_vcoef [out_h][vk]).  d_reduced [n][red_h][red_w][3] (may be NULL when fx = fy = 1),
+ * d_tmp [n][red_h][out_w][3], d_out [n][out_h][out_w][3]; swap_rb reverses the channel order of the
+ * output (BGR frames -> RGB thumbnails).  The JPEG encoding stays with the caller. */
+int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int fx, int fy,
+                 int red_h, int red_w, const uint32_t* mult4,
+                 const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
+                 const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
+                 int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp, uint8_t* d_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Duplicate / burst grouping — replaces the O(N^2) loop of utils/duplicate.py:94-119 and the
  * pairwise predicate of processing/scorer.py:1943-1968.
