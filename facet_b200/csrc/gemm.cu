@@ -17,6 +17,8 @@
 #include <mutex>
 #include <tuple>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -72,27 +74,40 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(fabsf(hx), fmaf(-p, e, 1.0f), hx);
 }
 
-template <int MODE, bool F16>
+// CL2: launched as clusters of two CTAs (a CTA pair) that compute one 256x256 tile with tcgen05.mma.cta_group::2:
+// each CTA loads its own 128 rows of A and HALF of the B tile (32 KB per k-block instead of 48 KB), so six
+// stages fit where four did and the TMA pipeline covers the L2 latency.  The leader CTA issues the MMAs for
+// both; its full barriers collect the bytes of both CTAs' loads, its commits free the stages and publish the
+// accumulators in both CTAs, and both CTAs' epilogue warps hand the accumulator back to the leader.
+template <int MODE, bool F16, bool CL2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the shared pointer (a round trip through an integer would
     // make every later access a generic LD/ST instead of LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-    uint8_t* epi_stage = smem + STAGES * kStageBytes;
+    constexpr int NS = CL2 ? 6 : STAGES;                                   // pipeline stages
+    constexpr int kBPart = CL2 ? kBBytes / 2 : kBBytes;                    // bytes of B this CTA holds per stage
+    constexpr int SB = kABytes + kBPart;                                   // stage bytes (NS * SB = 192 KB either way)
+    static_assert(NS * SB == STAGES * kStageBytes, "stage ring must fill the same shared memory");
+    uint8_t* epi_stage = smem + NS * SB;
     uint8_t* epi_bias = epi_stage + kEpiStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kEpiStageBytes + kEpiBiasBytes);
-    uint64_t* full_bar = bars;                   // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * SB + kEpiStageBytes + kEpiBiasBytes);
+    uint64_t* full_bar = bars;                   // [NS]
+    uint64_t* empty_bar = bars + NS;             // [NS]
+    uint64_t* tmem_full = bars + 2 * NS;         // [2]
+    uint64_t* tmem_empty = bars + 2 * NS + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_n = (p.N + BN - 1) / BN;
     const int tiles_m = (p.M + BM - 1) / BM;
-    const int num_tiles = tiles_m * tiles_n;
+    const int crank = CL2 ? (int)tc::cluster_ctarank() : 0;
+    // CL2 walks pairs of tile rows: pair t -> tile rows 2 (t / tiles_n) + rank, tile column t % tiles_n
+    const int num_tiles = CL2 ? ((tiles_m + 1) / 2) * tiles_n : tiles_m * tiles_n;
+    const int tile_first = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kblocks = p.K / BK;
     // similarity mode only needs tiles that contain an element with col > global row
     constexpr bool tri = (MODE == FB_GEMM_THRESHOLD_PAIRS);
@@ -111,19 +126,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int gm_ = min(kGroupM, tiles_m - g_ * kGroupM);                       \
         m0_ = (g_ * kGroupM + w_ % gm_) * BM;                                       \
         n0_ = (w_ / gm_) * BN;                                                      \
+    } else if (CL2) {                                                               \
+        m0_ = (2 * ((tile_) / tiles_n) + crank) * BM;                               \
+        n0_ = ((tile_) % tiles_n) * BN;                                             \
     } else {                                                                        \
         m0_ = ((tile_) / tiles_n) * BM;                                             \
         n0_ = ((tile_) % tiles_n) * BN;                                             \
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < NS; ++s) {
+            tc::mbar_init(&full_bar[s], CL2 ? 2 : 1);         // pair: one arrive.expect_tx per CTA
             tc::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tmem_full[a], 1);
-            tc::mbar_init(&tmem_empty[a], kEpiWarps);
+            tc::mbar_init(&tmem_empty[a], CL2 ? 2 * kEpiWarps : kEpiWarps);
         }
         tc::mbar_fence_init();
         tc::fence_proxy_async();
@@ -132,9 +150,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc::tma_prefetch_desc(&tmap_a);
         tc::tma_prefetch_desc(&tmap_b);
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 1) {
+        if (CL2) tc::tmem_alloc_pair(tmem_slot, 512);
+        else tc::tmem_alloc(tmem_slot, 512);
+    }
     tc::tc_fence_before();
     __syncthreads();
+    if (CL2) tc::cluster_sync_all();     // the peer's barriers are initialised before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -143,27 +165,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 FB_TILE_COORDS(tile, m0, n0)
                 if (FB_TILE_SKIPPED(m0, n0)) continue;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * kStageBytes;
-                    tc::mbar_expect_tx(&full_bar[stage], kStageBytes);
-                    tc::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
-                    tc::tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    uint8_t* sa = smem + stage * SB;
+                    if (CL2) {
+                        // both CTAs report their bytes to the leader's full barrier; tmap_b has a 128-row box here and
+                        // this CTA holds rows [n0 + 128 rank, +128) of the B tile
+                        const uint32_t lead_bar = tc::mapa_u32(tc::smem_u32(&full_bar[stage]), 0u);
+                        tc::mbar_expect_tx_cluster(lead_bar, SB);
+                        tc::tma_load_2d_pair(&tmap_a, lead_bar, sa, kb * BK, m0);
+                        tc::tma_load_2d_pair(&tmap_b, lead_bar, sa + kABytes, kb * BK, n0 + crank * (BN / 2));
+                    } else {
+                        tc::mbar_expect_tx(&full_bar[stage], SB);
+                        tc::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m0);
+                        tc::tma_load_2d(&tmap_b, &full_bar[stage], sa + kABytes, kb * BK, n0);
+                    }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc16<F16>(BM, BN);
+        if (lane == 0 && crank == 0) {            // pair: the leader issues for both CTAs
+            const uint32_t idesc = tc::make_idesc16<F16>(CL2 ? 2 * BM : BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 FB_TILE_COORDS(tile, m0, n0)
                 if (FB_TILE_SKIPPED(m0, n0)) continue;
                 const int acc = iter & 1;
@@ -173,18 +204,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = 0; kb < kblocks; ++kb) {
                     tc::mbar_wait(&full_bar[stage], phase);
                     tc::tc_fence_after();
-                    const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = tc::smem_u32(smem + stage * SB);
                     const uint64_t da = tc::make_desc_k_sw128(sa);
                     const uint64_t db = tc::make_desc_k_sw128(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the address field
-                        tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if (CL2) tc::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else tc::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    tc::umma_commit(&empty_bar[stage]);      // frees the smem stage when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    // frees the smem stage when the MMAs retire (pair: in both CTAs)
+                    if (CL2) tc::umma_commit_pair(&empty_bar[stage], (uint16_t)3);
+                    else tc::umma_commit(&empty_bar[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
-                tc::umma_commit(&tmem_full[acc]);            // accumulator complete
+                // accumulator complete (pair: published to both CTAs' epilogues)
+                if (CL2) tc::umma_commit_pair(&tmem_full[acc], (uint16_t)3);
+                else tc::umma_commit(&tmem_full[acc]);
                 ++iter;
             }
         }
@@ -197,7 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float* bias_s = reinterpret_cast<float*>(epi_bias + ew * 512);
         constexpr bool bf16_out = (MODE == FB_GEMM_BIAS_BF16 || MODE == FB_GEMM_BIAS_GELU_BF16);
         int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
             FB_TILE_COORDS(tile, m0, n0)
             if (FB_TILE_SKIPPED(m0, n0)) continue;
             const int acc = iter & 1;
@@ -321,7 +357,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (c == 3) {
                         tc::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                        if (lane == 0) {
+                            if (CL2) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tmem_empty[acc]), 0u));   // the leader waits for both CTAs
+                            else tc::mbar_arrive(&tmem_empty[acc]);
+                        }
                     }
                     process(va, c, rz);
                 }
@@ -347,7 +386,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) {
+                            if (CL2) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tmem_empty[acc]), 0u));   // the leader waits for both CTAs
+                            else tc::mbar_arrive(&tmem_empty[acc]);
+                        }
                 process(va, 3, rb);
             } else {
                 // two register sets: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
@@ -371,7 +413,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // the accumulator is in registers now: hand the TMEM buffer back before the last chunk's math
                 tc::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) {
+                            if (CL2) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tmem_empty[acc]), 0u));   // the leader waits for both CTAs
+                            else tc::mbar_arrive(&tmem_empty[acc]);
+                        }
                 process(vb, 3, rb);
             }
             ++iter;
@@ -380,7 +425,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+    if (CL2) tc::cluster_sync_all();     // the peer may still arrive on this CTA's barriers until it is done too
+    if (warp == 1) {
+        if (CL2) tc::tmem_dealloc_pair(tmem_base, 512);
+        else tc::tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ---- tensor-map encoding through the driver entry point (no link against libcuda) ------------
@@ -420,36 +469,110 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return 0;
 }
 
+// Clusters of two CTAs that can be co-resident for a kernel (the persistent grid must not exceed it).
+template <typename K>
+static int max_cluster_pairs(K kernel, int* out) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * sm_count(), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    FB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+    *out = n;
+    return 0;
+}
+
+template <typename K>
+static int launch_cluster2(K kernel, int pairs, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& p, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FB_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
+    return 0;
+}
+
 static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, long long ldb, GemmArgs p, cudaStream_t stream) {
+    static const bool no_cluster = getenv("FB_GEMM_NO_CLUSTER") != nullptr;     // A/B switch
+    // clusters of two with a multicast B tile: the ViT-layer GEMMs (large M, B = weights)
+    const bool cl2 = !no_cluster && p.mode != FB_GEMM_THRESHOLD_PAIRS && p.mode != FB_GEMM_F32 && p.M >= 4 * BM && p.N % BN == 0;
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16_2d(&ta, d_a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, BM, BK);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb, BN, BK);
+    rc = make_tmap_bf16_2d(&tb, d_b, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb, cl2 ? BN / 2 : BN, BK);
     if (rc) return rc;
-    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int tiles = tiles_m * tiles_n;
     const int grid = tiles < sm_count() ? tiles : sm_count();
 #define FB_LAUNCH_MODE(MODE_)                                                                                          \
     case MODE_: {                                                                                                      \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        if (p.f16) gemm_bf16_kernel<MODE_, true><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                   \
-        else gemm_bf16_kernel<MODE_, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                        \
+        if (p.f16) gemm_bf16_kernel<MODE_, true, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);            \
+        else gemm_bf16_kernel<MODE_, false, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                 \
         break;                                                                                                         \
     }
-    switch (p.mode) {
-        FB_LAUNCH_MODE(FB_GEMM_BIAS_BF16)
-        FB_LAUNCH_MODE(FB_GEMM_BIAS_GELU_BF16)
-        FB_LAUNCH_MODE(FB_GEMM_BIAS_RESIDUAL_F32)
-        FB_LAUNCH_MODE(FB_GEMM_F32)
-        FB_LAUNCH_MODE(FB_GEMM_THRESHOLD_PAIRS)
-        default:
-            FB_REQUIRE(false, "fb_gemm_bf16: unknown epilogue mode %d", p.mode);
+#define FB_LAUNCH_MODE_CL2(MODE_)                                                                                      \
+    case MODE_: {                                                                                                      \
+        static int max_pairs = -1;                                                                                     \
+        if (max_pairs < 0) {                                                                                           \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            int a_ = 0, b_ = 0;                                                                                        \
+            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, false, true>, &a_);                                         \
+            if (rc) return rc;                                                                                         \
+            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, true, true>, &b_);                                          \
+            if (rc) return rc;                                                                                         \
+            max_pairs = a_ < b_ ? a_ : b_;                                                                             \
+        }                                                                                                              \
+        const int work_ = ((tiles_m + 1) / 2) * tiles_n;                                                               \
+        const int pairs_ = work_ < max_pairs ? work_ : max_pairs;                                                      \
+        FB_REQUIRE(pairs_ >= 1, "fb_gemm_bf16: no cluster of two CTAs fits on this device");                          \
+        rc = p.f16 ? launch_cluster2(gemm_bf16_kernel<MODE_, true, true>, pairs_, ta, tb, p, stream)                   \
+                   : launch_cluster2(gemm_bf16_kernel<MODE_, false, true>, pairs_, ta, tb, p, stream);                 \
+        if (rc) return rc;                                                                                             \
+        break;                                                                                                         \
+    }
+    if (cl2) {
+        switch (p.mode) {
+            FB_LAUNCH_MODE_CL2(FB_GEMM_BIAS_BF16)
+            FB_LAUNCH_MODE_CL2(FB_GEMM_BIAS_GELU_BF16)
+            FB_LAUNCH_MODE_CL2(FB_GEMM_BIAS_RESIDUAL_F32)
+            default:
+                FB_REQUIRE(false, "fb_gemm_bf16: unknown epilogue mode %d", p.mode);
+        }
+    } else {
+        switch (p.mode) {
+            FB_LAUNCH_MODE(FB_GEMM_BIAS_BF16)
+            FB_LAUNCH_MODE(FB_GEMM_BIAS_GELU_BF16)
+            FB_LAUNCH_MODE(FB_GEMM_BIAS_RESIDUAL_F32)
+            FB_LAUNCH_MODE(FB_GEMM_F32)
+            FB_LAUNCH_MODE(FB_GEMM_THRESHOLD_PAIRS)
+            default:
+                FB_REQUIRE(false, "fb_gemm_bf16: unknown epilogue mode %d", p.mode);
+        }
     }
 #undef FB_LAUNCH_MODE
+#undef FB_LAUNCH_MODE_CL2
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }
