@@ -355,8 +355,8 @@ def main():
               "vit_tflops": B * GFLOP_PER_IMAGE * 1e9 / (ms_vit * 1e-3) / 1e12}
     peaks = measured_peaks()
     gemm_tflops = B * GEMM_GFLOP_PER_IMAGE * 1e9 / (gemm_ms * 1e-3) / 1e12
-    # DRAM traffic of the GEMM launches of one layer at batch 128, from profiles/r1_gemm_ncu.txt (ncu --set full)
-    traffic_per_layer_b128 = (436.5 + 108.1 + 73.7 + 155.5 + 204.3 + 86.2 + 75.8 + 221.0) * 1e6
+    # DRAM traffic of the GEMM launches of one layer at batch 128, from profiles/r1_gemm_ncu_v2.txt (ncu --set full)
+    traffic_per_layer_b128 = (73.8 + 153.7 + 204.3 + 82.5 + 75.9 + 222.8 + 436.6 + 106.3) * 1e6
     roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05), {gemm_launches} launches per step",
                 "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": gemm_tflops / peaks["bf16_tflops"],

@@ -15,7 +15,7 @@ l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum l1tex__data_pipe_lsu_wavefron
 sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active
 sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
 gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed sm__throughput.avg.pct_of_peak_sustained_elapsed
-sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active""".split()
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active lts__throughput.avg.pct_of_peak_sustained_elapsed launch__grid_size launch__block_size sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active""".split()
 for i, h in enumerate(hdr):
     if h in KEYS or ("pcsamp_warps_issue_stalled" in h and "not_issued" not in h):
         print(f"{h:86s} {vals[i]:>18s} {units[i]}")
