@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="facet_b200", choices=["facet_b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=float, default=50.0, help="NVML sampling period during the timed region (0 = off)")
     return ap.parse_args()
 
 
@@ -309,8 +310,8 @@ def main():
     # ---- timed region: K steps, CUDA events on the launching stream -------------------------------------
     launches0 = int(lib.fb_launch_count())
     # one sampler per node (rank 0's GPU): concurrent nvidia-smi pollers slow every rank's launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank, period_s=max(args.clock_period_ms, 1.0) * 1e-3)
+    if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
         time.sleep(0.3)
     barrier()
