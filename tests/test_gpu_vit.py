@@ -13,7 +13,10 @@ def _rand_bf16(shape, seed, scale=1.0, dtype=None):
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 256, 128), (1000, 768, 1024), (257 * 8, 3072, 1024),
-                                   (2056, 1024, 4096), (129, 32, 640), (4096, 1024, 640)])
+                                   (2056, 1024, 4096), (129, 32, 640), (4096, 1024, 640),
+                                   # CTA-pair form (M >= 512, N % 256 == 0): exactly two pairs, an odd number of row
+                                   # tiles with a ragged last one, many column tiles, a single k-block, a long K
+                                   (512, 256, 64), (513, 512, 128), (640, 4096, 1024), (1283, 256, 64), (768, 256, 8192)])
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 def test_gemm_all_epilogues(m, n, k, dt):
     import torch
