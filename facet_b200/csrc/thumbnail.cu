@@ -109,49 +109,81 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 }
 
 // Horizontal pass: in [n][rows][in_w][3] (row pitch in_pitch bytes, image stride in_stride) -> out [n][rows][out_w][3].
+// One CTA per (row, image): the input row is staged in shared memory with word loads (byte loads when the
+// row is not 4-byte aligned), then thread = output pixel.
 __global__ void __launch_bounds__(256) resample_h_u8_kernel(const uint8_t* __restrict__ in, long long in_stride, long long in_pitch,
-                                                            int rows, int out_w, const int* __restrict__ bounds,
+                                                            int in_w, int rows, int out_w, const int* __restrict__ bounds,
                                                             const int* __restrict__ coef, int ksize, uint8_t* __restrict__ out) {
-    const int n_img = blockIdx.z, y = blockIdx.y;
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xo >= out_w) return;
+    extern __shared__ __align__(16) uint8_t s_row[];
+    const int n_img = blockIdx.y, y = blockIdx.x;
     const uint8_t* src = in + (size_t)n_img * in_stride + (size_t)y * in_pitch;
-    const int first = bounds[2 * xo], cnt = bounds[2 * xo + 1];
-    const int* k = coef + (size_t)xo * ksize;
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-    for (int t = 0; t < cnt; ++t) {
-        const int kv = __ldg(k + t);
-        const uint8_t* p = src + (size_t)(first + t) * 3;
-        a0 += (int)__ldg(p) * kv;
-        a1 += (int)__ldg(p + 1) * kv;
-        a2 += (int)__ldg(p + 2) * kv;
+    const int nbytes = in_w * 3;
+    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const int nwords = nbytes >> 2;
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(s_row)[i] = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+        for (int i = (nwords << 2) + threadIdx.x; i < nbytes; i += blockDim.x) s_row[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < nbytes; i += blockDim.x) s_row[i] = __ldg(src + i);
     }
-    uint8_t* o = out + (((size_t)n_img * rows + y) * out_w + xo) * 3;
-    o[0] = clip8(a0);
-    o[1] = clip8(a1);
-    o[2] = clip8(a2);
+    __syncthreads();
+    uint8_t* orow = out + ((size_t)n_img * rows + y) * out_w * 3;
+    for (int xo = threadIdx.x; xo < out_w; xo += blockDim.x) {
+        const int first = __ldg(bounds + 2 * xo), cnt = __ldg(bounds + 2 * xo + 1);
+        const int* k = coef + (size_t)xo * ksize;
+        const uint8_t* p = s_row + first * 3;
+        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+        for (int t = 0; t < cnt; ++t) {
+            const int kv = __ldg(k + t);
+            a0 += (int)p[3 * t] * kv;
+            a1 += (int)p[3 * t + 1] * kv;
+            a2 += (int)p[3 * t + 2] * kv;
+        }
+        orow[3 * xo] = clip8(a0);
+        orow[3 * xo + 1] = clip8(a1);
+        orow[3 * xo + 2] = clip8(a2);
+    }
 }
 
-// Vertical pass: in [n][rows][w][3] -> out [n][out_h][w][3]; thread = one byte column; swap_rb reverses the
-// channel order on the way out (BGR frames -> RGB thumbnails).
+// Vertical pass: in [n][rows][w][3] -> out [n][out_h][w][3]; thread = 4 consecutive bytes of the row when the row
+// length allows word loads (one byte otherwise); swap_rb reverses the channel order on the way out (BGR frames
+// -> RGB thumbnails).
+template <int VEC>
 __global__ void __launch_bounds__(256) resample_v_u8_kernel(const uint8_t* __restrict__ in, int rows, int w, int out_h,
                                                             const int* __restrict__ bounds, const int* __restrict__ coef, int ksize,
                                                             int swap_rb, uint8_t* __restrict__ out) {
     const int n_img = blockIdx.z, yo = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // byte within the row
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;       // first byte within the row
     const int rowb = w * 3;
     if (i >= rowb) return;
     const uint8_t* src = in + (size_t)n_img * rows * rowb;
     const int first = bounds[2 * yo], cnt = bounds[2 * yo + 1];
     const int* k = coef + (size_t)yo * ksize;
-    int acc = 1 << (kPrecisionBits - 1);
-    for (int t = 0; t < cnt; ++t) acc += (int)__ldg(src + (size_t)(first + t) * rowb + i) * __ldg(k + t);
-    int oi = i;
-    if (swap_rb) {
-        const int c = i % 3;
-        oi = i - c + (2 - c);
+    int acc[VEC];
+#pragma unroll
+    for (int b = 0; b < VEC; ++b) acc[b] = 1 << (kPrecisionBits - 1);
+    for (int t = 0; t < cnt; ++t) {
+        const int kv = __ldg(k + t);
+        if (VEC == 4) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(first + t) * rowb + i));
+            acc[0] += (int)(v & 255) * kv;
+            acc[1 % VEC] += (int)((v >> 8) & 255) * kv;
+            acc[2 % VEC] += (int)((v >> 16) & 255) * kv;
+            acc[3 % VEC] += (int)(v >> 24) * kv;
+        } else {
+            acc[0] += (int)__ldg(src + (size_t)(first + t) * rowb + i) * kv;
+        }
     }
-    out[((size_t)n_img * out_h + yo) * rowb + oi] = clip8(acc);
+    uint8_t* orow = out + ((size_t)n_img * out_h + yo) * rowb;
+#pragma unroll
+    for (int b = 0; b < VEC; ++b) {
+        int oi = i + b;
+        if (swap_rb) {
+            const int c = oi % 3;
+            oi = oi - c + (2 - c);
+        }
+        orow[oi] = clip8(acc[b]);
+    }
 }
 
 }  // namespace
@@ -163,7 +195,7 @@ int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long ima
     FB_REQUIRE(d_images && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_out, "fb_thumbnail: null pointer");
     FB_REQUIRE(n >= 1 && H >= 1 && W >= 1 && fx >= 1 && fy >= 1 && out_h >= 1 && out_w >= 1, "fb_thumbnail: bad sizes");
     FB_REQUIRE(red_h == (H + fy - 1) / fy && red_w == (W + fx - 1) / fx, "fb_thumbnail: reduced size does not match the factors");
-    FB_REQUIRE(n <= 65535 && red_h <= 65535 && out_h <= 65535, "fb_thumbnail: batch or height too large for one launch");
+    FB_REQUIRE(n <= 65535 && out_h <= 65535, "fb_thumbnail: batch or height too large for one launch");
     const uint8_t* src = d_images;
     long long src_stride = image_stride, src_pitch = (long long)W * 3;
     if (fx > 1 || fy > 1) {
@@ -188,13 +220,23 @@ int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long ima
         src_pitch = (long long)red_w * 3;
     }
     {
-        dim3 grid((out_w + 255) / 256, red_h, n);
-        resample_h_u8_kernel<<<grid, 256, 0, stream>>>(src, src_stride, src_pitch, red_h, out_w, d_hbounds, d_hcoef, hk, d_tmp);
+        const size_t smem = ((size_t)red_w * 3 + 15) & ~(size_t)15;
+        FB_REQUIRE(smem <= 200 * 1024, "fb_thumbnail: a row of %d pixels does not fit in shared memory", red_w);
+        if (smem > 48 * 1024)
+            FB_CUDA_OK(cudaFuncSetAttribute(resample_h_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(red_h, n);
+        resample_h_u8_kernel<<<grid, 256, smem, stream>>>(src, src_stride, src_pitch, red_w, red_h, out_w, d_hbounds, d_hcoef, hk, d_tmp);
         FB_CUDA_OK(cudaGetLastError());
     }
     {
-        dim3 grid((out_w * 3 + 255) / 256, out_h, n);
-        resample_v_u8_kernel<<<grid, 256, 0, stream>>>(d_tmp, red_h, out_w, out_h, d_vbounds, d_vcoef, vk, swap_rb, d_out);
+        const int rowb = out_w * 3;
+        if (rowb % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tmp) & 3) == 0) {
+            dim3 grid((rowb / 4 + 255) / 256, out_h, n);
+            resample_v_u8_kernel<4><<<grid, 256, 0, stream>>>(d_tmp, red_h, out_w, out_h, d_vbounds, d_vcoef, vk, swap_rb, d_out);
+        } else {
+            dim3 grid((rowb + 255) / 256, out_h, n);
+            resample_v_u8_kernel<1><<<grid, 256, 0, stream>>>(d_tmp, red_h, out_w, out_h, d_vbounds, d_vcoef, vk, swap_rb, d_out);
+        }
         FB_CUDA_OK(cudaGetLastError());
     }
     count_launch(2);
