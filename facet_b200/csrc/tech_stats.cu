@@ -8,15 +8,19 @@
 // Outputs are exact integers; every metric dict of technical.py is a closed form of them
 // (facet_b200/analyzers/_closed_form.py).
 //
-// Fast kernel (W % 16 == 0, 16-byte aligned rows):
-//   * persistent grid = #SMs, 512 threads, 1 CTA/SM; the CTA owns a contiguous range of
-//     "units" (512-px x R-row tiles) so that it mostly stays inside one image
-//   * a warp walks down its tile: lane = 16 consecutive pixels (3 x LDG.128 per row,
-//     prefetched two rows ahead); gray of the two previous rows and their horizontal second
-//     differences stay in registers as exact fp16 pairs, so the 4-neighbour Laplacian and the
-//     Immerkaer response (outer product of [1,-2,1]) cost one pass of packed half2 adds
-//   * HS histogram (46080 x u32 = 180 KB) and a lane-private luminance histogram
-//     (256 x 32 lanes, conflict-free) live in shared memory; they are merged into the
+// Fast kernel (W % 8 == 0, 8-byte aligned rows):
+//   * persistent grid = #SMs, 640 threads, 1 CTA/SM; the CTA owns a contiguous range of
+//     "units" (256-px x R-row tiles, R <= 128) so that it mostly stays inside one image; warps claim
+//     units dynamically
+//   * a warp walks down its tile: lane = 8 consecutive pixels (3 x LDG.64 per row, the next row
+//     prefetched behind the first use of the current one); gray straight from the interleaved bytes
+//     with IDP.2A; gray, dxx and the two second-difference carries of the previous rows stay in
+//     registers as exact fp16 pairs, so the 4-neighbour Laplacian and the Immerkaer response (outer
+//     product of [1,-2,1]) cost one pass of packed half2 adds
+//   * OpenCV RGB2HSV_b two pixels per instruction in packed fp16; its two fixed-point divisions as
+//     one round-down packed fp32 FMA on reciprocal tables (bit-exact, see hsv_pair / fixed_products)
+//   * HS histogram (180 rows x 257 words) and a lane-private luminance histogram (256 x 32 lanes,
+//     conflict-free) live in shared memory at compile-time offsets; they are merged into the
 //     per-image global histograms only when the CTA crosses an image boundary
 // Generic kernel: any W/H >= 2, any alignment; one thread per pixel, global atomics.
 #include <cuda_fp16.h>
@@ -33,7 +37,7 @@ constexpr int kHsBins = 180 * 256;
 #define FB_TECH_LANE_PX 8
 #endif
 #ifndef FB_TECH_THREADS
-#define FB_TECH_THREADS 768
+#define FB_TECH_THREADS 640
 #endif
 constexpr int kThreads = FB_TECH_THREADS;
 constexpr int kWarps = kThreads / 32;

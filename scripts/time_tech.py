@@ -31,18 +31,20 @@ def make_frames(kind, n, h=4000, w=6000, seed=0):
 
 def main():
     res = {}
+    with_luma = "luma" in sys.argv[1:]          # also emit the pHash luma plane, as the full pass does
     for kind in ("noise", "photo", "smooth", "flat"):
         n = 16
         fr = make_frames(kind, n)
+        luma = torch.empty(fr.shape[:3], dtype=torch.uint8, device=fr.device) if with_luma else None
         torch.cuda.synchronize()
         for _ in range(2):
-            ops.tech_stats_raw(fr)
+            ops.tech_stats_raw(fr, luma_out=luma)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         reps = 3
         for _ in range(reps):
-            ops.tech_stats_raw(fr)
+            ops.tech_stats_raw(fr, luma_out=luma)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
