@@ -7,12 +7,16 @@
 // weights [out,in] are already "B[N,K]").
 //
 // Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer: 128x64 A tile + 256x64 B tile per stage, 4-stage mbarrier ring,
-//               128-byte swizzle
-//   warp 1      tcgen05.mma issuer (one elected lane): 128x256x16 UMMAs, fp32 accumulators in
-//               TMEM, two 256-column accumulator buffers so tile i+1 overlaps the epilogue of i
-//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / GELU / residual, direct
-//               16-byte global stores
+//   warp 0      TMA producer, mbarrier ring, 128-byte swizzle
+//   warp 1      tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM, two 256-column
+//               accumulator buffers so tile i+1 overlaps the epilogue of i
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / GELU / residual / threshold,
+//               per-warp shared-memory transpose, 16-byte global stores of full row segments
+// Two forms of the same kernel (template parameter CL2):
+//   single CTA  128x256 tile, 128x64 A box + 256x64 B box per stage, 4 stages (patch embedding, similarity)
+//   CTA pair    clusters of two CTAs, tcgen05.mma.cta_group::2 on a 256x256 tile: each CTA loads its 128 rows
+//               of A and half of B (32 KB per stage), 6 stages; the leader CTA issues the MMAs for both (the
+//               ViT-layer GEMMs: QKV, out-projection, fc, proj)
 #include <map>
 #include <mutex>
 #include <tuple>
