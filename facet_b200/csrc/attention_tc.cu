@@ -29,8 +29,7 @@ namespace fb {
 namespace {
 
 constexpr int kTok = 257, kW = 1024, kD = 64;
-constexpr int kThreadsAttn = 512;
-constexpr int kWgThreads = 256;
+constexpr int kThreadsAttn = 512;      // two groups of 256 threads
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
 
 // per-warpgroup shared memory map (bytes)

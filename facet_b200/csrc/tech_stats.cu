@@ -94,11 +94,6 @@ __device__ __forceinline__ int hs_bin_of(int b, int g, int r, const unsigned int
     return h * 256 + s;
 }
 
-__device__ __forceinline__ __half2 u16x2_to_half2(uint32_t packed) {
-    // 0x6400 | x is the fp16 number 1024 + x for x < 1024
-    uint32_t bits = packed | 0x64006400u;
-    return __hsub2(*reinterpret_cast<__half2*>(&bits), __half2half2(__ushort_as_half(0x6400)));
-}
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 
