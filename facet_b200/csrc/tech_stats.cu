@@ -45,7 +45,7 @@ constexpr int kLanePx = FB_TECH_LANE_PX;       // pixels per lane per row: 8 (3 
 constexpr int kLaneWords = 3 * kLanePx / 4;
 constexpr int kPairs = kLanePx / 2;
 constexpr int kGroups = kLanePx / 4;
-constexpr int kTileW = 32 * kLanePx;   // 512 px per warp row
+constexpr int kTileW = 32 * kLanePx;   // pixels per warp row (256 at 8 px per lane)
 constexpr int kH256Copies = 32;        // one luminance-histogram column per lane
 constexpr int kHsStride = 257;          // shared-memory row stride of the H-S histogram: bank = (h + s) mod 32, so
                                        // pixels of similar saturation and different hue do not collide
