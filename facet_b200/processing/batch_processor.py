@@ -6,9 +6,13 @@ The reference collects `batch_size` loaded items (dicts with 'path', 'pil_img', 
 (`_process_batch`, batch_processor.py:169-360).  Here a batch is grouped by frame shape and every
 group goes through ONE device pass (`Facet.score_images`: technical metrics, perceptual hash, CLIP
 preprocess, ViT-L/14 + aesthetic head + tags).  Results come back in input order as dicts with the
-reference's column names (batch_processor.py:298-355); columns owned by analyzers that are out of
-scope (faces, composition, EXIF, aggregate) are filled by the optional `finish` callback, which is
-where the reference's own `calculate_aggregate_logic` plugs in.
+reference's column names and roundings (batch_processor.py:298-355), including `category` and
+`aggregate` (`calculate_aggregate_logic`, vectorised over the group in processing/aggregate.py) and
+the `is_silhouette` rule of utils/detection.py.  Columns owned by analyzers that are outside this
+path take what the item carries — `face_res` (an `analyze_faces` result, analyzers/face.py:91),
+`exif_data`, `leading_lines_score` — or the reference's own "nothing found" values (no faces,
+centred-subject composition 7.0 / 5.0, no EXIF); a `scorer.face_analyzer`, when present, is called
+like the reference calls it.  The optional `finish(item, result)` callback sees every result last.
 
 Errors follow the reference's convention: a bad item never poisons the batch, it becomes
 `{'path': ..., 'error': ...}` (batch_processor.py:109,359).
@@ -18,6 +22,14 @@ from __future__ import annotations
 from collections import defaultdict
 
 import numpy as np
+
+from ..analyzers.composition import CompositionAnalyzer
+from ..utils.detection import detect_silhouette
+
+# analyze_faces() when nothing is detected (analyzers/face.py:91-97)
+NO_FACES = {"face_count": 0, "face_quality": 0, "eye_sharpness": 0, "is_blink": 0, "face_area": 0, "bbox": None,
+            "face_sharpness": 0, "raw_eye_sharpness": 0, "is_group_portrait": 0, "max_face_confidence": 0,
+            "face_details": []}
 
 
 class BatchProcessor:
@@ -58,9 +70,8 @@ class BatchProcessor:
             try:
                 frames = np.stack([batch[i]["img_cv"] for i in idxs])
                 scored = self.scorer.score_images(frames, mono_threshold=self.mono_threshold, tag_threshold=thr, max_tags=max_tags)
+                scored = self._finish_group([batch[i] for i in idxs], scored)
                 for i, res in zip(idxs, scored):
-                    res["path"] = batch[i].get("path")
-                    res["filename"] = str(batch[i].get("path", "")).rsplit("/", 1)[-1]
                     if self.finish is not None:
                         res = self.finish(batch[i], res)
                     results[i] = res
@@ -71,6 +82,70 @@ class BatchProcessor:
         self.metrics["images_processed"] += sum(1 for r in results if r and "error" not in r)
         self.metrics["images_failed"] += sum(1 for r in results if r and "error" in r)
         return results
+
+    def _finish_group(self, items, scored):
+        """Everything `_process_batch` does per image after the analyzers (batch_processor.py:236-355): faces /
+        composition / EXIF inputs, silhouette rule, aggregate + category, the result columns."""
+        cfg = getattr(self.scorer, "config", None)
+        face_analyzer = getattr(self.scorer, "face_analyzer", None)
+        metrics, extras = [], []
+        for item, res in zip(items, scored):
+            h, w = res["image_height"], res["image_width"]
+            face_res = item.get("face_res")
+            if face_res is None:
+                face_res = face_analyzer.analyze_faces(item["img_cv"]) if face_analyzer is not None else dict(NO_FACES)
+            face_ratio = face_res.get("face_area", 0) / (h * w)
+            comp = CompositionAnalyzer.get_placement_data(face_res.get("bbox"), w, h, cfg)
+            isolation_bonus, is_blink = 1.0, 0
+            if face_res["face_count"] > 0:
+                isolation_bonus = max(1.0, face_res["face_sharpness"] / (res["raw_sharpness_variance"] + 1))
+                is_blink = face_res.get("is_blink", 0)
+            exif = item.get("exif_data") or {}
+            is_silhouette = detect_silhouette({"is_silhouette": res["is_silhouette"]}, res["tags"], face_res.get("face_count", 0))
+            # the reference hands exactly these keys to calculate_aggregate_logic (batch_processor.py:271-294):
+            # no tags, luminance or noise columns, so only the face / silhouette / EXIF category rules can fire here
+            metrics.append({
+                "aesthetic": res["aesthetic_unrounded"], "face_count": face_res["face_count"],
+                "face_quality": face_res["face_quality"], "eye_sharpness": face_res["eye_sharpness"],
+                "tech_sharpness": res["tech_sharpness_unrounded"], "color_score": res["color_score_unrounded"],
+                "exposure_score": res["exposure_score_unrounded"], "face_ratio": face_ratio, "comp_score": comp["score"],
+                "isolation_bonus": isolation_bonus, "is_blink": is_blink, "shadow_clipped": res["shadow_clipped"],
+                "highlight_clipped": res["highlight_clipped"], "is_silhouette": is_silhouette,
+                "histogram_spread": res["histogram_spread"], "iso": exif.get("iso"), "f_stop": exif.get("f_stop"),
+                "quality_score": res["quality_score"], "scoring_model": res["scoring_model"],
+            })
+            extras.append((face_res, face_ratio, comp, isolation_bonus, is_blink, exif, is_silhouette))
+        if cfg is not None and hasattr(cfg, "_scoring"):
+            aggregates, categories = cfg._scoring().score_batch(metrics)
+        elif cfg is not None:        # the reference's own ScoringConfig object
+            from .aggregate import AggregateScorer
+            aggregates, categories = AggregateScorer(cfg).score_batch(metrics)
+        else:
+            aggregates, categories = [None] * len(items), [None] * len(items)
+        out = []
+        for item, res, agg, cat, (face_res, face_ratio, comp, iso_bonus, is_blink, exif, is_sil) in zip(
+                items, scored, aggregates, categories, extras):
+            for k in ("aesthetic_unrounded", "tech_sharpness_unrounded", "color_score_unrounded", "exposure_score_unrounded"):
+                res.pop(k)
+            path = item.get("path")
+            res.update({
+                "path": path, "filename": str(path if path is not None else "").rsplit("/", 1)[-1],
+                "category": cat, "aggregate": None if agg is None else round(float(agg), 2),
+                "face_count": face_res["face_count"], "face_quality": face_res["face_quality"],
+                "eye_sharpness": face_res["eye_sharpness"], "face_sharpness": face_res["face_sharpness"],
+                "face_ratio": face_ratio, "comp_score": round(comp["score"], 2), "isolation_bonus": round(iso_bonus, 2),
+                "is_blink": is_blink, "power_point_score": float(comp["power_point_score"]),
+                "raw_eye_sharpness": float(face_res.get("raw_eye_sharpness", 0)),
+                "config_version": getattr(cfg, "version_hash", None),
+                "is_silhouette": is_sil, "is_group_portrait": face_res.get("is_group_portrait", 0),
+                "leading_lines_score": item.get("leading_lines_score", 0),
+                "face_confidence": face_res.get("max_face_confidence", 0),
+                "composition_explanation": comp.get("vlm_explanation"), "composition_pattern": None,
+                "face_details": face_res.get("face_details", []),
+            })
+            res.update(exif)
+            out.append(res)
+        return out
 
     def process_items(self, items):
         """Stream items through `_process_batch` in chunks of batch_size; yields results in order."""

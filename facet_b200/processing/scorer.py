@@ -6,8 +6,9 @@ Only the members the per-image pass touches are provided:
   .score_from_embedding, .tagger, .tech_analyzer
 plus `score_images`, the batched entry the data-parallel driver uses: one call runs the technical
 pass, the CLIP preprocess, the ViT tower + heads + tag similarities for a same-shaped batch that is
-already on the device.  Aggregate scoring (`calculate_aggregate_logic`, scorer.py:769) and SQLite
-writes are host-side consumers of the dicts produced here and stay with the reference.
+already on the device.  Aggregate scoring (`calculate_aggregate_logic`, scorer.py:769) is the
+host-side consumer of the dicts produced here (processing/aggregate.py); SQLite writes stay with
+the reference.
 """
 from __future__ import annotations
 
@@ -81,6 +82,19 @@ class Facet:
         raw = torch.nn.functional.linear(h, self._head["aesthetic_head.2.weight"], self._head["aesthetic_head.2.bias"])
         return _aesthetic_from_raw(float(raw.flatten()[0]))
 
+    # -- scorer.py:726-950 ---------------------------------------------------------------------------------
+    def calculate_aggregate_logic(self, m, config=None):
+        from .aggregate import calculate_aggregate_logic
+        cfg = config or self.config
+        if cfg is None:
+            raise ValueError("calculate_aggregate_logic needs a ScoringConfig (Facet(config=...))")
+        return calculate_aggregate_logic(m, cfg)
+
+    def _determine_photo_category(self, m, cfg=None):
+        from .aggregate import AggregateScorer
+        cfg = cfg or self.config
+        return (cfg._scoring() if hasattr(cfg, "_scoring") else AggregateScorer(cfg)).category_of(m)
+
     # -- batched device-resident entry -------------------------------------------------------------------
     def score_images_device(self, images, rgb_order=False, with_phash=True):
         """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;
@@ -123,6 +137,10 @@ class Facet:
             aest = _aesthetic_from_raw(raw[i])
             results.append({
                 "image_width": w, "image_height": h,
+                # the aggregate is computed from the unrounded analyzer values (batch_processor.py:271-294);
+                # BatchProcessor pops these four
+                "aesthetic_unrounded": aest, "tech_sharpness_unrounded": sharp["normalized"],
+                "color_score_unrounded": color["normalized"], "exposure_score_unrounded": hd["exposure_score"],
                 "aesthetic": round(aest, 2),
                 "tech_sharpness": round(sharp["normalized"], 2),
                 "color_score": round(color["normalized"], 2),
