@@ -92,3 +92,46 @@ def test_tagger_and_single_image_twins(scorer):
     want = [t for t, _ in sorted(best.items(), key=lambda kv: -kv[1])[:3]]
     assert got == want
     assert 0.0 <= sc.score_from_embedding(e) <= 10.0
+
+
+def test_batch_processor_with_config_fills_aggregate_and_category(tmp_path):
+    """With a ScoringConfig the pass also yields `category` / `aggregate` (processing/aggregate.py, pinned on the
+    CPU against the reference); here: they are computed from the unrounded analyzer values of the device pass."""
+    import json
+    import os
+    from facet_b200.config import ScoringConfig
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.processing.aggregate import calculate_aggregate_logic
+    from facet_b200.processing.batch_processor import BatchProcessor
+    from facet_b200.processing.scorer import Facet
+    with open(os.path.join(os.path.dirname(__file__), "golden", "aggregate_golden.json")) as f:
+        cfg_dict = json.load(f)["cases"][0]["config"]
+    path = tmp_path / "scoring_config.json"
+    path.write_text(json.dumps(cfg_dict))
+    cfg = ScoringConfig(str(path))
+    sc = Facet(random_state_dict(0), config=cfg)
+    items = [{"path": f"/x/{i}.jpg", "img_cv": synth_image_bgr(40 + i, 128, 192)} for i in range(5)]
+    items[1]["face_res"] = {"face_count": 1, "face_quality": 8.0, "eye_sharpness": 7.0, "is_blink": 0, "face_area": 4000,
+                            "bbox": [60, 30, 120, 90], "face_sharpness": 900.0, "raw_eye_sharpness": 50.0,
+                            "is_group_portrait": 0, "max_face_confidence": 0.95, "face_details": []}
+    items[2]["exif_data"] = {"iso": 64, "f_stop": 1.8}
+    res = list(BatchProcessor(sc, batch_size=8).process_items(items))
+    direct = sc.score_images(np.stack([it["img_cv"] for it in items]), mono_threshold=cfg.get_monochrome_settings()["saturation_threshold_percent"] / 100)
+    for it, r, d in zip(items, res, direct):
+        assert "error" not in r, r
+        assert r["config_version"] == cfg.version_hash and r["tags"] is None
+        face = it.get("face_res")
+        m = {"aesthetic": d["aesthetic_unrounded"], "face_count": face["face_count"] if face else 0,
+             "face_quality": face["face_quality"] if face else 0, "eye_sharpness": face["eye_sharpness"] if face else 0,
+             "tech_sharpness": d["tech_sharpness_unrounded"], "color_score": d["color_score_unrounded"],
+             "exposure_score": d["exposure_score_unrounded"], "face_ratio": (4000 / (128 * 192)) if face else 0.0,
+             "comp_score": r["comp_score"], "isolation_bonus": max(1.0, 900.0 / (d["raw_sharpness_variance"] + 1)) if face else 1.0,
+             "is_blink": 0, "shadow_clipped": d["shadow_clipped"], "highlight_clipped": d["highlight_clipped"],
+             "is_silhouette": 1 if (d["is_silhouette"] and face) else 0, "histogram_spread": d["histogram_spread"],
+             "iso": it.get("exif_data", {}).get("iso"), "f_stop": it.get("exif_data", {}).get("f_stop"),
+             "quality_score": None, "scoring_model": "clip-mlp"}
+        want, cat = calculate_aggregate_logic(m, cfg)
+        assert r["category"] == cat and r["aggregate"] == round(want, 2)
+        assert 0.0 <= r["aggregate"] <= 10.0
+    assert res[1]["category"] in ("portrait", "portrait_bw", "silhouette", "human_others")
+    assert res[0]["category"] in ("default", "monochrome", "night")
