@@ -36,6 +36,7 @@ _SIGNATURES = {
                                      _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_phash": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int,
                            _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "fb_orient": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "fb_thumbnail": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fb_hamming_pairs": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),

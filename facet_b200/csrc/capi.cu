@@ -233,6 +233,23 @@ int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t 
                             d_vbounds, d_vcoef, vk, out_h, out_w, swap_rb, d_reduced, d_tmp, d_out, (cudaStream_t)stream);
 }
 
+int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_stride, int exif_orientation, int swap_rb,
+              uint8_t* d_dst, int64_t dst_stride, void* stream) {
+    // PIL's transpose method per EXIF orientation (ImageOps.exif_transpose) as (swap, flip_x, flip_y):
+    // 1 none, 2 FLIP_LEFT_RIGHT, 3 ROTATE_180, 4 FLIP_TOP_BOTTOM, 5 TRANSPOSE, 6 ROTATE_270, 7 TRANSVERSE, 8 ROTATE_90
+    static const int kMethod[9][3] = {{0, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 1, 1}, {0, 0, 1}, {1, 0, 0}, {1, 0, 1}, {1, 1, 1}, {1, 1, 0}};
+    if (exif_orientation < 1 || exif_orientation > 8) {
+        fb::set_error("fb_orient: EXIF orientation %d outside 1..8", exif_orientation);
+        return -1;
+    }
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    const int* m = kMethod[exif_orientation];
+    int rc = launch_orient(d_src, n, height, width, (long long)src_stride, m[0], m[1], m[2], swap_rb, d_dst,
+                           (long long)dst_stride, (cudaStream_t)stream);
+    if (rc == 0 && n > 0) count_launch(1);
+    return rc;
+}
+
 int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts, int32_t* d_pairs,
                      int64_t cap, uint64_t* d_count, void* stream) {
     ProfScope ps(PROF_HAMMING, (cudaStream_t)stream);

@@ -39,6 +39,8 @@ int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_s
                  const int* d_hcoef, int hk, const int* d_vbounds, const int* d_vcoef, int vk, uint8_t* d_tmp,
                  unsigned long long* d_hashes, uint8_t* d_small, double* d_dct, uint8_t* d_luma, int luma_ready,
                  const int8_t* d_tc_coef, int tc_kw, int tc_limbs, const int* d_tc_kb0, cudaStream_t stream);
+int launch_orient(const uint8_t* d_src, int n, int H, int W, long long src_stride, int swap, int flip_x, int flip_y,
+                  int swap_rb, uint8_t* d_dst, long long dst_stride, cudaStream_t stream);
 int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
                      const unsigned int* mult4, const int* d_hbounds, const int* d_hcoef, int hk, const int* d_vbounds,
                      const int* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp,

@@ -328,6 +328,25 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
             cap = max(nc, m)
 
 
+def orient(images, exif_orientation: int = 1, swap_rb: bool = False):
+    """`ImageOps.exif_transpose` of a same-shaped batch for the given EXIF orientation code (1..8), then an
+    optional channel swap (`cv2.cvtColor(RGB2BGR)`): the pixel work of utils/image_loading.py:101-106.
+    images: uint8 [n,H,W,3] or [H,W,3].  Returns a new CUDA uint8 tensor ([n,W,H,3] for orientations 5..8)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(images)
+    n, h, w, _ = t.shape
+    code = int(exif_orientation)
+    if not 1 <= code <= 8:
+        raise ValueError(f"EXIF orientation {exif_orientation} outside 1..8")
+    oh, ow = (w, h) if code >= 5 else (h, w)
+    with torch.cuda.device(t.device):
+        out = torch.empty((n, oh, ow, 3), dtype=torch.uint8, device=t.device)
+        _lib.check(lib.fb_orient(_ptr(t), n, h, w, h * w * 3, code, int(bool(swap_rb)), _ptr(out), oh * ow * 3,
+                                 _lib.stream_ptr()), "fb_orient")
+    return out
+
+
 _THUMB_PLANS: dict = {}
 
 

@@ -1,0 +1,31 @@
+"""Orientation / channel order of decoded frames (the tail of utils/image_loading.py:44-112).
+
+The reference decodes on the CPU (`Image.open` / rawpy), applies `ImageOps.exif_transpose`, converts to
+RGB and hands the analyzers a BGR copy (`cv2.cvtColor(RGB2BGR)`, :106).  File decoding stays outside this
+path; what is here is the pixel work after it, for frames that are uploaded as
+decoded: one byte-moving kernel does the transpose method PIL would pick for the EXIF orientation and the
+channel swap (`csrc/orient.cu`).
+"""
+from __future__ import annotations
+
+EXIF_ORIENTATION_TAG = 0x0112
+
+# (swap, flip_x, flip_y) of out(x', y') = in(sx, sy), (u, v) = swap ? (y', x') : (x', y'),
+# sx = flip_x ? W-1-u : u, sy = flip_y ? H-1-v : v -- the table fb_orient uses, keyed by the EXIF code
+METHODS = {1: (0, 0, 0), 2: (0, 1, 0), 3: (0, 1, 1), 4: (0, 0, 1), 5: (1, 0, 0), 6: (1, 0, 1), 7: (1, 1, 1), 8: (1, 1, 0)}
+
+
+def exif_orientation(pil_img) -> int:
+    """EXIF orientation code of a PIL image (1 when absent or invalid), as `exif_transpose` reads it."""
+    try:
+        code = int(pil_img.getexif().get(EXIF_ORIENTATION_TAG, 1))
+    except Exception:
+        return 1
+    return code if 1 <= code <= 8 else 1
+
+
+def orient_frames(frames_rgb, orientation: int = 1, to_bgr: bool = True):
+    """Decoded RGB frames ([n,H,W,3] or [H,W,3] uint8, host or device) -> device frames in the layout the
+    scoring pass takes (`img_cv`: upright, BGR).  Returns a CUDA uint8 tensor [n,H',W',3]."""
+    from .. import ops
+    return ops.orient(frames_rgb, orientation, swap_rb=to_bgr)

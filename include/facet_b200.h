@@ -156,6 +156,16 @@ int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t 
                  int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp, uint8_t* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Frame orientation — the pixel work of utils/image_loading.py:101-106 for frames already in device
+ * memory: ImageOps.exif_transpose (PIL transpose method chosen by EXIF tag 0x0112: 2 FLIP_LEFT_RIGHT,
+ * 3 ROTATE_180, 4 FLIP_TOP_BOTTOM, 5 TRANSPOSE, 6 ROTATE_270, 7 TRANSVERSE, 8 ROTATE_90, 1 none)
+ * followed, when swap_rb, by cv2.cvtColor(RGB2BGR).  d_src [n][height][width][3], d_dst
+ * [n][height'][width'][3] with (height', width') = (width, height) for orientations 5..8; strides in
+ * bytes between images; d_dst must not alias d_src. */
+int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_stride, int exif_orientation, int swap_rb,
+              uint8_t* d_dst, int64_t dst_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Duplicate / burst grouping — replaces the O(N^2) loop of utils/duplicate.py:94-119 and the
  * pairwise predicate of processing/scorer.py:1943-1968.
  *
