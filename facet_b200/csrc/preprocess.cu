@@ -156,13 +156,14 @@ __global__ void __launch_bounds__(256) roi_laplacian_kernel(const uint8_t* __res
     const int w = x2 - x1, h = y2 - y1;
     long long sl = 0;
     unsigned long long sq = 0;
-    const bool ok = w >= 2 && h >= 2 && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H;
+    const bool ok = w >= 1 && h >= 1 && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H;
     if (ok) {
         const long long npx = (long long)w * h;
         for (long long i = threadIdx.x; i < npx; i += blockDim.x) {
             const int yy = (int)(i / w), xx = (int)(i % w);
-            const int yu = yy == 0 ? 1 : yy - 1, yd = yy == h - 1 ? h - 2 : yy + 1;
-            const int xl = xx == 0 ? 1 : xx - 1, xr = xx == w - 1 ? w - 2 : xx + 1;
+            // reflect-101 of the crop; an extent of one pixel reflects onto itself
+            const int yu = yy == 0 ? (h > 1) : yy - 1, yd = yy == h - 1 ? (h > 1 ? h - 2 : 0) : yy + 1;
+            const int xl = xx == 0 ? (w > 1) : xx - 1, xr = xx == w - 1 ? (w > 1 ? w - 2 : 0) : xx + 1;
             const int c = gray_at(img, W, y1 + yy, x1 + xx, rgb);
             const int L = gray_at(img, W, y1 + yu, x1 + xx, rgb) + gray_at(img, W, y1 + yd, x1 + xx, rgb) +
                           gray_at(img, W, y1 + yy, x1 + xl, rgb) + gray_at(img, W, y1 + yy, x1 + xr, rgb) - 4 * c;

@@ -294,7 +294,17 @@ def roi_laplacian_sums(img_bgr: np.ndarray, box) -> tuple:
         return (0, 0, 0)
     g = gray_u8(crop)
     if g.shape[0] < 2 or g.shape[1] < 2:
-        # cv2 falls back to replicate-like behaviour for 1-px extents; out of contract here
-        raise ValueError("roi must be at least 2x2")
+        # reflect-101 of an extent of one pixel is the pixel itself (checked against cv2.Laplacian): that axis
+        # contributes nothing, the other one its second difference
+        gi = g.astype(np.int64)
+        lap = np.zeros_like(gi)
+        for axis in (0, 1):
+            if g.shape[axis] >= 2:
+                pad = [(1, 1) if a == axis else (0, 0) for a in (0, 1)]
+                e = np.pad(gi, pad, mode="reflect")
+                lo = e[:-2] if axis == 0 else e[:, :-2]
+                hi = e[2:] if axis == 0 else e[:, 2:]
+                lap += lo + hi - 2 * gi
+        return (int(lap.size), int(lap.sum()), int((lap * lap).sum()))
     lap = laplacian_i32(g).astype(np.int64)
     return (int(lap.size), int(lap.sum()), int((lap * lap).sum()))

@@ -146,3 +146,31 @@ def test_full_size_properties_24mp():
     crop = img[0, 1000:2000, 1504:3008].contiguous()
     cs = ops.tech_stats(crop, want_hs=True)[0]
     _check_stats(cs, onp.tech_stats(crop.cpu().numpy()))
+
+
+def test_crop_sharpness_matches_cv2_on_the_crop():
+    """FaceAnalyzer._get_crop_sharpness (analyzers/face.py:272-279): the reference's own cv2 calls on the cropped
+    array, including boxes that stick out of the frame and empty ones; isolation bonus of batch_processor.py:254-260."""
+    import cv2
+    from facet_b200.analyzers.face import crop_sharpness, crop_sharpness_batch, isolation_bonus, mean_face_sharpness
+    from facet_b200.analyzers import ImageCache
+    img = synth_image_bgr(5, 240, 360)
+    boxes = [(20, 30, 140, 200), (-15, -4, 60, 50), (300, 200, 500, 400), (0, 0, 360, 240), (50, 50, 50, 90), (400, 10, 420, 30),
+             (100, 100, 101, 103), (10, 10, 12, 12)]
+
+    def ref(b):
+        h, w = img.shape[:2]
+        y1, y2, x1, x2 = max(0, b[1]), min(h, b[3]), max(0, b[0]), min(w, b[2])
+        crop = img[y1:y2, x1:x2]
+        if crop.size == 0:
+            return 0
+        return cv2.Laplacian(cv2.cvtColor(crop, cv2.COLOR_BGR2GRAY), cv2.CV_64F).var()
+
+    got = crop_sharpness_batch(img, boxes)
+    for g, b in zip(got, boxes):
+        want = ref(b)
+        assert abs(g - want) <= 1e-9 * max(1.0, abs(want)), (b, g, want)
+    assert crop_sharpness(img, boxes[0]) == got[0]
+    assert mean_face_sharpness(img, boxes[:2]) == float(np.mean(got[:2])) and mean_face_sharpness(img, []) == 0
+    full = ImageCache(img).laplacian_variance
+    assert isolation_bonus(got[0], full) == max(1.0, got[0] / (full + 1)) and isolation_bonus(99.0, full, face_count=0) == 1.0

@@ -118,3 +118,18 @@ def test_oracle_vs_live_reference():
         _cmp_dict(m["dynamic_range"], TA.get_dynamic_range(img, cache=cache), rel=1e-9)
         _cmp_dict(m["noise"], TA.get_noise_estimate(img, cache=cache), rel=1e-9)
         _cmp_dict(m["contrast"], TA.get_contrast_score(img, cache=cache), rel=1e-9)
+
+
+def test_roi_laplacian_thin_crops_match_cv2():
+    """`_get_crop_sharpness` on crops with an extent of one pixel: reflect-101 maps onto the pixel itself."""
+    import cv2
+    from facet_b200.synth import synth_image_bgr
+    from oracle import technical_np as onp
+    img = synth_image_bgr(5, 120, 160)
+    for box in [(100, 100, 101, 103), (10, 10, 12, 12), (30, 40, 37, 41), (5, 5, 6, 6), (0, 0, 160, 120), (20, 30, 140, 100)]:
+        crop = img[box[1]:box[3], box[0]:box[2]]
+        want = cv2.Laplacian(cv2.cvtColor(crop, cv2.COLOR_BGR2GRAY), cv2.CV_64F).var()
+        n, s1, s2 = onp.roi_laplacian_sums(img, box)
+        assert n == crop.shape[0] * crop.shape[1]
+        assert abs((s2 / n - (s1 / n) ** 2) - want) <= 1e-9 * max(1.0, want), box
+    assert onp.roi_laplacian_sums(img, (50, 50, 50, 90)) == (0, 0, 0)
