@@ -62,8 +62,10 @@ class ScoringPipeline:
             self._free = [torch.cuda.Event() for _ in range(2)]
         return self._bufs
 
-    def run_host(self, host_batch, rgb_order=False):
-        """host_batch: CPU uint8 tensor [n,H,W,3] (pinned for full PCIe rate).  Returns a dict of
+    def run_host(self, host_batch, rgb_order=False, orientation=1):
+        """host_batch: CPU uint8 tensor [n,H,W,3] (pinned for full PCIe rate); `orientation` is the EXIF code of
+        the (same-shaped) frames when they are uploaded as decoded, without `exif_transpose` (the device does it,
+        utils/image_loading.py:101 of the reference).  Returns a dict of
         host numpy arrays: hist256 [n,256], sums [n,4], derived [n,4], embedding [n,768],
         aesthetic_raw [n], tag_sims [n,T] (or None).  H2D and D2H happen inside this call."""
         torch = _lib.require_cuda()
@@ -80,7 +82,8 @@ class ScoringPipeline:
                 bufs[slot][:k].copy_(host_batch[start:start + k], non_blocking=True)
                 self._ready[slot].record(self.copy_stream)
             compute.wait_event(self._ready[slot])
-            dev = self.scorer.score_images_device(bufs[slot][:k], rgb_order=rgb_order)
+            frames = bufs[slot][:k] if orientation == 1 else ops.orient(bufs[slot][:k], orientation)
+            dev = self.scorer.score_images_device(frames, rgb_order=rgb_order)
             self._free[slot].record(compute)
             outs.append(dev)
         cat = lambda key: torch.cat([o[key] for o in outs]).cpu().numpy() if outs[0][key] is not None else None
