@@ -62,7 +62,7 @@ def histogram(st: TechStats, shadow_threshold: float = 0.15, highlight_threshold
     counts = st.hist256.astype(np.float32)
     total = counts.sum()
     p = counts / total if total > 0 else counts
-    blob = struct.pack("256f", *p)
+    blob = p.astype("<f4", copy=False).tobytes()      # = struct.pack('256f', *p) of technical.py:158, 20x cheaper
     mu = np.sum(_BINS * p)
     spread = np.sqrt(np.sum(((_BINS - mu) ** 2) * p))
     lum = mu / 255.0
@@ -145,3 +145,101 @@ def contrast(st: TechStats) -> dict:
         "percentile_contrast": round(float(pc), 4),
         "rms_contrast": round(float(rms), 4),
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# The same closed forms over a whole batch (one image per row).  Every array operation is the
+# scalar function's operation applied row-wise in the same dtype and order (reductions run along
+# the contiguous axis, i.e. NumPy's pairwise sum per row), so the dicts are bit-identical to the
+# scalar ones (tests/test_closed_form_batch.py); only the Python-level work per image shrinks to
+# the rounding of the final numbers.
+# ---------------------------------------------------------------------------------------------
+def _percentiles_batch(hists: np.ndarray, qs) -> list:
+    """np.percentile(gray, q) per row for every q in qs -> list of float64 [n] arrays."""
+    cum = np.cumsum(hists, axis=1)
+    n = cum[:, -1]
+    out = []
+    for q in qs:
+        virtual = (n - 1) * (q / 100.0)
+        k = np.floor(virtual)
+        t = virtual - k
+        ki = k.astype(np.int64)
+        a = (cum < (ki + 1)[:, None]).sum(axis=1).astype(np.float64)           # searchsorted(cum, k + 1, 'left')
+        b = (cum < (np.minimum(ki + 1, n - 1) + 1)[:, None]).sum(axis=1).astype(np.float64)
+        out.append(np.where(t >= 0.5, b - (b - a) * (1 - t), a + (b - a) * t))
+    return out
+
+
+def all_metrics_batch(height: int, width: int, hists: np.ndarray, sum_lap, sum_lap_sq, sum_abs_noise, hs_entropy,
+                      sum_saturation, mono_threshold: float = 0.1, shadow_threshold: float = 0.15,
+                      highlight_threshold: float = 0.10) -> list:
+    """Per image: {'sharpness', 'color', 'histogram', 'monochrome', 'dynamic_range', 'noise', 'contrast'} with
+    the dicts of the scalar functions above.  hists: int64 [n,256]; the other arguments are length-n sequences."""
+    hists = np.ascontiguousarray(hists, dtype=np.int64)
+    n_img = hists.shape[0]
+    if n_img == 0:
+        return []
+    npx = height * width
+    # sharpness / colour / monochrome / noise: a handful of scalar operations per image
+    counts = hists.astype(np.float32)
+    total = counts.sum(axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = np.where((total > 0)[:, None], counts / total[:, None], counts)
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    bp = _BINS * p                                                # float64 [n,256]
+    mu = np.sum(bp, axis=1)
+    spread = np.sqrt(np.sum(((_BINS - mu[:, None]) ** 2) * p, axis=1))
+    lum = mu / 255.0
+    shadow = np.sum(p[:, :30], axis=1)
+    highlight = np.sum(p[:, 225:], axis=1)
+    low, high = np.sum(p[:, :85], axis=1), np.sum(p[:, 170:], axis=1)
+    x = p * 256
+    dev = x - x.mean(axis=1)[:, None]
+    d2 = dev * dev
+    m2 = np.mean(d2, axis=1)
+    m4 = np.mean(d2 * dev * dev, axis=1)
+    p2, p98, p5, p95 = _percentiles_batch(hists, (2, 98, 5, 95))
+    ntot = hists.sum(axis=1)
+    s1 = hists @ _BINS_I64
+    s2 = hists @ (_BINS_I64 * _BINS_I64)
+    denom = 6 * (width - 2) * (height - 2)
+    root_half_pi = np.sqrt(0.5 * np.pi)
+    out = []
+    for i in range(n_img):
+        mean = int(sum_lap[i]) / npx
+        var = int(sum_lap_sq[i]) / npx - mean * mean
+        ent = float(hs_entropy[i])
+        silhouette = 1 if (low[i] > 0.35 and high[i] > 0.25) else 0
+        bimodality = -(float(m4[i] / (m2[i] * m2[i])) - 3.0) if m2[i] != 0 else float("nan")
+        score = 7.0 - abs(lum[i] - 0.5) * 8 + min(4.0, spread[i] / 20.0) - max(0, bimodality - 1.0) * 0.6
+        if not silhouette:
+            score -= shadow[i] * 4.0 + highlight[i] * 5.0
+        score = max(0, min(10.0, score))
+        mean_sat = float(sum_saturation[i]) / npx / 255.0
+        lo2 = 1 if p2[i] < 1 else p2[i]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sigma = np.float64(int(sum_abs_noise[i])) * root_half_pi / denom
+        pc = (p95[i] - p5[i]) / 255.0
+        nn = int(ntot[i])
+        v = int(s2[i]) / nn - (int(s1[i]) / nn) ** 2
+        rms = math.sqrt(v if v > 0 else 0.0) / 255.0
+        out.append({
+            "sharpness": {"raw_variance": var, "normalized": float(min(10.0, var / 50.0))},
+            "color": {"raw_entropy": ent, "normalized": float(min(10.0, ent * 10.0 / 15.5))},
+            "histogram": {
+                "histogram_bytes": p[i].tobytes(),
+                "spread": round(float(spread[i]), 4),
+                "mean_luminance": round(float(lum[i]), 4),
+                "bimodality": round(float(bimodality), 4),
+                "exposure_score": round(float(score), 2),
+                "shadow_clipped": 1 if shadow[i] > shadow_threshold else 0,
+                "highlight_clipped": 1 if highlight[i] > highlight_threshold else 0,
+                "is_silhouette": silhouette,
+            },
+            "monochrome": {"is_monochrome": 1 if mean_sat < mono_threshold else 0, "mean_saturation": round(mean_sat, 4)},
+            "dynamic_range": {"dynamic_range_stops": round(float(np.log2(max(p98[i], 1) / lo2)), 2)},
+            "noise": {"noise_sigma": round(float(sigma), 2)},
+            "contrast": {"contrast_score": round(float(min(10.0, pc * 5.0 + rms * 20.0)), 2),
+                         "percentile_contrast": round(float(pc), 4), "rms_contrast": round(float(rms), 4)},
+        })
+    return out

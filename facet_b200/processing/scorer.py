@@ -125,11 +125,13 @@ class Facet:
         raw = dev["aesthetic_raw"].cpu().numpy()
         emb = dev["embedding"].cpu().numpy()
         sims = dev["tag_sims"].cpu().numpy() if dev["tag_sims"] is not None else None
+        metrics = cf.all_metrics_batch(h, w, hist, sums[:, 0], sums[:, 1], sums[:, 2], der[:, 0], der[:, 1],
+                                       mono_threshold=mono_threshold)      # the 7 analyzer dicts per image, one pass
         results = []
         for i in range(n):
-            st = cf.TechStats(h, w, hist[i], int(sums[i, 0]), int(sums[i, 1]), int(sums[i, 2]), float(der[i, 0]), float(der[i, 1]))
-            sharp, color, hd = cf.sharpness(st), cf.color_harmony(st), cf.histogram(st)
-            mono, dr, nz, ct = cf.monochrome(st, mono_threshold), cf.dynamic_range(st), cf.noise(st), cf.contrast(st)
+            m = metrics[i]
+            sharp, color, hd = m["sharpness"], m["color"], m["histogram"]
+            mono, dr, nz, ct = m["monochrome"], m["dynamic_range"], m["noise"], m["contrast"]
             tags = None
             if self.tagger is not None and sims is not None:
                 tl = self.tagger.get_tags_from_similarities(sims[i], tag_threshold, max_tags)
