@@ -391,11 +391,9 @@ def main():
         d2h = 0
         a.record()
         for _ in range(n_e2e):
-            embs, hashes_h = [], []
-            for _r in range(reps):
-                res = pipe.run_host(host)
-                embs.append(res["embedding"])
-                hashes_h.append(res["phash"])
+            # the step's B frames reach the pipeline as B/32 host batches, back to back like a loader delivers them
+            res = pipe.run_host_stream(host for _r in range(reps))
+            embs, hashes_h = [res["embedding"]], [res["phash"]]
             emb = torch.from_numpy(np.concatenate(embs)).to(device)
             emb = all_gather_embeddings(emb) if world > 1 else emb
             p_, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)

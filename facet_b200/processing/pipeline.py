@@ -68,24 +68,39 @@ class ScoringPipeline:
         utils/image_loading.py:101 of the reference).  Returns a dict of
         host numpy arrays: hist256 [n,256], sums [n,4], derived [n,4], embedding [n,768],
         aesthetic_raw [n], tag_sims [n,T] (or None).  H2D and D2H happen inside this call."""
+        return self.run_host_stream([host_batch], rgb_order=rgb_order, orientation=orientation)
+
+    def run_host_stream(self, host_batches, rgb_order=False, orientation=1):
+        """Like `run_host` for a sequence (or generator) of same-shaped host batches, e.g. what a loader thread hands
+        over: the chunks of consecutive batches follow each other through the two device buffers without draining
+        the copy / compute overlap in between, and the small results are read back once at the end."""
         torch = _lib.require_cuda()
-        n, h, w, _ = host_batch.shape
-        bufs = self._buffers(h, w)
         compute = torch.cuda.current_stream(self.device)
         outs = []
-        for ci, start in enumerate(range(0, n, self.chunk)):
-            k = min(self.chunk, n - start)
-            slot = ci & 1
-            with torch.cuda.stream(self.copy_stream):
-                if ci >= 2:
-                    self.copy_stream.wait_event(self._free[slot])     # compute finished with this buffer
-                bufs[slot][:k].copy_(host_batch[start:start + k], non_blocking=True)
-                self._ready[slot].record(self.copy_stream)
-            compute.wait_event(self._ready[slot])
-            frames = bufs[slot][:k] if orientation == 1 else ops.orient(bufs[slot][:k], orientation)
-            dev = self.scorer.score_images_device(frames, rgb_order=rgb_order)
-            self._free[slot].record(compute)
-            outs.append(dev)
+        ci = 0
+        bufs = None
+        for host_batch in host_batches:
+            n, h, w, _ = host_batch.shape
+            if bufs is None:
+                bufs = self._buffers(h, w)
+            elif tuple(bufs[0].shape[1:3]) != (h, w):
+                raise ValueError("run_host_stream takes batches of one frame shape")
+            for start in range(0, n, self.chunk):
+                k = min(self.chunk, n - start)
+                slot = ci & 1
+                with torch.cuda.stream(self.copy_stream):
+                    if ci >= 2:
+                        self.copy_stream.wait_event(self._free[slot])     # compute finished with this buffer
+                    bufs[slot][:k].copy_(host_batch[start:start + k], non_blocking=True)
+                    self._ready[slot].record(self.copy_stream)
+                compute.wait_event(self._ready[slot])
+                frames = bufs[slot][:k] if orientation == 1 else ops.orient(bufs[slot][:k], orientation)
+                dev = self.scorer.score_images_device(frames, rgb_order=rgb_order)
+                self._free[slot].record(compute)
+                outs.append(dev)
+                ci += 1
+        if not outs:
+            raise ValueError("run_host_stream needs at least one frame")
         cat = lambda key: torch.cat([o[key] for o in outs]).cpu().numpy() if outs[0][key] is not None else None
         res = {key: cat(key) for key in ("hist256", "sums", "derived", "embedding", "aesthetic_raw", "tag_sims", "phash")}
         res["hist256"] = res["hist256"].view(np.uint32)

@@ -74,6 +74,12 @@ def test_host_pipeline_matches_direct_call(scorer):
     assert np.array_equal(res["phash"], direct["phash"].cpu().numpy().view(np.uint64))
     np.testing.assert_allclose(res["embedding"], direct["embedding"].cpu().numpy(), rtol=0, atol=1e-6)
     assert pipe.h2d_bytes(11, 256, 384) == frames.nbytes
+    # consecutive host batches as one stream: same results as one call on their concatenation
+    parts = [host[:5], host[5:6], host[6:]]
+    streamed = pipe.run_host_stream(iter(parts))
+    for key in ("hist256", "sums", "phash"):
+        assert np.array_equal(streamed[key], res[key]), key
+    np.testing.assert_allclose(streamed["embedding"], res["embedding"], rtol=0, atol=1e-6)
     # frames uploaded as decoded (stored rotated, EXIF code 6, RGB): the device orients them
     stored = np.ascontiguousarray(np.rot90(frames[..., ::-1], k=1, axes=(1, 2)))
     res6 = pipe.run_host(torch.from_numpy(stored).pin_memory(), rgb_order=True, orientation=6)
