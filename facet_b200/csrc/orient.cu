@@ -8,7 +8,8 @@
 // sy = flip_y ? H-1-v : v.  A CTA moves one 64 x 64 pixel tile of the SOURCE through shared memory, so that the
 // transposing methods read and write full sectors too.
 //   fast path (full tile, 16-byte aligned rows; one instantiation per method): 16-byte loads into the input tile;
-//     every thread gathers 4 output pixels (12 byte loads at compile-time channel offsets, one address per pixel)
+//     every thread gathers 4 output pixels (non-transposing methods: three word loads and compile-time byte
+//     selections, mirror and channel swap included; transposing methods: 12 byte loads, one address per pixel)
 //     into three words of an output tile whose 49-word pitch keeps the transposed writes conflict-free; the output
 //     tile leaves as coalesced 16-byte (or 4-byte) stores.  Edge tiles whose sides are multiples of 16 x 4 pixels take
 //     the same path with bounds.  For the transposing methods a warp takes 32 consecutive source columns of
@@ -39,6 +40,40 @@ struct OrientArgs {
 constexpr int kPitchIn = kTile * 3 + 16;     // fast path: 16-byte aligned rows
 constexpr int kPitchOut = kTile * 3 + 4;     // 49 words: odd, so a column of the output tile spans all banks
 
+// Byte j (0..11) of four output pixels = byte src_byte_of(j) of the four source pixels they come from (12 contiguous
+// bytes, ascending x): mirrored pixel order when FX, reversed channel order when RB.
+template <bool FX, bool RB>
+__host__ __device__ constexpr int src_byte_of(int j) {
+    const int i = j / 3, c = j % 3;
+    return 3 * (FX ? 3 - i : i) + (RB ? 2 - c : c);
+}
+
+// One output word from bytes A, B, C, D (indices 0..11) of the three words (w0, w1, w2): one PRMT when they come from
+// at most two of the words, two otherwise.
+template <int A, int B, int C, int D>
+__device__ __forceinline__ uint32_t pick4(uint32_t w0, uint32_t w1, uint32_t w2) {
+    constexpr int wa[4] = {A >> 2, B >> 2, C >> 2, D >> 2};
+    constexpr int ba[4] = {A & 3, B & 3, C & 3, D & 3};
+    constexpr bool u0 = wa[0] == 0 || wa[1] == 0 || wa[2] == 0 || wa[3] == 0;
+    constexpr bool u1 = wa[0] == 1 || wa[1] == 1 || wa[2] == 1 || wa[3] == 1;
+    constexpr bool u2 = wa[0] == 2 || wa[1] == 2 || wa[2] == 2 || wa[3] == 2;
+    if constexpr (u0 && u1 && u2) {
+        // bytes of w0 / w1 into their final positions first (the positions fed by w2 are don't-cares), then w2
+        constexpr uint32_t sel1 = (wa[0] == 1 ? 4 + ba[0] : ba[0]) | ((wa[1] == 1 ? 4 + ba[1] : ba[1]) << 4) |
+                                  ((wa[2] == 1 ? 4 + ba[2] : ba[2]) << 8) | ((wa[3] == 1 ? 4 + ba[3] : ba[3]) << 12);
+        constexpr uint32_t sel2 = (wa[0] == 2 ? 4 + ba[0] : 0) | ((wa[1] == 2 ? 4 + ba[1] : 1) << 4) |
+                                  ((wa[2] == 2 ? 4 + ba[2] : 2) << 8) | ((wa[3] == 2 ? 4 + ba[3] : 3) << 12);
+        return __byte_perm(__byte_perm(w0, w1, sel1), w2, sel2);
+    } else {
+        constexpr int X = u0 ? 0 : 1;                    // first word in use
+        constexpr int Y = u2 ? 2 : 1;                    // last word in use (may equal X)
+        const uint32_t x = X == 0 ? w0 : w1, y = Y == 2 ? w2 : w1;
+        constexpr uint32_t sel = (wa[0] == X ? ba[0] : 4 + ba[0]) | ((wa[1] == X ? ba[1] : 4 + ba[1]) << 4) |
+                                 ((wa[2] == X ? ba[2] : 4 + ba[2]) << 8) | ((wa[3] == X ? ba[3] : 4 + ba[3]) << 12);
+        return __byte_perm(x, y, sel);
+    }
+}
+
 // FULL: a 64 x 64 tile, no bounds checks.  Otherwise tw (a multiple of 16) x th (a multiple of 4) pixels.
 // VEC: the destination rows are 16-byte aligned, so the output tile leaves as 16-byte stores.
 template <bool SWAP, bool FX, bool FY, bool RB, bool FULL, bool VEC>
@@ -65,20 +100,35 @@ __device__ __forceinline__ void tile_fast(const uint8_t* __restrict__ src_tile, 
         const int r = SWAP ? (g & 63) : (g >> 4);
         const int q = SWAP ? (g >> 6) : (g & 15);
         if (!FULL && (r >= oh || 4 * q >= ow)) continue;
-        uint32_t b[4][3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = 4 * q + i;
-            const int u = SWAP ? r : p, v = SWAP ? p : r;
-            const int lx = FX ? tw - 1 - u : u, ly = FY ? th - 1 - v : v;
-            const uint8_t* px = s_in + ly * kPitchIn + lx * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) b[i][c] = px[RB ? 2 - c : c];
-        }
         uint32_t* o = reinterpret_cast<uint32_t*>(s_out + r * kPitchOut + 12 * q);
-        o[0] = b[0][0] | (b[0][1] << 8) | (b[0][2] << 16) | (b[1][0] << 24);
-        o[1] = b[1][1] | (b[1][2] << 8) | (b[2][0] << 16) | (b[2][1] << 24);
-        o[2] = b[2][2] | (b[3][0] << 8) | (b[3][1] << 16) | (b[3][2] << 24);
+        if (!SWAP) {
+            // the 4 source pixels are 12 contiguous, word-aligned bytes of one row (ascending x): three word loads,
+            // then every output word is a compile-time byte selection of them (mirror in x and channel swap included)
+            const int ly = FY ? th - 1 - r : r;
+            const int s0 = FX ? tw - 4 - 4 * q : 4 * q;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + ly * kPitchIn + s0 * 3);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            o[0] = pick4<src_byte_of<FX, RB>(0), src_byte_of<FX, RB>(1), src_byte_of<FX, RB>(2), src_byte_of<FX, RB>(3)>(w0, w1, w2);
+            o[1] = pick4<src_byte_of<FX, RB>(4), src_byte_of<FX, RB>(5), src_byte_of<FX, RB>(6), src_byte_of<FX, RB>(7)>(w0, w1, w2);
+            o[2] = pick4<src_byte_of<FX, RB>(8), src_byte_of<FX, RB>(9), src_byte_of<FX, RB>(10), src_byte_of<FX, RB>(11)>(w0, w1, w2);
+        } else {
+            // the 4 source pixels sit in 4 consecutive rows at the same x: byte loads at compile-time channel offsets
+            // (a warp's 32 columns fall into 24 consecutive words).  Word loads + funnel shifts were measured too:
+            // faster for TRANSPOSE, slower for the three rotating methods, so the byte form stays.
+            const int lx = FX ? tw - 1 - r : r;
+            uint32_t b[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = 4 * q + i;
+                const int ly = FY ? th - 1 - p : p;
+                const uint8_t* px = s_in + ly * kPitchIn + lx * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) b[i][c] = px[RB ? 2 - c : c];
+            }
+            o[0] = b[0][0] | (b[0][1] << 8) | (b[0][2] << 16) | (b[1][0] << 24);
+            o[1] = b[1][1] | (b[1][2] << 8) | (b[2][0] << 16) | (b[2][1] << 24);
+            o[2] = b[2][2] | (b[3][0] << 8) | (b[3][1] << 16) | (b[3][2] << 24);
+        }
     }
     __syncthreads();
     if (VEC) {
