@@ -119,7 +119,7 @@ class ScoringConfig:
         if corrected:
             if self.config_path is not None:
                 self.save_config()
-            self.version_hash = self._compute_version_hash()
+            self.refresh()
             if verbose:
                 print(f"Corrected weights of {corrected}; saved to {self.config_path}")
         return len(corrected) == 0, corrected
@@ -169,14 +169,26 @@ class ScoringConfig:
         return sorted(self.config.get("categories", []), key=lambda c: c.get("priority", 100))
 
     def _scoring(self):
+        """The compiled scoring sections (processing/aggregate.py), built on first use.  Edits made to `self.config`
+        afterwards are picked up by `refresh()` (validate_weights calls it)."""
         from .processing.aggregate import AggregateScorer
         cached = getattr(self, "_aggregate_scorer", None)
         if cached is None or cached.version_hash != self.version_hash:
             cached = self._aggregate_scorer = AggregateScorer(self)
         return cached
 
+    def refresh(self):
+        """Re-hash and recompile after in-place edits of `self.config` (e.g. a weight optimiser)."""
+        self.version_hash = self._compute_version_hash()
+        self._aggregate_scorer = None
+
     def get_weights(self, category):
-        return dict(self._scoring().weights_of(category))
+        """scoring_config.py:301-338, always read from the live config."""
+        from .processing.aggregate import _convert_weights
+        for cat in self.config.get("categories", []):
+            if cat.get("name") == category:
+                return _convert_weights(cat)
+        return {}
 
     def determine_category(self, photo_data: dict) -> str:
         return self._scoring().match_category(photo_data)

@@ -169,3 +169,18 @@ def test_batch_processor_assembles_reference_columns(golden, tmp_path_factory):
             assert r["camera_model"] == "X"
         seen.add(cat)
     assert {"default", "portrait"} <= seen or len(seen) >= 3
+
+
+def test_refresh_picks_up_in_place_edits(golden):
+    cfg = ScoringConfig.from_dict(json.loads(json.dumps(golden["cases"][0]["config"])))
+    m = {"aesthetic": 8.0, "tech_sharpness": 3.0, "exposure_score": 6.0, "comp_score": 5.0, "color_score": 4.0}
+    before, cat = calculate_aggregate_logic(m, cfg)
+    assert cat == "default"
+    default = next(c for c in cfg.config["categories"] if c["name"] == "default")
+    default["weights"] = {"aesthetic_percent": 100}
+    default["modifiers"] = {}
+    assert cfg.get_weights("default") == {"aesthetic": 1.0}           # the getter reads the live config
+    old_hash = cfg.version_hash
+    cfg.refresh()
+    after, _ = calculate_aggregate_logic(m, cfg)
+    assert cfg.version_hash != old_hash and after == 8.0 and after != before
