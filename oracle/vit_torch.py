@@ -4,12 +4,15 @@ aesthetic head and the tag similarity, as the reference runs them
 
 open_clip (requirements.txt:8, `open-clip-torch>=2.20.0`) is third-party, not vendored under
 /root/reference and not installed in this image, and the reference has no test that pins its
-outputs: **parity unpinned** beyond architecture equivalence.  The forward pass below follows
-open_clip's published `VisionTransformer.forward` / `ResidualAttentionBlock` with
-`nn.MultiheadAttention` semantics (fused in_proj, 16 heads, scale 1/sqrt(64)); SURVEY.md §8c
-records that the equivalent HF `CLIPVisionModelWithProjection` config instantiates here.
-`tests/test_oracle_vit.py` checks this restatement against torch.nn.MultiheadAttention /
-torch.nn.functional primitives.
+outputs.  The forward pass below follows open_clip's published `VisionTransformer.forward` /
+`ResidualAttentionBlock` with `nn.MultiheadAttention` semantics (fused in_proj, 16 heads, scale
+1/sqrt(64)).  Pinned against two independent implementations:
+  * `tests/test_oracle_vit_hf.py`: HuggingFace `transformers.CLIPVisionModelWithProjection` (the tower
+    open_clip's ViT-L-14 checkpoints convert to) loaded with the same tensors, all 24 layers, pooled
+    output and per-layer hidden states at rtol 1e-4;
+  * `tests/test_oracle_vit.py`: torch.nn.MultiheadAttention modules on a 2-layer slice.
+open_clip's own code cannot be run here, so what remains unpinned is only the claim that open_clip's
+`ViT-L-14` is this architecture.
 """
 from __future__ import annotations
 
