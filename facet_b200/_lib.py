@@ -66,7 +66,7 @@ _SIGNATURES.update({
     "fb_vit_im2col": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_vit_layernorm": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "fb_vit_attention": (C.c_int, [_P, C.c_int, _P, _P]),
-    "fb_vit_attention_mma": (C.c_int, [_P, C.c_int, _P, _P]),
+    "fb_embedding_heads": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "fb_vit_attention_f16": (C.c_int, [_P, C.c_int, _P, _P]),
 })
 

@@ -29,44 +29,57 @@ const char* get_error() { return g_err; }
 void count_launch(int k) { g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
 
 // ---- event-pair profiler -----------------------------------------------------------------------------
+// A ProfScope takes (or creates) an event pair under the lock and keeps the two handles itself, so the
+// destructor never indexes the shared vectors (another thread's constructor may be growing them).
 namespace {
 struct ProfState {
     std::mutex mu;
-    bool on = false;
+    std::atomic<bool> on{false};
     std::vector<cudaEvent_t> ev;     // pairs: [2*i] begin, [2*i+1] end
     std::vector<int> cat;
     size_t used = 0;
 } g_prof;
 }  // namespace
 
-ProfScope::ProfScope(int c, cudaStream_t st) : slot(-1), stream(st) {
-    if (!g_prof.on) return;
-    std::lock_guard<std::mutex> lk(g_prof.mu);
-    if (g_prof.used == g_prof.cat.size()) {
-        cudaEvent_t a, b;
-        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
-        g_prof.ev.push_back(a);
-        g_prof.ev.push_back(b);
-        g_prof.cat.push_back(c);
+ProfScope::ProfScope(int c, cudaStream_t st) : slot(-1), stream(st), begin(nullptr), end(nullptr) {
+    if (!g_prof.on.load(std::memory_order_relaxed)) return;
+    {
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        if (!g_prof.on.load(std::memory_order_relaxed)) return;
+        if (g_prof.used == g_prof.cat.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess) return;
+            if (cudaEventCreate(&b) != cudaSuccess) {
+                cudaEventDestroy(a);
+                return;
+            }
+            g_prof.ev.push_back(a);
+            g_prof.ev.push_back(b);
+            g_prof.cat.push_back(c);
+        }
+        slot = (int)g_prof.used++;
+        g_prof.cat[slot] = c;
+        begin = g_prof.ev[2 * slot];
+        end = g_prof.ev[2 * slot + 1];
     }
-    slot = (int)g_prof.used++;
-    g_prof.cat[slot] = c;
-    cudaEventRecord(g_prof.ev[2 * slot], stream);
+    cudaEventRecord(begin, stream);
 }
 ProfScope::~ProfScope() {
-    if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+    if (slot >= 0) cudaEventRecord(end, stream);
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
-        cached = sms;
+    // per device ordinal: one process may drive several different GPUs
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> cached[kMaxDev];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) dev = 0;
+    int sms = cached[dev].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached[dev].store(sms, std::memory_order_relaxed);
     }
-    return cached;
+    return sms;
 }
 
 }  // namespace fb
@@ -82,7 +95,7 @@ int fb_device_sm_count(void) { return sm_count(); }
 
 void fb_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
-    g_prof.on = on != 0;
+    g_prof.on.store(on != 0, std::memory_order_relaxed);
     g_prof.used = 0;
 }
 
@@ -333,8 +346,12 @@ int fb_vit_attention_f16(const void* d_qkv_f16, int batch, void* d_out_f16, void
     return rc;
 }
 
-int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
-    int rc = launch_attention(d_qkv_bf16, batch, d_out_bf16, (cudaStream_t)stream);
+int fb_embedding_heads(const float* d_vectors, int n, const float* head_w1, const float* head_b1, const float* head_w2,
+                       const float* head_b2, const float* d_tag_emb, int n_tags, float* d_raw, float* d_tag_sims,
+                       void* stream) {
+    ProfScope ps(PROF_TAIL, (cudaStream_t)stream);
+    int rc = launch_embedding_heads(d_vectors, n, head_w1, head_b1, head_w2, head_b2, d_tag_emb, n_tags, d_raw, d_tag_sims,
+                                    (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }

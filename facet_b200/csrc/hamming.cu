@@ -13,58 +13,72 @@ namespace fb {
 
 namespace {
 
-constexpr int kRowTile = 2048;     // == FB_HAMMING_ROW_TILE
-constexpr int kColTile = 2048;
 constexpr int kThreads = 256;
-constexpr int kRowsPerThread = kRowTile / kThreads;   // 8
 
+// Upper-triangle tile `lin` (row-major over the tiles (rt, ct), ct >= rt, of a T x T tile grid) -> (rt, ct).
+__device__ __forceinline__ void tri_tile(long long lin, long long T, long long& rt, long long& ct) {
+    // tiles before row r: r * T - r (r - 1) / 2
+    const double b = 2.0 * (double)T + 1.0;
+    long long r = (long long)((b - sqrt(b * b - 8.0 * (double)lin)) * 0.5);
+    r = r < 0 ? 0 : (r >= T ? T - 1 : r);
+    while (r > 0 && r * T - r * (r - 1) / 2 > lin) --r;
+    while ((r + 1) * T - (r + 1) * r / 2 <= lin) ++r;
+    rt = r;
+    ct = r + (lin - (r * T - r * (r - 1) / 2));
+}
+
+// Square tiles of TILE = 256 * RPT hashes; thread = RPT rows, the column tile staged in shared memory.  The
+// upper-triangle tiles are dealt to the parts round-robin by their linear index (tile `lin` belongs to part
+// lin % nparts), so a triangular problem balances across GPUs to within one tile, and CTAs stride over the
+// part's tiles (no grid-dimension limit).  RPT = 1 for small sets (enough tiles to fill the SMs), 8 otherwise.
+template <int RPT>
 __global__ void __launch_bounds__(kThreads) hamming_pairs_kernel(
-    const unsigned long long* __restrict__ h, long long n, int thr, int part, int nparts,
-    int* __restrict__ pairs, long long cap, unsigned long long* __restrict__ count) {
-    __shared__ unsigned long long s_cols[kColTile];
-    const long long rt = (long long)blockIdx.y * nparts + part;   // global row-tile index
-    const long long ct = blockIdx.x;
-    if (ct < rt) return;                                           // strictly-lower tiles hold no i<j pair
-    const long long row0 = rt * kRowTile, col0 = ct * kColTile;
-    if (row0 >= n || col0 >= n) return;
+    const unsigned long long* __restrict__ h, long long n, int thr, int part, int nparts, long long T,
+    long long my_tiles, int* __restrict__ pairs, long long cap, unsigned long long* __restrict__ count) {
+    constexpr int TILE = kThreads * RPT;
+    __shared__ unsigned long long s_cols[TILE];
     const int tid = threadIdx.x;
-
-    for (int c = tid; c < kColTile; c += kThreads) {
-        long long j = col0 + c;
-        s_cols[c] = (j < n) ? h[j] : 0ull;
-    }
-    unsigned long long hr[kRowsPerThread];
-    bool rv[kRowsPerThread];
-#pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
-        long long i = row0 + tid + (long long)r * kThreads;
-        rv[r] = i < n;
-        hr[r] = rv[r] ? h[i] : 0ull;
-    }
-    __syncthreads();
-    const int ncols = (int)min((long long)kColTile, n - col0);
-    const bool diagonal = (ct == rt);
-
-#pragma unroll 4
-    for (int c = 0; c < ncols; ++c) {
-        const unsigned long long hc = s_cols[c];
-        int d[kRowsPerThread];
-        int dmin = 64;
-#pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
-            d[r] = __popcll(hr[r] ^ hc);
-            dmin = min(dmin, d[r]);
+    for (long long k = blockIdx.x; k < my_tiles; k += gridDim.x) {
+        long long rt, ct;
+        tri_tile(k * nparts + part, T, rt, ct);
+        const long long row0 = rt * TILE, col0 = ct * TILE;
+        __syncthreads();                                   // the previous tile's columns are no longer read
+        for (int c = tid; c < TILE; c += kThreads) {
+            long long j = col0 + c;
+            s_cols[c] = (j < n) ? h[j] : 0ull;
         }
-        if (dmin <= thr) {
-            const long long j = col0 + c;
+        unsigned long long hr[RPT];
+        bool rv[RPT];
 #pragma unroll
-            for (int r = 0; r < kRowsPerThread; ++r) {
-                const long long i = row0 + tid + (long long)r * kThreads;
-                if (d[r] <= thr && rv[r] && (!diagonal || j > i)) {
-                    unsigned long long pos = atomicAdd(count, 1ull);
-                    if ((long long)pos < cap) {
-                        pairs[2 * pos] = (int)i;
-                        pairs[2 * pos + 1] = (int)j;
+        for (int r = 0; r < RPT; ++r) {
+            long long i = row0 + tid + (long long)r * kThreads;
+            rv[r] = i < n;
+            hr[r] = rv[r] ? h[i] : 0ull;
+        }
+        __syncthreads();
+        const int ncols = (int)min((long long)TILE, n - col0);
+        const bool diagonal = (ct == rt);
+#pragma unroll 4
+        for (int c = 0; c < ncols; ++c) {
+            const unsigned long long hc = s_cols[c];
+            int d[RPT];
+            int dmin = 64;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                d[r] = __popcll(hr[r] ^ hc);
+                dmin = min(dmin, d[r]);
+            }
+            if (dmin <= thr) {
+                const long long j = col0 + c;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const long long i = row0 + tid + (long long)r * kThreads;
+                    if (d[r] <= thr && rv[r] && (!diagonal || j > i)) {
+                        unsigned long long pos = atomicAdd(count, 1ull);
+                        if ((long long)pos < cap) {
+                            pairs[2 * pos] = (int)i;
+                            pairs[2 * pos + 1] = (int)j;
+                        }
                     }
                 }
             }
@@ -115,11 +129,17 @@ int launch_hamming_pairs(const unsigned long long* d_hashes, long long n, int ma
     FB_REQUIRE(max_distance >= 0 && max_distance <= 64, "fb_hamming_pairs: max_distance out of range");
     FB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
     if (n < 2) return 0;
-    const long long tiles = (n + kRowTile - 1) / kRowTile;
-    const long long my_tiles = (tiles - part + nparts - 1) / nparts;
+    // small sets: 256-hash tiles so that there are enough tiles for every SM of every part
+    const bool small = n <= (1ll << 16);
+    const long long tile = small ? kThreads : kThreads * 8;
+    const long long T = (n + tile - 1) / tile;
+    const long long U = T * (T + 1) / 2;                         // upper-triangle tiles
+    const long long my_tiles = (U - part + nparts - 1) / nparts;
     if (my_tiles <= 0) return 0;
-    dim3 grid((unsigned)tiles, (unsigned)my_tiles);
-    hamming_pairs_kernel<<<grid, kThreads, 0, stream>>>(d_hashes, n, max_distance, part, nparts, d_pairs, cap, d_count);
+    const long long max_grid = (long long)sm_count() * 64;
+    const unsigned grid = (unsigned)(my_tiles < max_grid ? my_tiles : max_grid);
+    if (small) hamming_pairs_kernel<1><<<grid, kThreads, 0, stream>>>(d_hashes, n, max_distance, part, nparts, T, my_tiles, d_pairs, cap, d_count);
+    else hamming_pairs_kernel<8><<<grid, kThreads, 0, stream>>>(d_hashes, n, max_distance, part, nparts, T, my_tiles, d_pairs, cap, d_count);
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -62,11 +62,12 @@ int launch_im2col_patch14(const float* d_x, int batch, void* d_out, int f16, cud
 int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
                      const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,
                      cudaStream_t stream);   // out_bf16: 0 = fp32, 1 = bf16, 2 = fp16
-int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream);      // mma.sync (legacy path)
 int launch_attention_tc(const void* d_qkv, int batch, void* d_out, int f16, cudaStream_t stream);   // tcgen05
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream);
+int launch_embedding_heads(const float* d_x, int n, const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* tags, int ntags, float* raw, float* sims, cudaStream_t stream);
 void count_launch(int k);
 
 // Optional per-category CUDA-event timing of the library's launches (bench.py roofline): when enabled every
@@ -78,6 +79,7 @@ struct ProfScope {
     ~ProfScope();
     int slot;
     cudaStream_t stream;
+    cudaEvent_t begin, end;
 };
 size_t vit_workspace_bytes(int batch);
 

@@ -25,6 +25,8 @@
 // Generic kernel: any W/H >= 2, any alignment; one thread per pixel, global atomics.
 #include <cuda_fp16.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -484,8 +486,9 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     acc.l2 += (unsigned long long)acc.l2u;
 }
 
-__global__ void smem_base_probe_kernel(unsigned int* out) {
-    if (threadIdx.x == 0) *out = (unsigned int)__cvta_generic_to_shared(fb_smem);
+__device__ unsigned int g_smem_base_probe;
+__global__ void smem_base_probe_kernel() {
+    if (threadIdx.x == 0) g_smem_base_probe = (unsigned int)__cvta_generic_to_shared(fb_smem);
 }
 
 template <bool RGB, bool LUMA>
@@ -498,6 +501,9 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
     unsigned int* const s_next = fb_smem + kOffHdiv + 256;       // next unclaimed unit of the current segment
 
     const int tid = threadIdx.x;
+    // every histogram / table access below uses compile-time offsets from kSmemBase: fail loudly (never silently
+    // wrong) should the dynamic block of THIS launch start anywhere else (the launcher also probes once per device)
+    if ((uint32_t)__cvta_generic_to_shared(fb_smem) != kSmemBase) __trap();
     for (int i = tid; i < kHsSmemWords + 256 * kH256Copies; i += kThreads) smem[i] = 0u;
     if (tid < 256) {
         // fixed-point reciprocals pre-scaled by 2^-12 (exact in fp32: integers below 2^21)
@@ -732,6 +738,36 @@ int tech_rows_per_unit(int n, int H, int W, int sms) {
     return rows;
 }
 
+// The fast kernel addresses shared memory with compile-time offsets from kSmemBase.  Checked once per device (not on
+// the caller's stream: a private stream, no allocation, result cached under a mutex) with the real kernel's dynamic
+// shared-memory size; if the base ever differs the generic kernel is used.  The kernel itself traps on a mismatch.
+static bool smem_base_matches() {
+    constexpr int kMaxDev = 64;
+    static std::mutex mu;
+    static int state[kMaxDev];          // 0 unknown, 1 ok, 2 mismatch
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (state[dev] == 0) {
+        const int smem = (int)(kSmemWords * sizeof(unsigned int));
+        unsigned int h_probe = 0;
+        cudaStream_t s = nullptr;
+        bool ok = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        if (ok) {
+            smem_base_probe_kernel<<<1, 32, smem, s>>>();
+            ok = cudaMemcpyFromSymbolAsync(&h_probe, g_smem_base_probe, sizeof(h_probe), 0, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                 cudaStreamSynchronize(s) == cudaSuccess;
+        }
+        if (s) cudaStreamDestroy(s);
+        state[dev] = (ok && h_probe == kSmemBase) ? 1 : 2;
+        if (state[dev] == 2)
+            fprintf(stderr, "facet_b200: dynamic shared memory starts at 0x%x, not 0x%x: the technical pass uses its "
+                            "generic (slow) kernel\n", h_probe, kSmemBase);
+    }
+    return state[dev] == 1;
+}
+
 int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
                       unsigned int* d_hist256, unsigned int* d_hs_hist, long long* d_sums, int force_generic,
                       uint8_t* d_luma, cudaStream_t stream) {
@@ -760,23 +796,8 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     const bool aligned = (W % kLanePx == 0) && ((reinterpret_cast<uintptr_t>(d_images) & (kAlign - 1)) == 0) &&
                          (image_stride % kAlign == 0) && (W >= kLanePx);
     const int sms = sm_count();
-    // the fast kernel addresses shared memory with compile-time offsets from kSmemBase: check once that the
-    // dynamic block really starts there on this driver
-    static int smem_base_ok = -1;
-    if (smem_base_ok < 0) {
-        unsigned int* d_probe = nullptr;
-        unsigned int h_probe = 0;
-        FB_CUDA_OK(cudaMalloc(&d_probe, sizeof(unsigned int)));
-        smem_base_probe_kernel<<<1, 32, 1024, stream>>>(d_probe);
-        FB_CUDA_OK(cudaMemcpyAsync(&h_probe, d_probe, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-        FB_CUDA_OK(cudaStreamSynchronize(stream));
-        FB_CUDA_OK(cudaFree(d_probe));
-        smem_base_ok = (h_probe == kSmemBase) ? 1 : 0;
-        if (!smem_base_ok)
-            fprintf(stderr, "facet_b200: dynamic shared memory starts at 0x%x, not 0x%x: the technical pass uses its "
-                            "generic (slow) kernel\n", h_probe, kSmemBase);
-    }
-    if (aligned && !force_generic && smem_base_ok) {
+    const bool smem_base_ok = aligned && !force_generic && smem_base_matches();
+    if (smem_base_ok) {
         a.tiles_x = (W + kTileW - 1) / kTileW;
         a.rows_per_unit = tech_rows_per_unit(n, H, W, sms);
         a.units_y = (H + a.rows_per_unit - 1) / a.rows_per_unit;

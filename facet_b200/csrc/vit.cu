@@ -5,7 +5,7 @@
 // (models/tagger.py:99-101) execute through open_clip / PyTorch in the reference:
 //   im2col_patch14_kernel   conv 14x14/14 patch embedding as the A operand of a GEMM
 //   layernorm_kernel        ln_pre (with class-token / positional-embedding assembly), ln_1, ln_2
-//   attention_kernel        softmax(Q K^T / 8) V per (image, head), S = 257, d = 64
+//   (attention lives in csrc/attention_tc.cu)
 //   vit_tail_kernel         ln_post(CLS) @ proj -> features; L2-normalised embedding;
 //                           MLP aesthetic head on the un-normalised features; tag similarities
 // The residual stream stays in fp32; GEMM inputs are bf16 (csrc/gemm.cu).
@@ -128,160 +128,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Attention: one CTA per (image, head); K and V (257 x 64 bf16, zero padded to 272 rows) staged in
-// shared memory with a 16-byte-chunk XOR swizzle; 9 warps, each owning m16 query tiles; flash-style
-// online softmax over key chunks of 64 (+ one chunk of 16).  mma.sync.m16n8k16 bf16 / fp32.
-constexpr int kAttnWarps = 9;
-constexpr int kKeysPad = 272;
-
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-// byte offset of (row, 16-byte chunk) in a [rows][64] bf16 tile with XOR swizzle
-__device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
-template <int NT>   // n-tiles (of 8 keys) in this chunk: 8 or 2
-__device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[4][4], uint32_t ks, uint32_t vs, int key0, int lane,
-                                           float (&o)[8][4], float (&mrow)[2], float (&lrow)[2]) {
-    float s[NT][4];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-    // S = Q K^T
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {            // d in steps of 16
-#pragma unroll
-        for (int np = 0; np < NT / 2; ++np) {   // pairs of n-tiles
-            uint32_t b[4];
-            const int r = key0 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-            const int ch = kk * 2 + ((lane >> 3) & 1);
-            ldmatrix_x4(b, ks + sw_off(r, ch));
-            mma_bf16_16816(s[2 * np], qf[kk], b[0], b[1]);
-            mma_bf16_16816(s[2 * np + 1], qf[kk], b[2], b[3]);
-        }
-    }
-    // mask padded keys, online softmax (scores scaled by 1/8 inside the exponent)
-    const float kScale = 0.125f * 1.4426950408889634f;
-    float mx[2] = {mrow[0], mrow[1]};
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-        const int key = key0 + n * 8 + (lane & 3) * 2;
-        if (key >= kTokens) s[n][0] = s[n][2] = -INFINITY;
-        if (key + 1 >= kTokens) s[n][1] = s[n][3] = -INFINITY;
-        mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
-        mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-    }
-    float corr[2], sum[2] = {0.f, 0.f};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        corr[h] = exp2f((mrow[h] - mx[h]) * kScale);
-        mrow[h] = mx[h];
-    }
-    uint32_t pf[NT / 2][4];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-        const float p0 = exp2f((s[n][0] - mx[0]) * kScale), p1 = exp2f((s[n][1] - mx[0]) * kScale);
-        const float p2 = exp2f((s[n][2] - mx[1]) * kScale), p3 = exp2f((s[n][3] - mx[1]) * kScale);
-        sum[0] += p0 + p1;
-        sum[1] += p2 + p3;
-        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-        pf[n >> 1][(n & 1) * 2] = *reinterpret_cast<uint32_t*>(&lo);
-        pf[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) lrow[h] = lrow[h] * corr[h] + sum[h];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-        o[n][0] *= corr[0]; o[n][1] *= corr[0];
-        o[n][2] *= corr[1]; o[n][3] *= corr[1];
-    }
-    // O += P V
-#pragma unroll
-    for (int kk = 0; kk < NT / 2; ++kk) {        // keys in steps of 16
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {         // pairs of d n-tiles
-            uint32_t b[4];
-            const int r = key0 + kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-            const int ch = np * 2 + (lane >> 4);
-            ldmatrix_x4_trans(b, vs + sw_off(r, ch));
-            mma_bf16_16816(o[2 * np], pf[kk], b[0], b[1]);
-            mma_bf16_16816(o[2 * np + 1], pf[kk], b[2], b[3]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kAttnWarps * 32, 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                    __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(128) uint8_t attn_smem[];
-    uint8_t* ksm = attn_smem;
-    uint8_t* vsm = attn_smem + kKeysPad * 128;
-    const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
-    const __nv_bfloat16* base = qkv + (size_t)b * kTokens * (3 * kWidth) + h * kHeadDim;
-    // stage K and V: 272 rows x 8 chunks of 16 bytes each
-    for (int i = threadIdx.x; i < kKeysPad * 8; i += blockDim.x) {
-        const int r = i >> 3, ch = i & 7;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (r < kTokens) {
-            const __nv_bfloat16* src = base + (size_t)r * (3 * kWidth) + ch * 8;
-            kv = *reinterpret_cast<const uint4*>(src + kWidth);
-            vv = *reinterpret_cast<const uint4*>(src + 2 * kWidth);
-        }
-        *reinterpret_cast<uint4*>(ksm + sw_off(r, ch)) = kv;
-        *reinterpret_cast<uint4*>(vsm + sw_off(r, ch)) = vv;
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ks = (uint32_t)__cvta_generic_to_shared(ksm), vs = (uint32_t)__cvta_generic_to_shared(vsm);
-    const int g = lane >> 2, t = lane & 3;
-    for (int mt = warp; mt < 17; mt += kAttnWarps) {
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
-        uint32_t qf[4][4];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int c = kk * 16 + 2 * t;
-            qf[kk][0] = (r0 < kTokens) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * (3 * kWidth) + c) : 0u;
-            qf[kk][1] = (r1 < kTokens) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * (3 * kWidth) + c) : 0u;
-            qf[kk][2] = (r0 < kTokens) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * (3 * kWidth) + c + 8) : 0u;
-            qf[kk][3] = (r1 < kTokens) ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * (3 * kWidth) + c + 8) : 0u;
-        }
-        float o[8][4];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-        float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) attn_chunk<8>(qf, ks, vs, c * 64, lane, o, mrow, lrow);
-        attn_chunk<2>(qf, ks, vs, 256, lane, o, mrow, lrow);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            lrow[hh] += __shfl_xor_sync(0xffffffffu, lrow[hh], 1);
-            lrow[hh] += __shfl_xor_sync(0xffffffffu, lrow[hh], 2);
-        }
-        const float inv0 = 1.0f / lrow[0], inv1 = 1.0f / lrow[1];
-        __nv_bfloat16* orow0 = out + ((size_t)b * kTokens + r0) * kWidth + h * kHeadDim;
-        __nv_bfloat16* orow1 = out + ((size_t)b * kTokens + r1) * kWidth + h * kHeadDim;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (r0 < kTokens) *reinterpret_cast<__nv_bfloat162*>(orow0 + n * 8 + 2 * t) = __floats2bfloat162_rn(o[n][0] * inv0, o[n][1] * inv0);
-            if (r1 < kTokens) *reinterpret_cast<__nv_bfloat162*>(orow1 + n * 8 + 2 * t) = __floats2bfloat162_rn(o[n][2] * inv1, o[n][3] * inv1);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Tail: one CTA (256 threads) per image.
 //   y = ln_post(x[b, 0, :]);  feat = y @ proj[1024,768]  (fp32, weights bf16-rounded like the GEMMs? no: fp32)
 //   emb = feat / max(||feat||, 1e-12)                      F.normalize, scorer.py:663
@@ -372,6 +218,51 @@ __global__ void __launch_bounds__(768) vit_tail_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Heads on stored embeddings (no tower): the per-image calls of the reference that start from the 3072-byte
+// `clip_embedding` BLOB — `Facet.score_from_embedding` (processing/scorer.py:620-629: the MLP head applied to
+// the vector as stored) and `CLIPTagger.get_tags_from_embedding` (models/tagger.py:99-101: emb @ T^T).
+// One CTA (8 warps) per vector; fp32 throughout, warp per hidden unit / per prompt like the tail kernel.
+__global__ void __launch_bounds__(256) embedding_heads_kernel(const float* __restrict__ x /*[n][768]*/,
+                                                              const float* __restrict__ w1, const float* __restrict__ b1,
+                                                              const float* __restrict__ w2, const float* __restrict__ b2,
+                                                              const float* __restrict__ tags, int ntags,
+                                                              float* __restrict__ raw_out, float* __restrict__ sims_out) {
+    __shared__ float v[768];
+    __shared__ float hid[256];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < 768; k += 256) v[k] = x[(size_t)b * 768 + k];
+    __syncthreads();
+    if (raw_out) {
+        for (int u = warp; u < 256; u += 8) {
+            const float* wr = w1 + (size_t)u * 768;
+            float h = 0.f;
+#pragma unroll 8
+            for (int k = lane; k < 768; k += 32) h = fmaf(__ldg(wr + k), v[k], h);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+            if (lane == 0) hid[u] = fmaxf(h + b1[u], 0.f) * w2[u];
+        }
+    }
+    for (int tg = warp; tg < ntags; tg += 8) {
+        const float* tr = tags + (size_t)tg * 768;
+        float d = 0.f;
+#pragma unroll 8
+        for (int k = lane; k < 768; k += 32) d = fmaf(v[k], __ldg(tr + k), d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) sims_out[(size_t)b * ntags + tg] = d;
+    }
+    __syncthreads();
+    if (raw_out && warp == 0) {
+        float r = 0.f;
+        for (int k = lane; k < 256; k += 32) r += hid[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) raw_out[b] = r + b2[0];
+    }
+}
+
 }  // namespace
 
 int launch_im2col_patch14(const float* d_x, int batch, void* d_out, int f16, cudaStream_t stream) {
@@ -404,26 +295,23 @@ int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* 
     return 0;
 }
 
-int launch_attention(const void* d_qkv, int batch, void* d_out, cudaStream_t stream) {
-    FB_REQUIRE(d_qkv && d_out && batch >= 1, "fb_vit_attention: bad arguments");
-    const int smem = 2 * kKeysPad * 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    attention_kernel<<<batch * kHeads, kAttnWarps * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_qkv),
-                                                                      reinterpret_cast<__nv_bfloat16*>(d_out));
-    FB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream) {
     FB_REQUIRE(d_x && g && be && proj && w1 && b1 && w2 && b2 && feat && emb && raw && batch >= 1, "fb_vit_tail: bad arguments");
     FB_REQUIRE(ntags == 0 || (tags && sims), "fb_vit_tail: tag matrix / output missing");
     vit_tail_kernel<<<batch, 768, 0, stream>>>(d_x, g, be, proj, w1, b1, w2, b2, tags, ntags, feat, emb, raw, sims);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_embedding_heads(const float* d_x, int n, const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* tags, int ntags, float* raw, float* sims, cudaStream_t stream) {
+    FB_REQUIRE(d_x && n >= 1, "fb_embedding_heads: bad arguments");
+    FB_REQUIRE(!raw || (w1 && b1 && w2 && b2), "fb_embedding_heads: head weights missing");
+    FB_REQUIRE(ntags == 0 || (tags && sims), "fb_embedding_heads: tag matrix / output missing");
+    FB_REQUIRE(raw || ntags > 0, "fb_embedding_heads: nothing to compute");
+    embedding_heads_kernel<<<n, 256, 0, stream>>>(d_x, w1, b1, w2, b2, tags, ntags, raw, sims);
     FB_CUDA_OK(cudaGetLastError());
     return 0;
 }

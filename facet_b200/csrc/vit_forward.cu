@@ -51,7 +51,6 @@ int vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void
     const int f16 = w->f16 ? 1 : 0;
     const int gflag = f16 ? FB_GEMM_F16_FLAG : 0;
     const int ln_out = f16 ? 2 : 1;
-    static const bool legacy_attn = getenv("FB_ATTN_LEGACY") != nullptr;   // A/B switch: mma.sync attention
     int rc;
 #define STEP_CAT(cat, call, n)          \
     do {                                \
@@ -74,8 +73,7 @@ int vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void
         STEP_CAT(PROF_LAYERNORM, launch_layernorm(ws.x, kWidth, M, L.ln1_g, L.ln1_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);
         STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.xn, kWidth, L.w_qkv, kWidth, M, 3 * kWidth, kWidth, FB_GEMM_BIAS_BF16 | gflag, L.b_qkv, ws.qkv,
                               3 * kWidth, nullptr, 0, st), 1);
-        if (legacy_attn && !f16) STEP_CAT(PROF_ATTENTION, launch_attention(ws.qkv, batch, ws.attn, st), 1);
-        else STEP_CAT(PROF_ATTENTION, launch_attention_tc(ws.qkv, batch, ws.attn, f16, st), 1);
+        STEP_CAT(PROF_ATTENTION, launch_attention_tc(ws.qkv, batch, ws.attn, f16, st), 1);
         STEP_CAT(PROF_GEMM, launch_gemm_bf16(ws.attn, kWidth, L.w_out, kWidth, M, kWidth, kWidth, FB_GEMM_BIAS_RESIDUAL_F32 | gflag, L.b_out, ws.x,
                               kWidth, ws.x, kWidth, st), 1);
         STEP_CAT(PROF_LAYERNORM, launch_layernorm(ws.x, kWidth, M, L.ln2_g, L.ln2_b, nullptr, nullptr, ws.xn, kWidth, ln_out, st), 1);

@@ -63,10 +63,12 @@ class CLIPTagger:
         return self._dev
 
     def similarities(self, clip_embedding_bytes):
-        """emb[1,768] @ T[n,768]^T on the GPU (float32), as tagger.py:99-101."""
+        """emb[1,768] @ T[n,768]^T on the GPU (float32), as tagger.py:99-101 (fb_embedding_heads, no library GEMV)."""
         import torch
-        emb = torch.from_numpy(bytes_to_embedding(clip_embedding_bytes).copy()).to(self.device)
-        return (emb.unsqueeze(0) @ self._device_matrix().T).squeeze(0).cpu().numpy()
+        from .. import ops
+        emb = torch.from_numpy(bytes_to_embedding(clip_embedding_bytes).copy()).to(self.device).reshape(1, -1)
+        _, sims = ops.embedding_heads(emb, tag_embeddings=self._device_matrix())
+        return sims[0].cpu().numpy()
 
     def get_tags_from_embedding(self, clip_embedding_bytes, threshold=0.25, max_tags=5):
         if self.text_embeddings is None or clip_embedding_bytes is None:

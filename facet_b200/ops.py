@@ -15,6 +15,17 @@ from . import _lib
 from .analyzers._closed_form import TechStats
 
 HS_BINS = 180 * 256
+# Largest pair list a single call materialises (2^28 pairs = 2 GiB of int32 pairs).  A degenerate library (many
+# identical hashes / embeddings) has O(n^2) pairs; the reference merely runs slowly there, this raises a clear
+# error instead of an opaque allocation failure.
+MAX_PAIRS = 1 << 28
+
+
+def _grown_cap(needed: int, what: str) -> int:
+    if needed > MAX_PAIRS:
+        raise RuntimeError(f"{what}: {needed} pairs exceed the {MAX_PAIRS}-pair limit of one call "
+                           "(degenerate input: deduplicate identical hashes first or split the row range)")
+    return int(needed)
 
 
 def _ptr(t) -> C.c_void_p:
@@ -163,7 +174,7 @@ def hamming_pairs(hashes, max_distance: int, part: int = 0, nparts: int = 1, cap
             m = int(count.item())
             if m <= cap:
                 return pairs[:m]
-            cap = m   # truncated: retry once with the exact size
+            cap = _grown_cap(m, 'hamming_pairs')   # truncated: retry once with the exact size
 
 
 def burst_links(hashes: np.ndarray, time_s: np.ndarray, flags: np.ndarray, lo: np.ndarray, thr: int,
@@ -187,7 +198,7 @@ def burst_links(hashes: np.ndarray, time_s: np.ndarray, flags: np.ndarray, lo: n
         m = int(count.item())
         if m <= cap:
             return last[:n].cpu().numpy(), rp[:m].cpu().numpy()
-        cap = m
+        cap = _grown_cap(m, 'burst_links')
 
 
 _PLAN_CACHE: dict = {}
@@ -278,19 +289,35 @@ def vit_layernorm(x, gamma, beta, out_bf16=True, class_emb=None, pos_emb=None, r
     return out
 
 
-def vit_attention(qkv, batch: int, legacy_mma: bool = False):
-    """qkv: CUDA bf16 [batch*257, 3072] -> bf16 [batch*257, 1024] (tcgen05 kernel; legacy_mma selects the
-    mma.sync variant kept for A/B checks)."""
+def vit_attention(qkv, batch: int):
+    """qkv: CUDA bf16 / fp16 [batch*257, 3072] -> same dtype [batch*257, 1024] (tcgen05 kernel)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     out = torch.empty((batch * 257, 1024), dtype=qkv.dtype, device=qkv.device)
-    if qkv.dtype == torch.float16:
-        fn = lib.fb_vit_attention_f16
-    else:
-        fn = lib.fb_vit_attention_mma if legacy_mma else lib.fb_vit_attention
+    fn = lib.fb_vit_attention_f16 if qkv.dtype == torch.float16 else lib.fb_vit_attention
     with torch.cuda.device(qkv.device):
         _lib.check(fn(_ptr(qkv), batch, _ptr(out), _lib.stream_ptr()), "fb_vit_attention")
     return out
+
+
+def embedding_heads(vectors, head=None, tag_embeddings=None):
+    """Heads on stored embeddings (fb_embedding_heads): vectors CUDA float32 [n,768]; head = (w1 [256,768], b1 [256],
+    w2 [256], b2 [1]) CUDA float32 tensors or None; tag_embeddings CUDA float32 [t,768] or None.
+    Returns (raw [n] or None, sims [n,t] or None) as CUDA tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    v = vectors.contiguous()
+    n = int(v.shape[0])
+    raw = torch.empty((n,), dtype=torch.float32, device=v.device) if head is not None else None
+    nt = int(tag_embeddings.shape[0]) if tag_embeddings is not None else 0
+    sims = torch.empty((n, nt), dtype=torch.float32, device=v.device) if nt else None
+    w1, b1, w2, b2 = head if head is not None else (None, None, None, None)
+    with torch.cuda.device(v.device):
+        _lib.check(lib.fb_embedding_heads(_ptr(v), n, _ptr(w1) if head is not None else None, _ptr(b1) if head is not None else None,
+                                          _ptr(w2) if head is not None else None, _ptr(b2) if head is not None else None,
+                                          _ptr(tag_embeddings) if nt else None, nt, _ptr(raw) if raw is not None else None,
+                                          _ptr(sims) if nt else None, _lib.stream_ptr()), "fb_embedding_heads")
+    return raw, sims
 
 
 def balanced_row_blocks(n: int, parts: int):
@@ -325,7 +352,7 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
             nc, m = (int(x) for x in counts.tolist())
             if nc <= cap and m <= cap:
                 return pairs[:m], sims[:m]
-            cap = max(nc, m)
+            cap = _grown_cap(max(nc, m), 'cosine_pairs')
 
 
 def orient(images, exif_orientation: int = 1, swap_rb: bool = False):

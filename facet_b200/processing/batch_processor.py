@@ -20,6 +20,7 @@ Errors follow the reference's convention: a bad item never poisons the batch, it
 from __future__ import annotations
 
 from collections import defaultdict
+from pathlib import Path
 
 import numpy as np
 
@@ -56,7 +57,10 @@ class BatchProcessor:
         results = [None] * len(batch)
         groups = defaultdict(list)
         for i, item in enumerate(batch):
-            img = item.get("img_cv") if isinstance(item, dict) else None
+            if not isinstance(item, dict):          # a loader that returned nothing usable (batch_processor.py:146)
+                results[i] = {"path": None, "error": "Failed to load image"}
+                continue
+            img = item.get("img_cv")
             if "error" in item:
                 results[i] = {"path": item.get("path"), "error": item["error"]}
             elif not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
@@ -76,8 +80,19 @@ class BatchProcessor:
                         res = self.finish(batch[i], res)
                     results[i] = res
             except Exception as exc:  # a CUDA failure is loud, but it is reported per item like the reference does
+                if len(idxs) == 1:
+                    results[idxs[0]] = {"path": batch[idxs[0]].get("path"), "error": str(exc)}
+                    continue
+                # the reference isolates failures per image (batch_processor.py:190-360 wraps each image): retry the
+                # group one frame at a time so a single bad item does not fail its whole shape group
                 for i in idxs:
-                    results[i] = {"path": batch[i].get("path"), "error": str(exc)}
+                    try:
+                        one = self.scorer.score_images(batch[i]["img_cv"][None], mono_threshold=self.mono_threshold,
+                                                       tag_threshold=thr, max_tags=max_tags)
+                        res = self._finish_group([batch[i]], one)[0]
+                        results[i] = self.finish(batch[i], res) if self.finish is not None else res
+                    except Exception as exc_i:
+                        results[i] = {"path": batch[i].get("path"), "error": str(exc_i)}
         self.metrics["batches"] += 1
         self.metrics["images_processed"] += sum(1 for r in results if r and "error" not in r)
         self.metrics["images_failed"] += sum(1 for r in results if r and "error" in r)
@@ -127,9 +142,11 @@ class BatchProcessor:
                 items, scored, aggregates, categories, extras):
             for k in ("aesthetic_unrounded", "tech_sharpness_unrounded", "color_score_unrounded", "exposure_score_unrounded"):
                 res.pop(k)
+            # batch_processor.py:298-300: the row key is the resolved absolute path, the filename its last component
             path = item.get("path")
+            resolved = Path(path).resolve() if path is not None else None
             res.update({
-                "path": path, "filename": str(path if path is not None else "").rsplit("/", 1)[-1],
+                "path": str(resolved) if resolved is not None else None, "filename": resolved.name if resolved is not None else "",
                 "category": cat, "aggregate": None if agg is None else round(float(agg), 2),
                 "face_count": face_res["face_count"], "face_quality": face_res["face_quality"],
                 "eye_sharpness": face_res["eye_sharpness"], "face_sharpness": face_res["face_sharpness"],

@@ -41,6 +41,8 @@ class Facet:
         self.model = ClipVitL14(state_dict, tag_embeddings=text_embeddings, device=self.device)
         self._head = {k: state_dict[k].detach().to(self.device, torch.float32)
                       for k in ("aesthetic_head.0.weight", "aesthetic_head.0.bias", "aesthetic_head.2.weight", "aesthetic_head.2.bias")}
+        self._head_tuple = (self._head["aesthetic_head.0.weight"].contiguous(), self._head["aesthetic_head.0.bias"].contiguous(),
+                            self._head["aesthetic_head.2.weight"].reshape(-1).contiguous(), self._head["aesthetic_head.2.bias"].contiguous())
 
     # -- scorer.preprocess: PIL RGB image -> float32 [3,224,224] (the transform open_clip returns) ----------
     def preprocess(self, pil_img):
@@ -78,9 +80,8 @@ class Facet:
         """scorer.py:620-629: the head applied to a stored (normalised) embedding."""
         import torch
         f = torch.from_numpy(np.frombuffer(embedding_bytes, dtype=np.float32).copy()).to(self.device).unsqueeze(0)
-        h = torch.relu(torch.nn.functional.linear(f, self._head["aesthetic_head.0.weight"], self._head["aesthetic_head.0.bias"]))
-        raw = torch.nn.functional.linear(h, self._head["aesthetic_head.2.weight"], self._head["aesthetic_head.2.bias"])
-        return _aesthetic_from_raw(float(raw.flatten()[0]))
+        raw, _ = ops.embedding_heads(f, head=self._head_tuple)
+        return _aesthetic_from_raw(float(raw.cpu()[0]))
 
     # -- scorer.py:726-950 ---------------------------------------------------------------------------------
     def calculate_aggregate_logic(self, m, config=None):

@@ -132,3 +132,67 @@ def synth_embeddings(n: int, dim: int = 768, seed: int = 11, cluster_fraction: f
             v = e[s] + jitter * sc * rng.standard_normal(dim).astype(np.float32)
             e[d] = v / np.linalg.norm(v)
     return np.ascontiguousarray(e)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Integer-only frames (bit-identical on every host: no floating point in the generator) for the
+# full-size (24 MP) parity goldens, and the extremal frames that reach the stated maxima of the
+# technical kernel's exactness arguments (|Laplacian| = 1020, |Immerkaer response| = 4080 per pixel).
+# ----------------------------------------------------------------------------------------------------
+EXTREMAL_KINDS = ("checker", "black", "white", "red", "green", "blue", "vstripes", "hstripes", "checker2", "halfplane")
+
+
+def synth_frame_int(index: int, height: int, width: int, seed: int = 5000) -> np.ndarray:
+    """Deterministic ``[H,W,3]`` uint8 BGR frame built from integer arithmetic only: per-channel planar
+    gradients, a coarse block pattern, filled rectangles and uniform integer noise."""
+    rng = np.random.default_rng(seed + index)
+    h, w = int(height), int(width)
+    yy = np.arange(h, dtype=np.int64)[:, None]
+    xx = np.arange(w, dtype=np.int64)[None, :]
+    out = np.empty((h, w, 3), np.uint8)
+    amp = int(rng.integers(2, 24))
+    blocks = rng.integers(0, 64, size=(h // 64 + 1, w // 64 + 1, 3), dtype=np.int64)
+    for c in range(3):
+        a, b, o = (int(v) for v in rng.integers(0, 256, size=3))
+        plane = (o + (a * xx) // max(w, 1) + (b * yy) // max(h, 1)) % 256
+        plane = plane + blocks[:, :, c].repeat(64, axis=0)[:h].repeat(64, axis=1)[:, :w]
+        plane = plane + rng.integers(-amp, amp + 1, size=(h, w), dtype=np.int64)
+        out[:, :, c] = np.clip(plane, 0, 255).astype(np.uint8)
+    for _ in range(int(rng.integers(3, 9))):
+        y0, x0 = int(rng.integers(0, h)), int(rng.integers(0, w))
+        y1 = min(h, y0 + int(rng.integers(1, max(2, h // 3))))
+        x1 = min(w, x0 + int(rng.integers(1, max(2, w // 3))))
+        out[y0:y1, x0:x1, :] = rng.integers(0, 256, size=3, dtype=np.int64).astype(np.uint8)
+    return np.ascontiguousarray(out)
+
+
+def extremal_frame(kind: str, height: int, width: int) -> np.ndarray:
+    """Frames that sit on the extremes of the per-pixel responses (BGR uint8)."""
+    h, w = int(height), int(width)
+    yy = np.arange(h)[:, None]
+    xx = np.arange(w)[None, :]
+    out = np.zeros((h, w, 3), np.uint8)
+    if kind == "checker":          # 0 / 255 at one-pixel pitch: |L| = 1020 and |N| = 4080 in the interior
+        out[:] = (((yy + xx) & 1) * 255).astype(np.uint8)[:, :, None]
+    elif kind == "checker2":       # two-pixel pitch, saturated colours alternating with their complements
+        m = (((yy >> 1) + (xx >> 1)) & 1).astype(bool)
+        out[:] = np.where(m[:, :, None], np.array([255, 0, 255], np.uint8), np.array([0, 255, 0], np.uint8))
+    elif kind == "black":
+        pass
+    elif kind == "white":
+        out[:] = 255
+    elif kind == "blue":
+        out[:, :, 0] = 255
+    elif kind == "green":
+        out[:, :, 1] = 255
+    elif kind == "red":
+        out[:, :, 2] = 255
+    elif kind == "vstripes":       # one-pixel vertical stripes
+        out[:] = ((xx & 1) * 255).astype(np.uint8)[:, :, None] * np.ones((h, 1, 1), np.uint8)
+    elif kind == "hstripes":
+        out[:] = ((yy & 1) * 255).astype(np.uint8)[:, :, None] * np.ones((1, w, 1), np.uint8)
+    elif kind == "halfplane":      # silhouette-like: left half black, right half white, one hard edge
+        out[:, w // 2:, :] = 255
+    else:
+        raise ValueError(f"unknown extremal frame kind {kind!r}")
+    return np.ascontiguousarray(out)

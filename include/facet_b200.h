@@ -170,13 +170,13 @@ int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_st
  * pairwise predicate of processing/scorer.py:1943-1968.
  *
  * fb_hamming_pairs: all pairs (i, j), i < j, i in this part's rows, with
- * popcount(h[i]^h[j]) <= max_distance.  Rows are dealt to parts in tiles of
- * FB_HAMMING_ROW_TILE (tile t belongs to part t % nparts) so a triangular problem balances
- * across GPUs.  d_pairs [cap][2] int32 receives the pairs in no particular order; *d_count
- * (uint64, device) receives how many pairs exist — if it exceeds cap the list is truncated
- * and the caller retries with a larger buffer.
+ * popcount(h[i]^h[j]) <= max_distance.  The upper-triangle tiles of the pair matrix are dealt to the
+ * parts round-robin (tile t of the row-major enumeration belongs to part t % nparts; tiles are 256 x 256
+ * hashes up to n = 65536 and 2048 x 2048 above), so a triangular problem balances across GPUs to within
+ * one tile and small sets still spread over every part.  d_pairs [cap][2] int32 receives the pairs in
+ * no particular order; *d_count (uint64, device) receives how many pairs exist — if it exceeds cap the
+ * list is truncated and the caller retries with a larger buffer.
  */
-#define FB_HAMMING_ROW_TILE 2048
 int fb_hamming_pairs(const uint64_t* d_hashes, int64_t n, int max_distance, int part, int nparts,
                      int32_t* d_pairs, int64_t cap, uint64_t* d_count, void* stream);
 
@@ -267,7 +267,15 @@ int fb_vit_layernorm(const float* d_in, int64_t ld_in, int rows, const float* ga
                      int out_bf16 /* 0 fp32, 1 bf16, 2 fp16 */, void* stream);
 int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);      /* tcgen05 */
 int fb_vit_attention_f16(const void* d_qkv_f16, int batch, void* d_out_f16, void* stream);     /* tcgen05, fp16 operands */
-int fb_vit_attention_mma(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream);  /* mma.sync variant, kept for A/B checks */
+
+/* Heads on stored embeddings (no tower) — replaces the two per-image calls of the reference that start from the
+ * 3072-byte `clip_embedding` BLOB: `Facet.score_from_embedding` (processing/scorer.py:620-629, the MLP head on the
+ * vector as stored) and `CLIPTagger.get_tags_from_embedding`'s product (models/tagger.py:99-101, emb @ T^T).
+ * d_vectors [n][768] float32.  d_raw [n] (NULL to skip the head; head_* as in fb_vit_weights) and
+ * d_tag_sims [n][n_tags] (n_tags = 0 to skip). */
+int fb_embedding_heads(const float* d_vectors, int n, const float* head_w1, const float* head_b1, const float* head_w2,
+                       const float* head_b2, const float* d_tag_emb, int n_tags, float* d_raw, float* d_tag_sims,
+                       void* stream);
 
 #ifdef __cplusplus
 }

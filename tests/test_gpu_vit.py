@@ -53,24 +53,29 @@ def test_layernorm_and_assembly():
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", ["tcgen05-bf16", "tcgen05-fp16", "mma-bf16"])
+@pytest.mark.parametrize("variant", ["tcgen05-bf16", "tcgen05-fp16"])
 def test_attention_vs_torch(variant):
     import torch
     from facet_b200 import ops
     bsz = 3
     qkv = _rand_bf16((bsz * 257, 3072), 5, scale=1.5, dtype=torch.float16 if variant.endswith("fp16") else None)
-    got = ops.vit_attention(qkv, bsz, legacy_mma=variant.startswith("mma")).float().reshape(bsz, 257, 16, 64)
+    got = ops.vit_attention(qkv, bsz).float().reshape(bsz, 257, 16, 64)
     q, k, v = qkv.float().reshape(bsz, 257, 3, 16, 64).unbind(2)
     att = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", q, k) * 0.125, dim=-1)
     ref = torch.einsum("bhqk,bkhd->bqhd", att, v)
     torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("dt,aest_tol", [("fp16", 0.01), ("bf16", 0.03)])
+@pytest.mark.parametrize("dt,aest_tol", [
+    ("fp16", 0.01),
+    # bf16 operands: cosine 0.999999 but 0.004 mean / 0.013 max aesthetic error on this random-init head (measured,
+    # DESIGN.md §7) — outside the north_star's 0.01, so the bound is NOT loosened and the case is an expected failure.
+    # The default (and everything the bench measures) is fp16, the precision the reference itself runs on CUDA
+    # (`self.model.half()`, processing/scorer.py:515).
+    pytest.param("bf16", 0.01, marks=pytest.mark.xfail(reason="bf16 activations: aesthetic max error 0.013 > 0.01", strict=False)),
+])
 def test_vit_tower_vs_fp32_oracle(dt, aest_tol):
-    """north_star tolerances: cosine >= 0.999 and aesthetic within 0.01 — met by the default fp16 mode (the
-    reference's own CUDA precision).  bf16 keeps the cosine bound; its 8-bit mantissa leaves ~0.004 mean /
-    ~0.013 max aesthetic noise on this random-init head, hence the looser bound for that variant."""
+    """north_star tolerances: cosine >= 0.999 and aesthetic within 0.01 of the fp32 oracle."""
     import torch
     from facet_b200.models.clip_vit import ClipVitL14, random_state_dict
     from oracle import vit_torch
@@ -89,3 +94,19 @@ def test_vit_tower_vs_fp32_oracle(dt, aest_tol):
     assert float((out["tag_sims"] - ref["tag_sims"]).abs().max()) <= 5e-3
     nrm = out["embedding"].norm(dim=-1)
     torch.testing.assert_close(nrm, torch.ones_like(nrm), rtol=1e-5, atol=1e-5)
+
+
+def test_embedding_heads_match_torch():
+    """fb_embedding_heads (score_from_embedding / tagger similarities on stored embeddings) vs plain fp32 PyTorch."""
+    import torch
+    from facet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    v = torch.nn.functional.normalize(torch.randn(5, 768, device="cuda", generator=g), dim=-1)
+    w1, b1 = torch.randn(256, 768, device="cuda", generator=g) * 768 ** -0.5, torch.randn(256, device="cuda", generator=g) * 0.02
+    w2, b2 = torch.randn(256, device="cuda", generator=g) * 256 ** -0.5, torch.randn(1, device="cuda", generator=g) * 0.02
+    tags = torch.nn.functional.normalize(torch.randn(240, 768, device="cuda", generator=g), dim=-1)
+    raw, sims = ops.embedding_heads(v, head=(w1, b1, w2, b2), tag_embeddings=tags)
+    ref_raw = torch.relu(v @ w1.T + b1) @ w2 + b2
+    torch.testing.assert_close(raw, ref_raw, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(sims, v @ tags.T, rtol=1e-5, atol=1e-5)
+    assert ops.embedding_heads(v, tag_embeddings=tags)[0] is None and ops.embedding_heads(v, head=(w1, b1, w2, b2))[1] is None
