@@ -164,6 +164,199 @@ class BatchProcessor:
             out.append(res)
         return out
 
+    # -- overlapped path ---------------------------------------------------------------------------------------
+    def process_items_streamed(self, items, chunk=16, vit_batch=64, rgb_order=False):
+        """Same results as `process_items` (one dict per item, input order), produced by an overlapped pipeline instead
+        of one blocking pass per batch — the role of the reference's loader threads / GPU thread / result queue
+        (batch_processor.py:123-167, 362-455):
+
+          copy stream     each item's frame goes host -> device (async when the array is in pinned memory) into one of two
+                          `chunk`-frame staging buffers while the previous chunk is being processed
+          compute stream  technical pass + pHash + CLIP preprocess per chunk; the ViT tower + heads once `vit_batch`
+                          frames have been preprocessed (frames of different shapes share a ViT launch)
+          D2H stream      ONE packed record per image (histogram, sums, hash, embedding, aesthetic, tag similarities;
+                          about 5 KB) into pinned host memory per ViT batch
+          worker thread   closed-form metric dicts, tag selection, aggregate + category, the result columns
+
+        `self.metrics` gains h2d_bytes / d2h_bytes of the call."""
+        import queue
+        import threading
+        from .. import _lib
+        torch = _lib.require_cuda()
+        scorer = self.scorer
+        dev = scorer.device
+        chunk, vit_batch = max(1, int(chunk)), max(1, int(vit_batch))
+        thr, max_tags = self._tag_params()
+        n_tags = scorer.model.n_tags
+        rec_bytes = 1024 + 32 + 32 + 8 + 8 + 3072 + 4 * n_tags
+        st = self._stream_state(torch, dev, vit_batch + chunk, rec_bytes)
+        compute = torch.cuda.current_stream(dev)
+        copy_s, d2h_s = st["copy"], st["d2h"]
+        results = {}
+        self.metrics.setdefault("h2d_bytes", 0)
+        self.metrics.setdefault("d2h_bytes", 0)
+        jobs = queue.Queue()
+
+        def post(job):
+            done, pack, metas = job
+            try:
+                done.synchronize()
+                a = pack[:len(metas)].numpy()
+                hist = a[:, :1024].view(np.uint32).astype(np.int64)
+                sums = a[:, 1024:1056].view(np.int64).copy()
+                der = a[:, 1056:1088].view(np.float64).copy()
+                hashes = a[:, 1088:1096].view(np.uint64).reshape(-1).copy()
+                raw = a[:, 1096:1100].view(np.float32).reshape(-1).copy()
+                emb = a[:, 1104:1104 + 3072].view(np.float32).copy()
+                sims = a[:, 1104 + 3072:].view(np.float32).copy() if n_tags else None
+            finally:
+                st["free_packs"].put(pack)
+            by_shape = defaultdict(list)
+            for k, (pos, item, h, w) in enumerate(metas):
+                by_shape[(h, w)].append(k)
+            for (h, w), ks in by_shape.items():
+                sel = np.asarray(ks)
+                try:
+                    scored = scorer.results_from_host(h, w, hist[sel], sums[sel], der[sel], raw[sel], emb[sel],
+                                                      sims[sel] if sims is not None else None,
+                                                      ["%016x" % int(v) for v in hashes[sel]], mono_threshold=self.mono_threshold,
+                                                      tag_threshold=thr, max_tags=max_tags)
+                    scored = self._finish_group([metas[k][1] for k in ks], scored)
+                    for k, res in zip(ks, scored):
+                        results[metas[k][0]] = self.finish(metas[k][1], res) if self.finish is not None else res
+                except Exception as exc:
+                    for k in ks:
+                        results[metas[k][0]] = {"path": metas[k][1].get("path"), "error": str(exc)}
+
+        def worker():
+            while True:
+                job = jobs.get()
+                if job is None:
+                    return
+                post(job)
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+
+        cur = {"shape": None, "slot": 0, "metas": [], "bufs": None}
+        acc = {"px": [], "metas": []}         # preprocessed chunks waiting for the ViT launch
+
+        def flush_vit():
+            if not acc["metas"]:
+                return
+            metas, pxs = acc["metas"], acc["px"]
+            acc["metas"], acc["px"] = [], []
+            try:
+                cat = (lambda key: torch.cat([p[key] for p in pxs]) if len(pxs) > 1 else pxs[0][key])
+                vit = scorer.model.encode(cat("clip_in"))
+                m = len(metas)
+                parts = [cat("hist256").view(torch.uint8).reshape(m, 1024), cat("sums").view(torch.uint8).reshape(m, 32),
+                         cat("derived").view(torch.uint8).reshape(m, 32), cat("phash").reshape(m, 1).view(torch.uint8),
+                         vit["aesthetic_raw"].reshape(m, 1).view(torch.uint8), torch.zeros((m, 4), dtype=torch.uint8, device=dev),
+                         vit["embedding"].view(torch.uint8).reshape(m, 3072)]
+                if n_tags:
+                    parts.append(vit["tag_sims"].contiguous().view(torch.uint8).reshape(m, 4 * n_tags))
+                rec = torch.cat(parts, dim=1)
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                pack = st["free_packs"].get()             # back-pressure: at most len(packs) ViT batches in flight
+                done = torch.cuda.Event()
+                with torch.cuda.stream(d2h_s):
+                    d2h_s.wait_event(ready)
+                    pack[:m].copy_(rec, non_blocking=True)
+                    done.record(d2h_s)
+                rec.record_stream(d2h_s)
+                self.metrics["d2h_bytes"] += m * rec_bytes
+                jobs.put((done, pack, metas))
+            except Exception as exc:
+                for pos, item, _h, _w in metas:
+                    results[pos] = {"path": item.get("path"), "error": str(exc)}
+
+        def flush_chunk():
+            metas = cur["metas"]
+            if not metas:
+                return
+            slot, bufs = cur["slot"], cur["bufs"]
+            cur["metas"], cur["shape"] = [], None
+            try:
+                bufs["ready"][slot].record(copy_s)
+                compute.wait_event(bufs["ready"][slot])
+                px = scorer.pixel_passes_device(bufs["frames"][slot][:len(metas)], rgb_order=rgb_order)
+                bufs["free"][slot].record(compute)
+                bufs["used"][slot] = True
+                acc["px"].append(px)
+                acc["metas"].extend(metas)
+            except Exception as exc:
+                for pos, item, _h, _w in metas:
+                    results[pos] = {"path": item.get("path"), "error": str(exc)}
+            if len(acc["metas"]) >= vit_batch:
+                flush_vit()
+
+        n_items = 0
+        for pos, item in enumerate(items):
+            n_items = pos + 1
+            if not isinstance(item, dict):
+                results[pos] = {"path": None, "error": "Failed to load image"}
+                continue
+            img = item.get("img_cv")
+            if "error" in item:
+                results[pos] = {"path": item.get("path"), "error": item["error"]}
+                continue
+            if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+                results[pos] = {"path": item.get("path"), "error": "Failed to load image"}
+                continue
+            h, w = int(img.shape[0]), int(img.shape[1])
+            if h < 2 or w < 2:
+                results[pos] = {"path": item.get("path"), "error": "image smaller than 2x2"}
+                continue
+            if cur["metas"] and (cur["shape"] != (h, w) or len(cur["metas"]) == chunk):
+                flush_chunk()
+            if not cur["metas"]:
+                bufs = self._chunk_buffers(torch, dev, h, w, chunk)
+                slot = bufs["next"]
+                bufs["next"] = slot ^ 1
+                cur.update(shape=(h, w), slot=slot, bufs=bufs)
+                if bufs["used"][slot]:
+                    copy_s.wait_event(bufs["free"][slot])         # the compute stream is done with this staging buffer
+            k = len(cur["metas"])
+            with torch.cuda.stream(copy_s):
+                cur["bufs"]["frames"][cur["slot"]][k].copy_(torch.from_numpy(np.ascontiguousarray(img)), non_blocking=True)
+            self.metrics["h2d_bytes"] += h * w * 3
+            cur["metas"].append((pos, item, h, w))
+        flush_chunk()
+        flush_vit()
+        jobs.put(None)
+        th.join()
+        self.metrics["batches"] += 1
+        out = [results[i] for i in range(n_items)]
+        self.metrics["images_processed"] += sum(1 for r in out if "error" not in r)
+        self.metrics["images_failed"] += sum(1 for r in out if "error" in r)
+        return out
+
+    def _stream_state(self, torch, dev, max_batch, rec_bytes):
+        import queue
+        st = getattr(self, "_stream", None)
+        if st is None or st["rec_bytes"] != rec_bytes or st["max_batch"] < max_batch:
+            st = {"copy": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "rec_bytes": rec_bytes,
+                  "max_batch": max_batch, "free_packs": queue.Queue(), "chunks": {}}
+            for _ in range(3):
+                st["free_packs"].put(torch.empty((max_batch, rec_bytes), dtype=torch.uint8, pin_memory=True))
+            self._stream = st
+        return st
+
+    def _chunk_buffers(self, torch, dev, h, w, chunk):
+        chunks = self._stream["chunks"]
+        key = (h, w, chunk)
+        if key not in chunks:
+            if len(chunks) >= 4:                       # bound the staging memory when many frame shapes go by
+                torch.cuda.current_stream(dev).synchronize()
+                self._stream["copy"].synchronize()
+                chunks.clear()
+            chunks[key] = {"frames": [torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)],
+                           "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                           "used": [False, False], "next": 0}
+        return chunks[key]
+
     def process_items(self, items):
         """Stream items through `_process_batch` in chunks of batch_size; yields results in order."""
         chunk = []

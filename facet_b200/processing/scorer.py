@@ -97,9 +97,9 @@ class Facet:
         return (cfg._scoring() if hasattr(cfg, "_scoring") else AggregateScorer(cfg)).category_of(m)
 
     # -- batched device-resident entry -------------------------------------------------------------------
-    def score_images_device(self, images, rgb_order=False, with_phash=True):
-        """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;
-        returns device tensors (nothing is copied to the host)."""
+    def pixel_passes_device(self, images, rgb_order=False, with_phash=True):
+        """The per-frame pixel work for a same-shaped CUDA uint8 batch [n,H,W,3]: technical pass (+ luma plane), perceptual
+        hash, CLIP preprocess.  Returns device tensors {hist256, sums, derived, phash, clip_in}; nothing is synchronised."""
         n, h, w, _ = images.shape
         luma = None
         if with_phash and ops.phash_uses_luma_plane(h, w):
@@ -109,23 +109,22 @@ class Facet:
         hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order, luma_out=luma)
         hashes = ops.phash(images, rgb_order=rgb_order, device_only=True, luma=luma) if with_phash else None
         clip_in = ops.clip_preprocess(images, mean=self.mean, std=self.std, rgb_order=rgb_order)
-        vit = self.model.encode(clip_in)
-        return {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, **vit}
+        return {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, "clip_in": clip_in}
 
-    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True):
-        """Full per-image pass for a same-shaped batch -> list of result dicts with the reference's
-        metric keys (processing/batch_processor.py:298-355, the analyzer-derived subset)."""
-        t = ops.to_device_u8(images)
-        n, h, w, _ = t.shape
-        dev = self.score_images_device(t, rgb_order=rgb_order, with_phash=with_phash)
-        hashes = (["%016x" % int(v) for v in dev["phash"].cpu().numpy().view(np.uint64)]   # batch_processor.py:216
-                  if with_phash else [None] * n)
-        hist = dev["hist256"].cpu().numpy().view(np.uint32).astype(np.int64)
-        sums = dev["sums"].cpu().numpy()
-        der = dev["derived"].cpu().numpy()
-        raw = dev["aesthetic_raw"].cpu().numpy()
-        emb = dev["embedding"].cpu().numpy()
-        sims = dev["tag_sims"].cpu().numpy() if dev["tag_sims"] is not None else None
+    def score_images_device(self, images, rgb_order=False, with_phash=True):
+        """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;
+        returns device tensors (nothing is copied to the host)."""
+        px = self.pixel_passes_device(images, rgb_order=rgb_order, with_phash=with_phash)
+        vit = self.model.encode(px.pop("clip_in"))
+        return {**px, **vit}
+
+    def results_from_host(self, h, w, hist, sums, der, raw, emb, sims, hashes, mono_threshold=0.10, tag_threshold=0.22,
+                          max_tags=5):
+        """Host half of the pass: the small per-image device results (as host arrays: hist [n,256] int64, sums [n,4] int64,
+        derived [n,4] float64, aesthetic_raw [n], embedding [n,768] float32, tag_sims [n,T] or None, hashes = list of hex
+        strings or Nones) -> result dicts with the reference's metric keys (processing/batch_processor.py:298-355, the
+        analyzer-derived subset)."""
+        n = len(raw)
         metrics = cf.all_metrics_batch(h, w, hist, sums[:, 0], sums[:, 1], sums[:, 2], der[:, 0], der[:, 1],
                                        mono_threshold=mono_threshold)      # the 7 analyzer dicts per image, one pass
         results = []
@@ -163,3 +162,19 @@ class Facet:
                 "tags": tags, "quality_score": None, "scoring_model": "clip-mlp", "phash": hashes[i],
             })
         return results
+
+    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True):
+        """Full per-image pass for a same-shaped batch -> list of result dicts (see results_from_host)."""
+        t = ops.to_device_u8(images)
+        n, h, w, _ = t.shape
+        dev = self.score_images_device(t, rgb_order=rgb_order, with_phash=with_phash)
+        hashes = (["%016x" % int(v) for v in dev["phash"].cpu().numpy().view(np.uint64)]   # batch_processor.py:216
+                  if with_phash else [None] * n)
+        hist = dev["hist256"].cpu().numpy().view(np.uint32).astype(np.int64)
+        sums = dev["sums"].cpu().numpy()
+        der = dev["derived"].cpu().numpy()
+        raw = dev["aesthetic_raw"].cpu().numpy()
+        emb = dev["embedding"].cpu().numpy()
+        sims = dev["tag_sims"].cpu().numpy() if dev["tag_sims"] is not None else None
+        return self.results_from_host(h, w, hist, sums, der, raw, emb, sims, hashes, mono_threshold=mono_threshold,
+                                      tag_threshold=tag_threshold, max_tags=max_tags)

@@ -147,3 +147,35 @@ def test_batch_processor_with_config_fills_aggregate_and_category(tmp_path):
         assert 0.0 <= r["aggregate"] <= 10.0
     assert res[1]["category"] in ("portrait", "portrait_bw", "silhouette", "human_others")
     assert res[0]["category"] in ("default", "monochrome", "night")
+
+
+def test_batch_processor_streamed_path_equals_the_blocking_one(scorer):
+    """`process_items_streamed` (pinned staging, copy / compute / D2H streams, one packed record per image, host
+    worker thread) returns exactly the dicts of `process_items`: mixed shapes, error items, chunks and ViT batches
+    that do not divide the item count, pinned and pageable frames."""
+    import torch
+    from facet_b200.processing.batch_processor import BatchProcessor
+    sc, tags, names = scorer
+    shapes = [(256, 384)] * 5 + [(200, 320)] * 3 + [(256, 384)] * 2 + [(97, 131)]
+    pinned = torch.empty((len(shapes), 256, 384, 3), dtype=torch.uint8, pin_memory=True)
+    items = []
+    for i, (h, w) in enumerate(shapes):
+        img = synth_image_bgr(60 + i, h, w)
+        if (h, w) == (256, 384) and i % 2 == 0:          # every other frame lives in pinned host memory
+            view = pinned[i].numpy()
+            view[:] = img
+            img = view
+        items.append({"path": f"/x/s{i}.jpg", "img_cv": img})
+    items.insert(4, {"path": "/x/broken.jpg", "error": "Failed to load image"})
+    items.append({"path": "/x/none.jpg", "img_cv": None})
+    items.append("not a dict")
+    want = list(BatchProcessor(sc, batch_size=16).process_items(items))
+    bp = BatchProcessor(sc, batch_size=16)
+    for chunk, vb in ((4, 6), (16, 64), (1, 1)):
+        got = bp.process_items_streamed(items, chunk=chunk, vit_batch=vb)
+        assert len(got) == len(want)
+        for g, w_ in zip(got, want):
+            assert g.keys() == w_.keys(), (g.keys() ^ w_.keys())
+            for k in w_:
+                assert g[k] == w_[k], (chunk, vb, w_.get("path"), k)
+    assert bp.metrics["h2d_bytes"] == 3 * sum(h * w * 3 for h, w in shapes) and bp.metrics["d2h_bytes"] > 0

@@ -28,11 +28,12 @@ def _frame(rec):
 
 @pytest.mark.parametrize("rec", CASES, ids=[f'{c["kind"]}{c["index"]}' for c in CASES])
 def test_24mp_frame_matches_reference_golden(rec):
+    from facet_b200 import ops
     from facet_b200.analyzers import ImageCache, TechnicalAnalyzer as TA
     img = _frame(rec)
     assert hashlib.sha256(img.tobytes()).hexdigest() == rec["frame_sha256"], "frame generator is not reproducible on this host"
-    cache = ImageCache(img)
-    st = cache.stats
+    st = ops.tech_stats(img, want_hs=True)[0]
+    cache = ImageCache(img, stats=st)
     assert st.hist256.tolist() == rec["hist256"]
     assert (st.sum_lap, st.sum_lap_sq, st.sum_abs_noise) == (rec["sum_lap"], rec["sum_lap_sq"], rec["sum_abs_noise"])
     hs = np.ascontiguousarray(st.hs_hist).astype("<u4")
