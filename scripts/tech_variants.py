@@ -30,6 +30,17 @@ for kind in ("noise", "photo"):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 3)
     res[kind] = round(n * 72e6 / (best * 1e-3) / 1e9, 1)
+    luma = torch.empty(fr.shape[:3], dtype=torch.uint8, device=fr.device)
+    best = 1e9
+    for _ in range(3):
+        e0.record()
+        for _ in range(3):
+            ops.tech_stats_raw(fr, luma_out=luma)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 3)
+    res[kind + "_luma"] = round(n * 72e6 / (best * 1e-3) / 1e9, 1)
+    del luma
     if check:
         a = ops.tech_stats_raw(fr[:2])
         b = ops.tech_stats_raw(fr[:2], force_generic=True)
