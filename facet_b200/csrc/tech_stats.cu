@@ -48,10 +48,6 @@ constexpr int kLaneWords = 3 * kLanePx / 4;
 constexpr int kPairs = kLanePx / 2;
 constexpr int kGroups = kLanePx / 4;
 constexpr int kTileW = 32 * kLanePx;   // pixels per warp row (256 at 8 px per lane)
-#ifndef FB_TECH_L2_PREFETCH
-#define FB_TECH_L2_PREFETCH 0
-#endif
-constexpr int kL2PrefetchRows = FB_TECH_L2_PREFETCH;   // rows ahead of the register prefetch that are requested into L2 (0 = off)
 constexpr int kH256Copies = 32;        // one luminance-histogram column per lane
 constexpr int kHsStride = 257;          // shared-memory row stride of the H-S histogram: bank = (h + s) mod 32, so
                                        // pixels of similar saturation and different hue do not collide
@@ -172,9 +168,6 @@ struct LaneCtx {
     int halo_delta;       // byte distance from the lane's first pixel to the aligned word with the halo pixel
     uint8_t* luma_lane;   // LUMA: address of (row 0, xl) in the luma plane
     int W;
-    int pf_delta;         // L2 prefetch: byte distance from the lane's span in the row being loaded to the 128-byte line
-                          // this lane requests kL2PrefetchRows rows further down (lanes 0..6 cover the warp's 768 bytes)
-    bool pf_lane;
 };
 
 template <bool NEED_HALO_CHECK = true>
@@ -297,7 +290,7 @@ enum RowMode { ROW_FIRST = 0, ROW_SECOND = 1, ROW_STEADY = 2, ROW_LAST = 3 };
 //       LAST   = halo row below the unit: stencil of the last owned row, vertical sum picks up -(g_p - g_c)
 template <bool RGB, bool FULL, bool LUMA, int MODE>
 __device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const uint8_t* img, uint32_t next_off,
-                                         bool need_halo, const LaneCtx& ln, int y, bool pf,
+                                         bool need_halo, const LaneCtx& ln, int y,
                                          const __half2 (&g_p)[kPairs], __half2 (&g_c)[kPairs],
                                          const __half2 (&d_p)[kPairs], __half2 (&d_c)[kPairs], __half2 (&p1)[kPairs],
                                          __half2 (&q1)[kPairs], WarpAcc& acc) {
@@ -324,8 +317,6 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const
 #ifndef FB_TECH_PREFETCH_EARLY
     if (MODE != ROW_LAST) load_row(nxt, img, next_off, need_halo, ln.halo_delta);
 #endif
-    if (kL2PrefetchRows > 0 && MODE != ROW_LAST && pf && ln.pf_lane)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(img + next_off + ln.pf_delta));
 
     if (hist) {
 #pragma unroll
@@ -454,8 +445,6 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     asm volatile("mov.b32 %0, 0x64646464;" : "=r"(ln.k64));
     asm volatile("mov.b32 %0, %1;" : "=r"(ln.hs_unbias) : "n"(0u - 4u * 0x4B000000u - (4u * kHsStride) * 0x4B400000u));
     ln.W = W;
-    ln.pf_lane = lane < 7;
-    ln.pf_delta = kL2PrefetchRows * W * 3 + (tx * kTileW - xl) * 3 + 128 * lane;
     ln.luma_lane = LUMA ? (a.luma + ((size_t)(img - a.img) / 3) + xl) : nullptr;
 
     const uint32_t row_bytes = (uint32_t)W * 3u;
@@ -476,25 +465,21 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
 
     // rows k = 0 .. rb+1 of the walk; row k prefetches row k+1.  Rows alternate between two register sets so
     // that (previous, current) swap by renaming instead of by moves.
-    // walk row k+1 is image row r0+k; its L2 prefetch partner is image row r0+k+kL2PrefetchRows (inside this unit's walk
-    // and not the last row of the image, so that the 768-byte request never leaves the frame)
-    const int pf_last = min(r0 + rb, H - 2) - kL2PrefetchRows;
-    auto pf_ok = [&](int k1) -> bool { return kL2PrefetchRows > 0 && (r0 - 1 + k1) <= pf_last && (r0 - 1 + k1) >= 0; };
     load_row(LA, img, row_off(0), need_halo, ln.halo_delta);
-    row_step<RGB, FULL, LUMA, ROW_FIRST>(LA, LB, img, row_off(1), need_halo, ln, r0 - 1, pf_ok(1), GB, GA, DB, DA, P1, Q1, acc);
-    row_step<RGB, FULL, LUMA, ROW_SECOND>(LB, LA, img, row_off(2), need_halo, ln, r0, pf_ok(2), GA, GB, DA, DB, P1, Q1, acc);
+    row_step<RGB, FULL, LUMA, ROW_FIRST>(LA, LB, img, row_off(1), need_halo, ln, r0 - 1, GB, GA, DB, DA, P1, Q1, acc);
+    row_step<RGB, FULL, LUMA, ROW_SECOND>(LB, LA, img, row_off(2), need_halo, ln, r0, GA, GB, DA, DB, P1, Q1, acc);
     bool odd_tail = false;
     int k = 2;
     for (; k <= rb; k += 2) {
-        row_step<RGB, FULL, LUMA, ROW_STEADY>(LA, LB, img, row_off(k + 1), need_halo, ln, r0 - 1 + k, pf_ok(k + 1), GB, GA, DB, DA, P1, Q1, acc);
+        row_step<RGB, FULL, LUMA, ROW_STEADY>(LA, LB, img, row_off(k + 1), need_halo, ln, r0 - 1 + k, GB, GA, DB, DA, P1, Q1, acc);
         if (k + 1 > rb) {
             odd_tail = true;
             break;
         }
-        row_step<RGB, FULL, LUMA, ROW_STEADY>(LB, LA, img, row_off(k + 2), need_halo, ln, r0 + k, pf_ok(k + 2), GA, GB, DA, DB, P1, Q1, acc);
+        row_step<RGB, FULL, LUMA, ROW_STEADY>(LB, LA, img, row_off(k + 2), need_halo, ln, r0 + k, GA, GB, DA, DB, P1, Q1, acc);
     }
-    if (odd_tail) row_step<RGB, FULL, LUMA, ROW_LAST>(LB, LA, img, 0u, need_halo, ln, r0 + rb, false, GA, GB, DA, DB, P1, Q1, acc);
-    else row_step<RGB, FULL, LUMA, ROW_LAST>(LA, LB, img, 0u, need_halo, ln, r0 + rb, false, GB, GA, DB, DA, P1, Q1, acc);
+    if (odd_tail) row_step<RGB, FULL, LUMA, ROW_LAST>(LB, LA, img, 0u, need_halo, ln, r0 + rb, GA, GB, DA, DB, P1, Q1, acc);
+    else row_step<RGB, FULL, LUMA, ROW_LAST>(LA, LB, img, 0u, need_halo, ln, r0 + rb, GB, GA, DB, DA, P1, Q1, acc);
 
     acc.l += (long long)__float2int_rn(acc.lf);
     acc.n += (unsigned long long)__float2uint_rn(acc.nf);

@@ -355,6 +355,11 @@ class BatchProcessor:
             chunks[key] = {"frames": [torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)],
                            "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
                            "used": [False, False], "next": 0}
+            # the caching allocator may hand out memory that kernels already queued on the compute stream still use
+            # (temporaries freed in stream order): the copy stream must not write into it before they have run
+            fence = torch.cuda.Event()
+            fence.record(torch.cuda.current_stream(dev))
+            self._stream["copy"].wait_event(fence)
         return chunks[key]
 
     def process_items(self, items):
