@@ -5,11 +5,14 @@
 
 One "step" = one pass of the hot path over one batch of B synthetic 24 MP frames per GPU:
 technical metrics (csrc/tech_stats.cu) + perceptual hash (csrc/phash.cu) + CLIP preprocess
-(csrc/preprocess.cu, csrc/resample_tc.cu) + ViT-L/14 tower,
-aesthetic head and tag similarities (csrc/gemm.cu, csrc/vit.cu) + the similarity stage on the
-step's embeddings (all-gather across ranks, cosine pairs, csrc/gemm.cu + csrc/similarity.cu).
-`value` is the whole-job rate with the frames already resident in HBM; `e2e` is the same pass
-through the host-buffer pipeline (pinned host frames, H2D and D2H inside the timed region).
+(csrc/preprocess.cu, csrc/resample_tc.cu) + ViT-L/14 tower, aesthetic head and tag similarities
+(csrc/gemm.cu, csrc/attention_tc.cu, csrc/vit.cu).  After the K steps the duplicate-grouping stage
+runs ONCE over everything scored (all-gather across ranks, cosine pairs csrc/gemm.cu +
+csrc/similarity.cu, Hamming pairs csrc/hamming.cu) inside the timed region — BASELINE configs[4].
+`value` is the whole-job rate with the frames already resident in HBM; `e2e` is the same work
+through the reference-shaped call (`BatchProcessor.process_items_streamed`: pinned host frames in,
+complete result dicts out; H2D, D2H and the host-side dict building inside the timed region) beside
+a copy-only ceiling.  `configs` carries short device-timed legs for BASELINE configs[1..3].
 Prints ONE JSON line on rank 0.  `--impl reference` times the reference's CPU path (oracle port;
 /root/reference does not exist on the GPU box) on a bounded sample instead.
 """
@@ -42,6 +45,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period-ms", type=float, default=50.0, help="NVML sampling period during the timed region (0 = off)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short legs for BASELINE configs[1..3]")
+    ap.add_argument("--sim-rows", type=int, default=262144, help="embeddings per GPU in the similarity leg (configs[3])")
+    ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per staging buffer of the streamed e2e path")
+    ap.add_argument("--e2e-vit-batch", type=int, default=128, help="frames per ViT launch of the streamed e2e path")
     return ap.parse_args()
 
 
@@ -185,60 +192,106 @@ def make_pool(n, seed, device):
     return out
 
 
+CPU_SAMPLE_FRAMES = 3            # frames per CPU step: same frames, same ViT batch in `--impl reference` and `cpu_baseline`
+
+
+def cpu_sample_frames():
+    """The bounded CPU sample: three frames of the workload's size from the host-side generator (facet_b200/synth.py)."""
+    from facet_b200.synth import synth_image_bgr
+    return [synth_image_bgr(2000 + i, H, W) for i in range(CPU_SAMPLE_FRAMES)]
+
+
+def cpu_arm():
+    """(ref_analyzers or None, kind, description).  oracle/_ref holds the reference's own analyzers/technical.py +
+    image_cache.py when oracle/build_ref.py ran in the build container; the CLIP tower is the oracle's fp32 restatement
+    either way (open_clip is third-party and not installable here)."""
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is not None:
+        return ref, "reference", ("technical metrics = the reference's own analyzers/technical.py + image_cache.py (oracle/_ref, "
+                                  "unmodified); pHash / PIL preprocess / fp32 torch-CPU ViT-L/14 = oracle port (imagehash, open_clip absent)")
+    return None, "port", "oracle/cpu_port.py (cv2+NumPy+SciPy technical metrics, PIL preprocess, fp32 torch-CPU ViT-L/14)"
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the reference's own CPU path (oracle port: cv2/NumPy/SciPy/PIL/torch-CPU calls in the
-    order of processing/batch_processor.py:198-233) timed on the host cores.  One 24 MP frame per step."""
+    """CPU arm: the reference's CPU path timed on the host cores (oracle/_ref analyzers when present, else the port:
+    the same cv2 / NumPy / SciPy / PIL / torch-CPU calls in the order of processing/batch_processor.py:198-233).
+    One step = CPU_SAMPLE_FRAMES 24 MP frames, batched through the tower, + the cosine grouping of what was scored so far."""
     if rank != 0:
         return
     import numpy as np
     import torch
     from facet_b200.models.clip_vit import random_state_dict
-    from facet_b200.synth import synth_embeddings, synth_image_bgr
+    from facet_b200.synth import synth_embeddings
     from oracle import cpu_port, grouping
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = random_state_dict(0)
     tags = torch.from_numpy(synth_embeddings(240, seed=7, cluster_fraction=0.0))
-    frames = [synth_image_bgr(2000 + i, H, W) for i in range(2)]
+    ref, kind, desc = cpu_arm()
+    frames = cpu_sample_frames()
     embs = []
 
-    def step(i):
-        _, vit = cpu_port.score_images_cpu([frames[i % len(frames)]], sd, tags)
+    def step():
+        _, vit = cpu_port.score_images_cpu(frames, sd, tags, ref_analyzers=ref)
         embs.append(vit["embedding"].numpy())
-        e = np.concatenate(embs[-64:], axis=0)
-        grouping.cosine_pairs(e, 0.9)
+        grouping.cosine_pairs(np.concatenate(embs[-64:], axis=0), 0.9)
 
-    for i in range(args.warmup):
-        step(i)
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
+    for _ in range(args.steps):
+        step()
     dt = time.perf_counter() - t0
-    val = args.steps / dt
+    val = args.steps * len(frames) / dt
     line = {
         "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, note="CPU arm: one 24 MP frame per step (bounded sample of the same workload)"),
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 synthetic 24 MP frame, oracle/cpu_port.py (cv2+NumPy+PIL+torch fp32)"},
+        "config": workload_config(args.batch),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {len(frames)} synthetic 24 MP frames (seeds 2000..) per step, ViT batch "
+                                   f"{len(frames)}; {desc}"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, note=None):
-    cfg = {"workload": "full legacy scoring pass on synthetic 6000x4000 (24 MP) BGR frames: technical metrics + pHash + CLIP "
-                       "preprocess + ViT-L/14 224px + MLP aesthetic + tag similarities + Hamming and cosine duplicate pairs "
-                       "(BASELINE.json configs[4], per-GPU share)",
-           "image": [H, W, 3], "batch_per_gpu": batch, "parallelism": "data-parallel, one rank per GPU",
-           "l2": "inputs larger than L2 (pool of batch x 72 MB frames per step)", "weights": "random-init ViT-L/14 (seed 0)",
-           "precision": "ViT GEMM operands fp16 (the reference's CUDA precision, scorer.py:515), fp32 accumulate and residual "
-                        "stream; technical metrics / preprocess exact integers"}
-    if note:
-        cfg["note"] = note
-    return cfg
+def workload_config(batch):
+    return {"workload": "full legacy scoring pass on synthetic 6000x4000 (24 MP) BGR frames: technical metrics + pHash + CLIP "
+                        "preprocess + ViT-L/14 224px + MLP aesthetic + tag similarities per image, then ONE duplicate-grouping "
+                        "stage (all-gather, cosine and Hamming pairs) over everything scored (BASELINE.json configs[4], per-GPU share)",
+            "image": [H, W, 3], "batch_per_gpu": batch, "parallelism": "data-parallel, one rank per GPU",
+            "l2": "inputs larger than L2 (pool of batch x 72 MB frames per step)", "weights": "random-init ViT-L/14 (seed 0)",
+            "precision": "ViT GEMM operands fp16 (the reference's CUDA precision, `self.model.half()`, scorer.py:515; NOT the bf16 "
+                         "BASELINE configs[2] names: bf16 operands miss the 0.01 aesthetic bound, tests/test_gpu_vit.py), fp32 "
+                         "accumulate and residual stream; technical metrics / preprocess exact integers"}
+
+
+def traffic_record():
+    """DRAM traffic per launch of the two roofline kernels, from ncu --set full captures (profiles/traffic.json names
+    the capture files and their sha256).  Absent file -> None: nothing is hard-coded here."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f)
+
+
+def device_embeddings(n, dim, seed, device, dup_fraction=0.15):
+    """[n, dim] float32 L2-normalised rows on the device with planted near-duplicates (cosine ~0.95)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    e = torch.randn((n, dim), device=device, generator=g)
+    e = torch.nn.functional.normalize(e, dim=-1)
+    nd = int(n * dup_fraction)
+    if nd:
+        dst = torch.randperm(n, device=device, generator=g)[:nd]
+        src = (torch.rand(nd, device=device, generator=g) * n).long().clamp_(max=n - 1)
+        v = e[src] + 0.012 * torch.randn((nd, dim), device=device, generator=g)
+        e[dst] = torch.nn.functional.normalize(v, dim=-1)
+    return e.contiguous()
 
 
 def main():
@@ -255,7 +308,7 @@ def main():
     import torch.distributed as dist
     from facet_b200 import _lib, ops
     from facet_b200.models.clip_vit import random_state_dict
-    from facet_b200.processing.pipeline import ScoringPipeline
+    from facet_b200.processing.batch_processor import BatchProcessor
     from facet_b200.processing.scorer import Facet
     from facet_b200.synth import synth_embeddings
     from facet_b200.utils.duplicate import all_gather_embeddings
@@ -268,7 +321,6 @@ def main():
     orig_affinity = os.sched_getaffinity(0)
     numa_node = bind_to_gpu_numa_node(local_rank)      # pinned e2e buffers local to the GPU's PCIe root
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry one JSON line only
         # stdout must carry exactly one JSON line: send NCCL's start-up banner ("NCCL version ...", printed on
         # stdout when the communicator is created) to stderr by redirecting fd 1 during initialisation
         sys.stdout.flush()
@@ -285,138 +337,225 @@ def main():
             os.close(saved)
     lib = _lib.load()
 
-    B = args.batch
+    B, K = args.batch, args.steps
     tags = synth_embeddings(240, seed=7, cluster_fraction=0.0)
     scorer = Facet(random_state_dict(0), text_embeddings=tags, tag_names=[f"tag{i // 4}" for i in range(240)], device=device)
     pool = make_pool(B, seed=2000 + 17 * rank, device=device)
+    emb_all = torch.empty((K * B, 768), dtype=torch.float32, device=device)
+    hash_all = torch.empty((K * B,), dtype=torch.int64, device=device)
     torch.cuda.synchronize()
 
-    def step():
+    def step(k):
+        """One batch of B frames through the per-image pass; embeddings / hashes are kept for the grouping stage.
+        No communication, no host synchronisation."""
         out = scorer.score_images_device(pool)                      # technical + pHash + preprocess + ViT/heads/tags
-        emb = all_gather_embeddings(out["embedding"]) if world > 1 else out["embedding"]
-        pairs, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)
-        hashes = all_gather_embeddings(out["phash"].view(-1, 1)).view(-1) if world > 1 else out["phash"]
-        ops.hamming_pairs(hashes, 6, part=rank, nparts=world)      # duplicate rule of utils/duplicate.py on the step's hashes
-        return out, pairs
+        emb_all[k * B:(k + 1) * B].copy_(out["embedding"])
+        hash_all[k * B:(k + 1) * B].copy_(out["phash"])
+        return out
+
+    def grouping(emb, hashes):
+        """The duplicate-grouping stage over everything scored (configs[4]): ONE all-gather of the embedding shards and of
+        the hashes, then every rank scans its balanced share of the pair triangle."""
+        e = all_gather_embeddings(emb) if world > 1 else emb
+        pairs, _ = ops.cosine_pairs(e, 0.90, part=rank, nparts=world)
+        h = all_gather_embeddings(hashes.view(-1, 1)).view(-1) if world > 1 else hashes
+        hp = ops.hamming_pairs(h, 6, part=rank, nparts=world)      # duplicate rule of utils/duplicate.py:94-119
+        return pairs, hp
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for k in range(max(args.warmup, 3)):
+        step(k % K)
+    grouping(emb_all, hash_all)
     barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream -------------------------------------
+    # ---- timed region: K steps + the grouping stage, CUDA events on the launching stream -------------------
     launches0 = int(lib.fb_launch_count())
-    # one sampler per node (rank 0's GPU): concurrent nvidia-smi pollers slow every rank's launches
+    # one sampler per node (rank 0's GPU): concurrent pollers slow every rank's launches
     sampler = ClockSampler(local_rank, period_s=max(args.clock_period_ms, 1.0) * 1e-3)
     if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
         time.sleep(0.3)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, eg = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     sampler.reset()
     e0.record()
-    for _ in range(args.steps):
-        out, pairs = step()
+    for k in range(K):
+        step(k)
+    eg.record()
+    pairs, hpairs = grouping(emb_all, hash_all)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    ms_group = eg.elapsed_time(e1)
     clocks = sampler.stop()
     launches = int(lib.fb_launch_count()) - launches0
     if world > 1:
-        t = torch.tensor([ms_total], device=device)
+        t = torch.tensor([ms_total, ms_group], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step * 1e-3)
+        ms_total, ms_group = (float(v) for v in t.tolist())
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total * 1e-3)
 
-    # ---- per-kernel device times of the SAME steps: the library records a CUDA-event pair around each of
-    # its launches on the launching stream (fb_profile_*); K more steps, identical inputs -------------------
+    # ---- per-kernel device times of the SAME work: the library records a CUDA-event pair around each of its
+    # launches on the launching stream (fb_profile_*); K more steps + grouping, identical inputs ----------------
     _lib.profile_enable(True)
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
-    for _ in range(args.steps):
-        step()
+    for k in range(K):
+        step(k)
+    grouping(emb_all, hash_all)
     pe1.record()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
-    ms_step_profiled = pe0.elapsed_time(pe1) / args.steps
-    per_step = {k: (v[0] / args.steps, v[1] // args.steps) for k, v in prof.items() if v[1]}
+    ms_step_profiled = pe0.elapsed_time(pe1) / K
+    per_step = {k: (v[0] / K, v[1] / K) for k, v in prof.items() if v[1]}
     ms_tech, ms_pre = per_step["technical"][0], per_step["preprocess"][0]
     ms_phash = per_step.get("other", (0.0, 0))[0]
     ms_vit = sum(per_step[k][0] for k in ("im2col", "gemm", "layernorm", "attention", "vit_tail") if k in per_step)
     gemm_ms, gemm_launches = per_step["gemm"]
     stages = {"technical_ms": ms_tech, "phash_ms": ms_phash, "preprocess_ms": ms_pre, "vit_ms": ms_vit,
+              "grouping_ms_total": ms_group, "grouping_rows": world * K * B,
               "kernel_ms_per_step": {k: round(v[0], 4) for k, v in per_step.items()},
-              "launches_per_step": {k: v[1] for k, v in per_step.items()},
+              "launches_per_step": {k: round(v[1], 2) for k, v in per_step.items()},
               "step_ms_with_event_pairs": ms_step_profiled,
               "technical_gbs": B * TECH_BYTES_PER_IMAGE / (ms_tech * 1e-3) / 1e9,
               "vit_tflops": B * GFLOP_PER_IMAGE * 1e9 / (ms_vit * 1e-3) / 1e12}
     peaks = measured_peaks()
     gemm_tflops = B * GEMM_GFLOP_PER_IMAGE * 1e9 / (gemm_ms * 1e-3) / 1e12
-    # DRAM traffic of the GEMM launches of one layer at batch 128, from profiles/r1_gemm_ncu_v2.txt (ncu --set full)
-    traffic_per_layer_b128 = (73.8 + 153.7 + 204.3 + 82.5 + 75.9 + 222.8 + 436.6 + 106.3) * 1e6
-    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05), {gemm_launches} launches per step",
+    tr = traffic_record()
+    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05), {gemm_launches:.0f} launches per step",
                 "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": gemm_tflops / peaks["bf16_tflops"],
-                "traffic": (24 * traffic_per_layer_b128 * B / 128) if world >= 1 else None,
-                "traffic_note": "bytes per step, scaled from the ncu capture at batch 128 (24 layers x 4 launches)",
+                "traffic": (tr["gemm"]["dram_bytes_per_layer_at_batch_128"] * 24 * B / 128) if tr else None,
+                "traffic_source": tr["gemm"]["source"] if tr else None,
                 "algorithmic_flops_per_step": B * GEMM_GFLOP_PER_IMAGE * 1e9, "kernel_ms_per_step": gemm_ms,
                 "timing": "CUDA-event pairs around every launch of the kernel, on the launching stream, over K steps",
                 "peak_source": peaks["source"], "share_of_step": gemm_ms / ms_step_profiled,
                 "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
                                      "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"],
                                      "algorithmic_bytes_per_step": B * TECH_BYTES_PER_IMAGE,
-                                     "traffic": (610.1e6 + 144.9e6) / 8 * B,
-                                     "traffic_note": "ncu dram bytes read + written (frames + the luma plane the pass also emits "
-                                                     "for the pHash), 8-frame capture of profiles/r1_tech_stats_ncu_v2.txt scaled"}}
+                                     "traffic": (tr["technical"]["dram_bytes_per_frame"] * B) if tr else None,
+                                     "traffic_source": tr["technical"]["source"] if tr else None}}
 
-    # ---- e2e: pinned host frames -> pipeline (H2D + kernels + D2H inside the timed region) ---------------
+    # ---- the other BASELINE configs, each a short device-timed leg (best of 3) ------------------------------
+    def best_ms(fn, reps=3):
+        best = 1e30
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(reps):
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    configs = {}
+    if not args.no_configs:
+        # configs[1]: technical metrics only, 64-frame pool (4.6 GB >> L2), no luma plane
+        n1 = min(64, B)
+        ops.tech_stats_raw(pool[:n1])
+        ms1 = best_ms(lambda: ops.tech_stats_raw(pool[:n1]))
+        configs["tech_only"] = {"baseline_config": 1, "frames_per_launch": n1, "ms": ms1, "images_per_s_per_gpu": n1 / (ms1 * 1e-3),
+                                "GB_s": n1 * TECH_BYTES_PER_IMAGE / (ms1 * 1e-3) / 1e9,
+                                "frac_of_measured_hbm": n1 * TECH_BYTES_PER_IMAGE / (ms1 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                "note": "pool of distinct device-resident 24 MP frames cycled (10k-image runs repeat this launch)"}
+        # configs[2]: ViT-L/14 + head, batch 512 (fp16 operands, see config.precision)
+        g = torch.Generator(device=device).manual_seed(3 + rank)
+        clip_in = torch.randn((512, 3, 224, 224), device=device, generator=g)
+        scorer.model.encode(clip_in)
+        ms2 = best_ms(lambda: scorer.model.encode(clip_in))
+        tf2 = 512 * GFLOP_PER_IMAGE * 1e9 / (ms2 * 1e-3) / 1e12
+        configs["vit_b512"] = {"baseline_config": 2, "batch": 512, "ms": ms2, "images_per_s_per_gpu": 512 / (ms2 * 1e-3),
+                               "TFLOP_s": tf2, "frac_of_sustained_bf16": tf2 / peaks["bf16_tflops"], "dtype": "fp16"}
+        del clip_in
+        # configs[3]: all-pairs cosine over n3 x 768 embeddings per GPU (gathered: world x n3 rows)
+        n3 = args.sim_rows
+        e_loc = device_embeddings(n3, 768, 11 + rank, device)
+
+        def sim():
+            e = all_gather_embeddings(e_loc) if world > 1 else e_loc
+            return ops.cosine_pairs(e, 0.90, part=rank, nparts=world)
+
+        sim()
+        barrier()
+        ms3 = best_ms(sim)
+        if world > 1:
+            t = torch.tensor([ms3], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms3 = float(t.item())
+        ntot = world * n3
+        configs["similarity"] = {"baseline_config": 3, "rows_per_gpu": n3, "rows_total": ntot, "dim": 768, "tau": 0.90, "ms": ms3,
+                                 "pair_comparisons_per_s": ntot * (ntot - 1) / 2 / (ms3 * 1e-3),
+                                 "TFLOP_s_total": ntot * (ntot - 1) * 768 / (ms3 * 1e-3) / 1e12,
+                                 "all_gather_bytes_per_rank": (world - 1) * n3 * 768 * 4 if world > 1 else 0}
+        del e_loc
+
+    # ---- e2e: the reference-shaped call.  B items per step ({'path', 'img_cv'} with frames in pinned host memory)
+    # -> BatchProcessor.process_items_streamed -> the complete result dicts of batch_processor.py:298-355; then the
+    # grouping stage on the embeddings / hashes of those dicts.  H2D, D2H and all host work inside the timed region. ----
     e2e = None
     if not args.no_e2e:
-        pipe = ScoringPipeline(scorer, chunk=8)
-        # pinned host frames: a 32-frame buffer (2.3 GB per rank) sent B/32 times per step keeps the host
-        # footprint bounded at N=8 while every step still moves B x 72 MB over PCIe
-        eb = min(B, 32)
+        bp = BatchProcessor(scorer, batch_size=B)
+        eb = min(B, 32)              # pinned pool: 32 frames (2.3 GB per rank) referenced B/32 times per step
         reps = max(1, B // eb)
         host = torch.empty((eb, H, W, 3), dtype=torch.uint8, pin_memory=True)
         host.copy_(pool[:eb])
         torch.cuda.synchronize()
-        pipe.run_host(host)          # warm-up
+        views = [host[i].numpy() for i in range(eb)]
+        items = [{"path": f"/bench/rank{rank}/img_{j:06d}.jpg", "img_cv": views[j % eb]} for j in range(eb * reps)]
+        chunk, vit_batch = args.e2e_chunk, args.e2e_vit_batch
+        bp.process_items_streamed(items[:eb], chunk=chunk, vit_batch=vit_batch)          # warm-up
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(2, min(args.steps, 5))
-        d2h = 0
-        a.record()
+        n_e2e = max(2, min(K, 4))
+        bp.metrics["h2d_bytes"] = bp.metrics["d2h_bytes"] = 0
+        extra_h2d = extra_d2h = 0
+        res_all = []
+        t0 = time.perf_counter()
         for _ in range(n_e2e):
-            # the step's B frames reach the pipeline as B/32 host batches, back to back like a loader delivers them
-            res = pipe.run_host_stream(host for _r in range(reps))
-            embs, hashes_h = [res["embedding"]], [res["phash"]]
-            emb = torch.from_numpy(np.concatenate(embs)).to(device)
-            emb = all_gather_embeddings(emb) if world > 1 else emb
-            p_, _ = ops.cosine_pairs(emb, 0.90, part=rank, nparts=world)
-            hh = torch.from_numpy(np.concatenate(hashes_h).view(np.int64)).to(device)
-            hh = all_gather_embeddings(hh.view(-1, 1)).view(-1) if world > 1 else hh
-            q_ = ops.hamming_pairs(hh, 6, part=rank, nparts=world)
-            d2h = int(p_.cpu().numel() + q_.cpu().numel()) * 4
-        b.record()
+            res_all.extend(bp.process_items_streamed(items, chunk=chunk, vit_batch=vit_batch))
+        assert all("error" not in r for r in res_all), "e2e: a frame failed"
+        emb = torch.from_numpy(np.frombuffer(b"".join(r["clip_embedding"] for r in res_all), dtype=np.float32).reshape(-1, 768).copy()).to(device)
+        hh = torch.from_numpy(np.array([int(r["phash"], 16) for r in res_all], dtype=np.uint64).view(np.int64)).to(device)
+        p_, q_ = grouping(emb, hh)
+        extra_h2d = emb.numel() * 4 + hh.numel() * 8
+        extra_d2h = int(p_.cpu().numel() + q_.cpu().numel()) * 4
         barrier()
-        ms_e = a.elapsed_time(b) / n_e2e
+        ms_e = (time.perf_counter() - t0) * 1e3
+        # copy-only ceiling: the same pinned frames through the same staging buffers, no kernels, all ranks at once
+        stage = [torch.empty((chunk, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+        cs = torch.cuda.Stream(device=device)
+        barrier()
+        t1 = time.perf_counter()
+        with torch.cuda.stream(cs):
+            for j in range(eb * reps):
+                stage[(j // chunk) & 1][j % chunk].copy_(host[j % eb], non_blocking=True)
+        cs.synchronize()
+        barrier()
+        ms_c = (time.perf_counter() - t1) * 1e3
         if world > 1:
-            t = torch.tensor([ms_e], device=device)
+            t = torch.tensor([ms_e, ms_c], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e = float(t.item())
+            ms_e, ms_c = (float(v) for v in t.tolist())
         frames_per_step = eb * reps
-        e2e = {"value": world * frames_per_step / (ms_e * 1e-3), "unit": "images/s", "steps": n_e2e,
-               "frames_per_step_per_gpu": frames_per_step,
-               "numa_node_rank0": numa_node,
-               "h2d_bytes_per_step": pipe.h2d_bytes(frames_per_step, H, W) + frames_per_step * (768 * 4 + 8),
-               "d2h_bytes_per_step": pipe.d2h_bytes(frames_per_step, 240) + d2h}
-        del host
+        e2e_val = world * frames_per_step * n_e2e / (ms_e * 1e-3)
+        ceiling = world * frames_per_step / (ms_c * 1e-3)
+        e2e = {"value": e2e_val, "unit": "images/s", "steps": n_e2e, "frames_per_step_per_gpu": frames_per_step,
+               "api": "BatchProcessor.process_items_streamed -> result dicts (batch_processor.py:298-355 columns incl. aggregate inputs, tags, "
+                      "pHash, embedding bytes), then the grouping stage on their embeddings / hashes",
+               "timing": "wall clock between synchronised points (host dict building is inside), max over ranks",
+               "chunk_frames": chunk, "vit_batch": vit_batch, "numa_node_rank0": numa_node,
+               "h2d_bytes_per_step": bp.metrics["h2d_bytes"] // n_e2e + extra_h2d // n_e2e,
+               "d2h_bytes_per_step": bp.metrics["d2h_bytes"] // n_e2e + extra_d2h // n_e2e,
+               "h2d_ceiling_images_per_s": ceiling, "h2d_ceiling_GB_s_per_gpu": frames_per_step * TECH_BYTES_PER_IMAGE / (ms_c * 1e-3) / 1e9,
+               "frac_of_h2d_ceiling": e2e_val / ceiling,
+               "ceiling_note": "copy-only leg: the same pinned frames into the same staging buffers on one copy stream, no kernels, all "
+                               "ranks concurrently"}
+        del host, stage
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload -----------------
+    # ---- CPU baseline beside it (rank 0, N=1 only): the same bounded sample `--impl reference` runs -------------
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, orig_affinity)      # the CPU arm may use every host core again
@@ -424,28 +563,30 @@ def main():
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sd = random_state_dict(0)
-        frames = [pool[i].cpu().numpy() for i in (1, 2, 4)]
-        cpu_port.score_images_cpu(frames[:1], sd, torch.from_numpy(tags))
+        ref, kind, desc = cpu_arm()
+        frames = cpu_sample_frames()
+        cpu_port.score_images_cpu(frames[:1], sd, torch.from_numpy(tags), ref_analyzers=ref)
         t0 = time.perf_counter()
-        tech_cpu, vit_cpu = cpu_port.score_images_cpu(frames, sd, torch.from_numpy(tags))
+        tech_cpu, vit_cpu = cpu_port.score_images_cpu(frames, sd, torch.from_numpy(tags), ref_analyzers=ref)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": len(frames) / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"{len(frames)} of the step's 24 MP frames through oracle/cpu_port.py "
-                                  "(cv2+NumPy+SciPy technical metrics, PIL preprocess, fp32 torch-CPU ViT-L/14)"}
+        cpu_baseline = {"value": len(frames) / dt, "unit": "images/s", "cores": cores, "kind": kind,
+                        "sample": f"{len(frames)} synthetic 24 MP frames (seeds 2000..), ViT batch {len(frames)}; {desc}"}
         # parity spot check on those frames (checker only)
         got = scorer.score_images(np.stack(frames))
         cosv = [float(np.dot(np.frombuffer(g["clip_embedding"], np.float32), vit_cpu["embedding"][i].numpy())) for i, g in enumerate(got)]
         cpu_baseline["parity_spot_check"] = {
             "hist_exact": all(g["histogram_data"] == t["histogram"]["histogram_bytes"] for g, t in zip(got, tech_cpu)),
+            "phash_equal": all(g["phash"] == t["phash"] for g, t in zip(got, tech_cpu)),
             "min_embedding_cosine": min(cosv)}
 
     if rank == 0:
         line = {
-            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "config": workload_config(B),
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "stages": stages, "pairs_last_step": int(pairs.shape[0]),
+            "stages": stages, "configs": configs,
+            "pairs": {"cosine": int(pairs.shape[0]), "hamming": int(hpairs.shape[0])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

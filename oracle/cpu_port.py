@@ -72,6 +72,20 @@ def technical_metrics_cv(img_bgr: np.ndarray, mono_threshold: float = 0.10) -> d
     return out
 
 
+def technical_metrics_ref(img_bgr: np.ndarray, image_cache_cls, analyzer_cls, mono_threshold: float = 0.10) -> dict:
+    """The same seven dicts through the reference's OWN classes (oracle/_ref, placed by oracle/build_ref.py), in the
+    call order of processing/batch_processor.py:198-233."""
+    cache = image_cache_cls(img_bgr)
+    ta = analyzer_cls
+    return {"sharpness": ta.get_sharpness_data(img_bgr, cache=cache),
+            "color": ta.get_color_harmony_data(img_bgr, cache=cache),
+            "histogram": ta.get_histogram_data(img_bgr, cache=cache),
+            "monochrome": ta.detect_monochrome(img_bgr, threshold=mono_threshold, cache=cache),
+            "dynamic_range": ta.get_dynamic_range(img_bgr, cache=cache),
+            "noise": ta.get_noise_estimate(img_bgr, cache=cache),
+            "contrast": ta.get_contrast_score(img_bgr, cache=cache)}
+
+
 def clip_preprocess_pil(img_bgr: np.ndarray, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
     import torchvision.transforms as T
     from PIL import Image
@@ -80,12 +94,17 @@ def clip_preprocess_pil(img_bgr: np.ndarray, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5
     return tf(Image.fromarray(np.ascontiguousarray(img_bgr[..., ::-1])))
 
 
-def score_images_cpu(images_bgr, state_dict, tag_embeddings=None):
-    """The reference's per-image pass on the CPU for a list of BGR frames (fp32 tower)."""
+def score_images_cpu(images_bgr, state_dict, tag_embeddings=None, ref_analyzers=None):
+    """The reference's per-image pass on the CPU for a list of BGR frames (fp32 tower).  ref_analyzers =
+    (ImageCache, TechnicalAnalyzer) of the reference (oracle.build_ref.load()) routes the technical metrics through the
+    reference's own code instead of the port."""
     import torch
     from . import vit_torch
     from . import phash as _ph
-    tech = [technical_metrics_cv(im) for im in images_bgr]
+    if ref_analyzers is not None:
+        tech = [technical_metrics_ref(im, *ref_analyzers) for im in images_bgr]
+    else:
+        tech = [technical_metrics_cv(im) for im in images_bgr]
     for t, im in zip(tech, images_bgr):
         t["phash"] = _ph.phash_hex(im)                      # imagehash.phash, batch_processor.py:216
     clip_in = torch.stack([clip_preprocess_pil(im) for im in images_bgr])
