@@ -5,8 +5,11 @@
 // (pair kept iff similarity >= threshold, Union-Find).  The all-pairs product runs as a bf16
 // tcgen05 GEMM with a threshold epilogue (csrc/gemm.cu, FB_GEMM_THRESHOLD_PAIRS) that emits
 // candidates with sim >= tau - band; bf16 input rounding moves a unit-vector dot product by at most
-// 2^-8, so band = 0.01 cannot lose a pair.  Candidates are then re-scored here in fp32 on the
-// stored float32 embeddings, which decides the final pair set.
+// 2^-8, so band = 0.01 cannot lose a pair.  Candidates are then re-scored here on the stored float32
+// embeddings with float64 accumulation (every product of two floats is exact in a double, the 768-term sum is
+// good to ~1e-13), which decides the final pair set: `double(dot) >= double(float(tau))`.  A float32 dot product
+// (what NumPy / BLAS computes in the reference's formula sites) depends on the summation order by ~1e-7, so
+// it cannot define a pair set bit-exactly; the float64 criterion can, on both sides (oracle: float64 matmul).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
     }
 }
 
-// one warp per candidate: fp32 dot product in a fixed order, keep iff >= tau
+// one warp per candidate: float64 dot product of the float32 rows in a fixed order, keep iff >= tau
 __global__ void __launch_bounds__(256) cosine_recheck_kernel(const float* __restrict__ emb, long long ld, int k,
                                                              const int* __restrict__ cand, const unsigned long long* __restrict__ ncand,
                                                              long long cand_cap, float tau, int* __restrict__ pairs,
@@ -38,16 +41,16 @@ __global__ void __launch_bounds__(256) cosine_recheck_kernel(const float* __rest
         const int i = cand[2 * c], j = cand[2 * c + 1];
         const float* a = emb + (size_t)i * ld;
         const float* b = emb + (size_t)j * ld;
-        float d = 0.f;
-        for (int x = lane; x < k; x += 32) d = fmaf(a[x], b[x], d);
+        double d = 0.0;
+        for (int x = lane; x < k; x += 32) d = fma((double)a[x], (double)b[x], d);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0 && d >= tau) {
+        if (lane == 0 && d >= (double)tau) {
             const unsigned long long pos = atomicAdd(count, 1ull);
             if ((long long)pos < cap) {
                 pairs[2 * pos] = i;
                 pairs[2 * pos + 1] = j;
-                sims[pos] = d;
+                sims[pos] = (float)d;
             }
         }
     }

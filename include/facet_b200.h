@@ -196,8 +196,9 @@ int fb_burst_links(const uint64_t* d_hashes, const int64_t* d_time_s, const uint
  * [row_offset, row_offset+rows), with <e_i, e_j> >= tau on the stored L2-normalised float32
  * embeddings (formula sites models/tagger.py:99-101, api/routers/gallery.py:465-471; grouping as
  * utils/duplicate.py).  The N x N product runs as a bf16 tcgen05 GEMM whose epilogue emits
- * candidates with sim >= tau - band into d_cand; they are then re-scored in fp32 from d_emb_f32
- * and the survivors written to d_pairs [(i,j)] / d_sims.  Counts above the capacities mean the
+ * candidates with sim >= tau - band into d_cand; they are then re-scored from d_emb_f32 with float64
+ * accumulation (pair kept iff double(dot) >= double(tau): order-independent to ~1e-13, unlike a float32 dot)
+ * and the survivors written to d_pairs [(i,j)] / d_sims (the dot rounded to float32).  Counts above the capacities mean the
  * lists were truncated (caller retries with larger buffers).  band >= 2^-8 is loss-free. */
 int fb_f32_to_bf16(const float* d_in, void* d_out_bf16, int64_t n, void* stream);
 int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, int dim, float tau, float band,

@@ -102,6 +102,24 @@ def cosine_pairs(emb: np.ndarray, tau: float, block: int = 2048) -> np.ndarray:
     return p[np.lexsort((p[:, 1], p[:, 0]))].astype(np.int64)
 
 
+def cosine_pairs_exact(emb: np.ndarray, tau: float, block: int = 1024) -> np.ndarray:
+    """All (i<j) with float64 dot of the stored float32 rows >= float64(float32(tau)): the order-independent
+    criterion (to ~1e-13) that the device recheck implements; cosine_pairs above is the reference's float32 formula,
+    whose result near tau depends on the BLAS summation order."""
+    n = emb.shape[0]
+    e = np.ascontiguousarray(emb, dtype=np.float32).astype(np.float64)
+    t = np.float64(np.float32(tau))
+    out = []
+    for i0 in range(0, n, block):
+        sims = e[i0:i0 + block] @ e.T
+        ii, jj = np.nonzero(sims >= t)
+        ii = ii + i0
+        keep = jj > ii
+        out.append(np.stack([ii[keep], jj[keep]], axis=1))
+    p = np.concatenate(out, axis=0) if out else np.zeros((0, 2), np.int64)
+    return p[np.lexsort((p[:, 1], p[:, 0]))].astype(np.int64)
+
+
 def cosine_groups(emb: np.ndarray, aggregates, tau: float):
     return groups_from_pairs(emb.shape[0], cosine_pairs(emb, tau), aggregates)
 

@@ -19,7 +19,10 @@ def test_cosine_pair_set_matches_oracle(n):
         pairs, sims = ops.cosine_pairs(et, tau)
         got = pairs.cpu().numpy().astype(np.int64)
         got = got[np.lexsort((got[:, 1], got[:, 0]))] if len(got) else got.reshape(0, 2)
-        # pairs whose fp32 similarity sits within 2e-6 of tau may legitimately flip with summation order
+        # bit-exact against the order-independent criterion (float64 dot of the float32 rows >= tau) ...
+        assert got.tolist() == og.cosine_pairs_exact(e, tau).tolist()
+        # ... and equal to the reference's float32 formula wherever that formula is itself well defined: a float32 dot
+        # within 2e-6 of tau flips with the BLAS summation order
         full = e @ e.T
         def strict(p, margin):
             return {tuple(x) for x in p.tolist() if abs(float(full[x[0], x[1]]) - tau) > margin}
