@@ -39,6 +39,9 @@ _SIGNATURES = {
     "fb_orient": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "fb_thumbnail": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fb_jpeg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "fb_jpeg_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int,
+                                 _P, C.c_size_t, _P, C.c_int64, _P, _P]),
     "fb_hamming_pairs": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P]),
     "fb_burst_links": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int64, C.c_double, _P, _P, C.c_int64, _P, _P]),
 }

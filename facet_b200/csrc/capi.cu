@@ -356,6 +356,24 @@ int fb_embedding_heads(const float* d_vectors, int n, const float* head_w1, cons
     return rc;
 }
 
+size_t fb_jpeg_workspace_bytes(int n, int width, int height, int ncomp, int h0, int v0, int restart_interval, int64_t max_scan_bytes) {
+    return jpeg_workspace_bytes(n, width, height, ncomp, h0, v0, restart_interval, (long long)max_scan_bytes);
+}
+
+int fb_jpeg_decode(const uint8_t* d_bytes, const int64_t* d_scan_offset, const int64_t* d_scan_bytes, const int32_t* d_table_slot,
+                   const void* d_table_sets, int n, int width, int height, int ncomp, const int32_t* hs3, const int32_t* vs3,
+                   const int32_t* tq3, const int32_t* td3, const int32_t* ta3, int restart_interval, int64_t max_scan_bytes, int bgr_order,
+                   void* d_workspace, size_t workspace_bytes, uint8_t* d_frames, int64_t frame_stride, int32_t* d_status, void* stream) {
+    FB_REQUIRE(hs3 && vs3 && tq3 && td3 && ta3, "fb_jpeg_decode: null component arrays");
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    int rc = launch_jpeg_decode(d_bytes, reinterpret_cast<const long long*>(d_scan_offset), reinterpret_cast<const long long*>(d_scan_bytes),
+                                d_table_slot, d_table_sets, n, width, height, ncomp, hs3, vs3, tq3, td3, ta3, restart_interval,
+                                (long long)max_scan_bytes, bgr_order, d_workspace, workspace_bytes, d_frames, (long long)frame_stride,
+                                d_status, (cudaStream_t)stream);
+    if (rc == 0) count_launch(restart_interval > 0 ? 6 : 3);
+    return rc;
+}
+
 int fb_vit_attention(const void* d_qkv_bf16, int batch, void* d_out_bf16, void* stream) {
     int rc = launch_attention_tc(d_qkv_bf16, batch, d_out_bf16, 0, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);

@@ -1,0 +1,607 @@
+// Baseline JPEG decoding on the device: file bytes -> upright-agnostic [n][H][W][3] uint8 frames.
+//
+// Replaces the decode inside `load_image_from_path` (utils/image_loading.py:90-106 of the reference:
+// `Image.open(path)` ... `.convert('RGB')` through Pillow / libjpeg-turbo, then `cv2.cvtColor(RGB2BGR)`), byte-exact:
+//   restart scan      finds the RSTn markers of every stream (three small kernels: count, prefix, write)
+//   huffman           one thread per restart interval (ITU T.81 F.2: DC prediction restarts with the interval, so
+//                     intervals are independent); a stream without DRI is one interval, i.e. one thread — correct
+//                     but serial: loaders that want the GPU rate write restart markers (Pillow: restart_marker_blocks)
+//   idct              dequantise + jidctint.c `jpeg_idct_islow` (13-bit constants, 2 extra bits after pass 1, the
+//                     10-bit wrap of libjpeg's range-limit table), one thread per 8x8 block
+//   upsample+colour   jdsample.c h2v1 / h2v2 "fancy" (triangle) upsampling with replicated edges + jdcolor.c
+//                     ycc_rgb_convert (16-bit fixed point), four pixels per thread, RGB or BGR order
+// Host parsing of the marker segments and the table layout: facet_b200/utils/jpeg.py.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fb {
+
+namespace {
+
+constexpr int kLutBits = 9;
+
+struct JpegHuff {
+    uint16_t lut[1 << kLutBits];      // (length << 8) | symbol for codes of <= 9 bits, else 0
+    int32_t maxcode[18];              // largest code of each length (-1: none), [17] = sentinel
+    int32_t valptr[17];               // symbol index = code + valptr[length]
+    uint8_t values[256];
+    uint8_t pad[4];
+};
+struct JpegTableSet {
+    uint16_t q[4][64];                // natural (row-major) order
+    JpegHuff dc[4], ac[4];
+};
+static_assert(sizeof(JpegHuff) == 1424 && sizeof(JpegTableSet) == 11904, "layout shared with facet_b200/utils/jpeg.py");
+
+#define FB_HD __host__ __device__ __forceinline__
+
+static const uint8_t h_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
+                                     13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
+                                     52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+__constant__ uint8_t c_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
+                                     13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
+                                     52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+FB_HD int zigzag_at(int k) {
+#ifdef __CUDA_ARCH__
+    return c_zigzag[k];
+#else
+    return h_zigzag[k];
+#endif
+}
+
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc;
+    int n;
+};
+
+// Top up to > 32 buffered bits.  Inside an interval the only 0xFF bytes are stuffed ones (followed by 0x00); past
+// the end zeros are fed (T.81 F.2.2.5).
+FB_HD void refill(BitReader& br) {
+    while (br.n <= 32) {
+        uint32_t b = 0;
+        if (br.p < br.end) {
+            b = *br.p++;
+            if (b == 0xFF && br.p < br.end && *br.p == 0x00) ++br.p;
+        }
+        br.acc = (br.acc << 8) | b;
+        br.n += 8;
+    }
+}
+FB_HD uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (br.n - k)) & ((1u << k) - 1u); }
+
+// One Huffman symbol (>= 16 bits buffered).  Returns -1 for a code that is not in the table.
+FB_HD int decode_symbol(BitReader& br, const JpegHuff& h) {
+    const uint32_t e = h.lut[peek(br, kLutBits)];
+    if (e) {
+        br.n -= (int)(e >> 8);
+        return (int)(e & 255u);
+    }
+    const int code16 = (int)peek(br, 16);
+#pragma unroll 1
+    for (int len = kLutBits + 1; len <= 16; ++len) {
+        const int code = code16 >> (16 - len);
+        if (code <= h.maxcode[len]) {
+            br.n -= len;
+            return (int)h.values[(code + h.valptr[len]) & 255];
+        }
+    }
+    return -1;
+}
+FB_HD int receive_extend(BitReader& br, int s) {       // F.2.2.1 / F.2.2.4, s >= 1
+    const int v = (int)peek(br, s);
+    br.n -= s;
+    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+struct JpegGeom {
+    int width, height, ncomp;
+    int hs[3], vs[3], tq[3], td[3], ta[3];
+    int restart_interval, mcux, mcuy, n_intervals;
+    int blocks_w[3], blocks_h[3];                 // padded block grid per component
+    long long coef_comp_off[3], coef_image_stride;   // in int16 elements
+    long long plane_comp_off[3], plane_image_stride; // in bytes; planes are blocks_w*8 wide, blocks_h*8 high
+};
+
+// ---- restart scan ---------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256, kScanBytesPerThread = 64, kScanChunk = kScanThreads * kScanBytesPerThread;
+
+__device__ __forceinline__ int count_markers(const uint8_t* s, long long len, long long lo, long long hi, uint32_t* out, int base) {
+    int c = 0;
+    for (long long p = lo; p < hi && p + 1 < len; ++p) {
+        if (s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0) {
+            if (out) out[base + c] = (uint32_t)(p + 2);
+            ++c;
+        }
+    }
+    return c;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kScanThreads) jpeg_restart_scan_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
+                                                                         const long long* __restrict__ scan_len, int chunks, int n_intervals,
+                                                                         int* __restrict__ counts, uint32_t* __restrict__ starts) {
+    __shared__ int s_cnt[kScanThreads];
+    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* s = bytes + scan_off[img];
+    const long long len = scan_len[img];
+    const long long lo = (long long)chunk * kScanChunk + (long long)tid * kScanBytesPerThread;
+    const long long hi = min(lo + kScanBytesPerThread, len);
+    const int mine = lo < len ? count_markers(s, len, lo, hi, nullptr, 0) : 0;
+    s_cnt[tid] = mine;
+    __syncthreads();
+    // inclusive scan over the block (Hillis-Steele; 256 entries)
+    for (int o = 1; o < kScanThreads; o <<= 1) {
+        const int v = tid >= o ? s_cnt[tid - o] : 0;
+        __syncthreads();
+        s_cnt[tid] += v;
+        __syncthreads();
+    }
+    if (!WRITE) {
+        if (tid == kScanThreads - 1) counts[(size_t)img * chunks + chunk] = s_cnt[tid];
+    } else if (mine) {
+        const int base = counts[(size_t)img * chunks + chunk] + s_cnt[tid] - mine;       // exclusive position among the image's markers
+        if (base + mine <= n_intervals - 1)
+            count_markers(s, len, lo, hi, starts + (size_t)img * n_intervals + 1, base);
+    }
+}
+
+// exclusive prefix of the per-chunk counts of one image; status[img] |= 1 when the number of markers is not n_intervals - 1
+__global__ void __launch_bounds__(256) jpeg_restart_prefix_kernel(int* __restrict__ counts, int chunks, int n_intervals,
+                                                                  uint32_t* __restrict__ starts, int* __restrict__ status) {
+    __shared__ int s_part[256];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    int* c = counts + (size_t)img * chunks;
+    const int per = (chunks + 255) / 256;
+    const int lo = min(tid * per, chunks), hi = min(lo + per, chunks);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += c[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = c[i];
+        c[i] = run;
+        run += v;
+    }
+    if (tid == 255) {
+        if (s_part[255] != n_intervals - 1) atomicOr(status + img, 1);
+        starts[(size_t)img * n_intervals] = 0u;
+    }
+}
+
+// Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside).  Writes whole
+// 8x8 blocks (zeros included) of quantised coefficients in natural order.  Returns false on invalid Huffman data.
+FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, int16_t* cimg) {
+    BitReader br;
+    br.p = p0;
+    br.end = p1;
+    br.acc = 0;
+    br.n = 0;
+    const int total_mcus = g.mcux * g.mcuy;
+    const int m0 = g.restart_interval ? iv * g.restart_interval : 0;
+    const int m1 = g.restart_interval ? (m0 + g.restart_interval < total_mcus ? m0 + g.restart_interval : total_mcus) : total_mcus;
+    int pred[3] = {0, 0, 0};
+    __align__(16) int16_t blk[64];
+    for (int m = m0; m < m1; ++m) {
+        const int my = m / g.mcux, mx = m - my * g.mcux;
+        for (int c = 0; c < g.ncomp; ++c) {
+            const JpegHuff& hd = T.dc[g.td[c]];
+            const JpegHuff& ha = T.ac[g.ta[c]];
+            for (int by = 0; by < g.vs[c]; ++by) {
+                for (int bx = 0; bx < g.hs[c]; ++bx) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(blk)[i] = make_uint4(0u, 0u, 0u, 0u);
+                    refill(br);
+                    const int t = decode_symbol(br, hd);
+                    if (t < 0 || t > 15) return false;
+                    if (t) {
+                        refill(br);
+                        pred[c] += receive_extend(br, t);
+                    }
+                    blk[0] = (int16_t)pred[c];
+                    int k = 1;
+                    while (k < 64) {
+                        refill(br);
+                        const int rs = decode_symbol(br, ha);
+                        if (rs < 0) return false;
+                        const int r = rs >> 4, sz = rs & 15;
+                        if (sz == 0) {
+                            if (r != 15) break;          // EOB
+                            k += 16;                     // ZRL
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) return false;
+                        blk[zigzag_at(k)] = (int16_t)receive_extend(br, sz);      // >= 16 bits are still buffered after the symbol
+                        ++k;
+                    }
+                    const size_t b = (size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx);
+                    uint4* dst = reinterpret_cast<uint4*>(cimg + g.coef_comp_off[c] + b * 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(blk)[i];
+                }
+            }
+        }
+    }
+    return true;
+}
+
+// ---- entropy decoding -----------------------------------------------------------------------------------------------
+constexpr int kHuffThreads = 64;
+
+__global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
+                                                                    const long long* __restrict__ scan_len, const int* __restrict__ table_slot,
+                                                                    const JpegTableSet* __restrict__ tables, const uint32_t* __restrict__ starts,
+                                                                    JpegGeom g, int16_t* __restrict__ coef, int* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    JpegTableSet* T = reinterpret_cast<JpegTableSet*>(s_raw);
+    const int img = blockIdx.y, tid = threadIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tables + table_slot[img]);
+        uint4* dst = reinterpret_cast<uint4*>(s_raw);
+        for (int i = tid; i < (int)(sizeof(JpegTableSet) / 16); i += kHuffThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int iv = blockIdx.x * kHuffThreads + tid;
+    if (iv >= g.n_intervals) return;
+    if (status[img] & 1) return;                  // restart markers do not match the header: nothing can be trusted
+    const uint8_t* s = bytes + scan_off[img];
+    const long long len = scan_len[img];
+    const uint32_t* st = starts + (size_t)img * g.n_intervals;
+    const uint8_t* p0 = s + st[iv];
+    const uint8_t* p1 = (iv + 1 < g.n_intervals) ? s + st[iv + 1] - 2 : s + len;     // up to the next RSTn marker
+    const bool bad = !decode_interval(p0, p1, iv, g, *T, coef + (size_t)img * g.coef_image_stride);
+    if (bad) atomicOr(status + img, 2);
+}
+
+// ---- inverse DCT (jidctint.c, jpeg_idct_islow) ------------------------------------------------------------------------
+constexpr int CONST_BITS = 13, PASS1_BITS = 2;
+#define FIX_0_298631336 2446
+#define FIX_0_390180644 3196
+#define FIX_0_541196100 4433
+#define FIX_0_765366865 6270
+#define FIX_0_899976223 7373
+#define FIX_1_175875602 9633
+#define FIX_1_501321110 12299
+#define FIX_1_847759065 15137
+#define FIX_1_961570560 16069
+#define FIX_2_053119869 16819
+#define FIX_2_562915447 20995
+#define FIX_3_072711026 25172
+
+// 1-D pass on eight values (libjpeg works in `JLONG`; 32 bits are enough for 8-bit data: |input| <= 2^15 * 2^2 after
+// pass 1, constants < 2^15, four-term sums), results descaled by `shift` with rounding.
+FB_HD void idct8(int (&d)[8], int shift) {
+    int z2 = d[2], z3 = d[6];
+    int z1 = (z2 + z3) * FIX_0_541196100;
+    const int tmp2 = z1 + z3 * (-FIX_1_847759065);
+    const int tmp3 = z1 + z2 * FIX_0_765366865;
+    z2 = d[0];
+    z3 = d[4];
+    const int tmp0 = (z2 + z3) * (1 << CONST_BITS);
+    const int tmp1 = (z2 - z3) * (1 << CONST_BITS);
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    int t0 = d[7], t1 = d[5], t2 = d[3], t3 = d[1];
+    z1 = t0 + t3;
+    z2 = t1 + t2;
+    z3 = t0 + t2;
+    int z4 = t1 + t3;
+    const int z5 = (z3 + z4) * FIX_1_175875602;
+    t0 *= FIX_0_298631336;
+    t1 *= FIX_2_053119869;
+    t2 *= FIX_3_072711026;
+    t3 *= FIX_1_501321110;
+    z1 *= -FIX_0_899976223;
+    z2 *= -FIX_2_562915447;
+    z3 = z3 * (-FIX_1_961570560) + z5;
+    z4 = z4 * (-FIX_0_390180644) + z5;
+    t0 += z1 + z3;
+    t1 += z2 + z4;
+    t2 += z2 + z3;
+    t3 += z1 + z4;
+    const int r = 1 << (shift - 1);
+    d[0] = (tmp10 + t3 + r) >> shift;
+    d[7] = (tmp10 - t3 + r) >> shift;
+    d[1] = (tmp11 + t2 + r) >> shift;
+    d[6] = (tmp11 - t2 + r) >> shift;
+    d[2] = (tmp12 + t1 + r) >> shift;
+    d[5] = (tmp12 - t1 + r) >> shift;
+    d[3] = (tmp13 + t0 + r) >> shift;
+    d[4] = (tmp13 - t0 + r) >> shift;
+}
+
+// One 8x8 block: 64 quantised coefficients (natural order) -> 8 rows of 8 samples at `out` (row pitch `pitch` bytes).
+FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch) {
+    int ws[8][8];
+    // dequantise; pass 1 runs down the columns
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + 8 * r);
+        const uint4 qq = *reinterpret_cast<const uint4*>(q + 8 * r);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w}, qw[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ws[r][2 * j] = (int)(int16_t)(w[j] & 0xffffu) * (int)(qw[j] & 0xffffu);
+            ws[r][2 * j + 1] = (int)(int16_t)(w[j] >> 16) * (int)(qw[j] >> 16);
+        }
+    }
+#pragma unroll
+    for (int col = 0; col < 8; ++col) {
+        int d[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) d[r] = ws[r][col];
+        idct8(d, CONST_BITS - PASS1_BITS);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[r][col] = d[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = ws[r][j];
+        idct8(d, CONST_BITS + PASS1_BITS + 3);
+        uint32_t pk[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // libjpeg's range-limit table is indexed with the low 10 bits: wrap to [-512, 511], then clamp(v + 128)
+            const int v10 = ((d[j] & 1023) ^ 512) - 512;
+            const int s = v10 + 128 < 0 ? 0 : (v10 + 128 > 255 ? 255 : v10 + 128);
+            pk[j >> 2] |= (uint32_t)s << (8 * (j & 3));
+        }
+        *reinterpret_cast<uint2*>(out + (size_t)r * pitch) = make_uint2(pk[0], pk[1]);
+    }
+}
+
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t* __restrict__ coef, const int* __restrict__ table_slot,
+                                                        const JpegTableSet* __restrict__ tables, JpegGeom g, int n,
+                                                        uint8_t* __restrict__ planes) {
+    long long blocks_per_image = 0;
+    for (int c = 0; c < g.ncomp; ++c) blocks_per_image += (long long)g.blocks_w[c] * g.blocks_h[c];
+    const long long total = blocks_per_image * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int img = (int)(i / blocks_per_image);
+        long long b = i - (long long)img * blocks_per_image;
+        int c = 0;
+        while (c + 1 < g.ncomp && b >= (long long)g.blocks_w[c] * g.blocks_h[c]) {
+            b -= (long long)g.blocks_w[c] * g.blocks_h[c];
+            ++c;
+        }
+        const int bw = g.blocks_w[c];
+        const int brow = (int)(b / bw), bcol = (int)(b - (long long)brow * bw);
+        idct_block(coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c] + b * 64, tables[table_slot[img]].q[g.tq[c]],
+                   planes + (size_t)img * g.plane_image_stride + g.plane_comp_off[c] + ((size_t)brow * 8) * ((size_t)bw * 8) + (size_t)bcol * 8,
+                   (size_t)bw * 8);
+    }
+}
+
+// ---- chroma upsampling + colour conversion --------------------------------------------------------------------------------
+constexpr int SCALEBITS = 16;
+constexpr int ONE_HALF = 1 << (SCALEBITS - 1);
+constexpr int kCrR = 91881, kCbB = 116130, kCrG = 46802, kCbG = 22554;        // FIX(1.40200), FIX(1.77200), FIX(0.71414), FIX(0.34414)
+
+FB_HD int clamp8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+// MODE 0: chroma at full resolution (4:4:4); 1: h2v1 fancy; 2: h2v2 fancy.  Four consecutive pixels x0 .. x0+3 of row y
+// of one image (P = its planes) -> 12 bytes at o.
+template <int MODE>
+FB_HD void color_group(const uint8_t* P, const JpegGeom& g, int y, int x0, int bgr, uint8_t* o) {
+    const int W = g.width, H = g.height;
+    const int yp = g.blocks_w[0] * 8;                                   // plane pitches
+    const int cp = g.ncomp == 3 ? g.blocks_w[1] * 8 : 0;
+    const int cw = MODE == 0 ? W : (W + 1) / 2;                         // downsampled chroma size (ceil(size * samp / max))
+    const int ch = MODE == 2 ? (H + 1) / 2 : H;
+    const uint8_t* Y = P + g.plane_comp_off[0] + (size_t)y * yp;
+    int cbv[4] = {128, 128, 128, 128}, crv[4] = {128, 128, 128, 128};
+    if (g.ncomp == 3) {
+        const uint8_t* CB = P + g.plane_comp_off[1];
+        const uint8_t* CR = P + g.plane_comp_off[2];
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = x0 + j < W ? x0 + j : W - 1;
+                cbv[j] = CB[(size_t)y * cp + x];
+                crv[j] = CR[(size_t)y * cp + x];
+            }
+        } else {
+            // chroma columns c0-1 .. c0+2 around the two samples this group of four pixels sits on, clamped: the
+            // replicated edge columns reproduce libjpeg's first / last column special cases
+            const int c0 = x0 >> 1;
+            int cols[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 - 1 + j;
+                cols[j] = c < 0 ? 0 : (c > cw - 1 ? cw - 1 : c);
+            }
+            int sb[4], sr[4];                                   // per chroma column: the vertically filtered value
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sb[j] = CB[(size_t)y * cp + cols[j]];
+                    sr[j] = CR[(size_t)y * cp + cols[j]];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 1 + (j >> 1);                 // own chroma sample: column c0 (pixels 0,1) or c0+1 (pixels 2,3)
+                    const int nbk = (j & 1) ? k + 1 : k - 1;    // even pixel leans left (+1), odd pixel leans right (+2)
+                    const int bias = (j & 1) ? 2 : 1;
+                    cbv[j] = (3 * sb[k] + sb[nbk] + bias) >> 2;
+                    crv[j] = (3 * sr[k] + sr[nbk] + bias) >> 2;
+                }
+            } else {
+                const int cy = y >> 1;
+                int ny = (y & 1) ? cy + 1 : cy - 1;             // replicated context row at the top / bottom (jdmainct.c)
+                ny = ny < 0 ? 0 : (ny > ch - 1 ? ch - 1 : ny);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sb[j] = 3 * CB[(size_t)cy * cp + cols[j]] + CB[(size_t)ny * cp + cols[j]];
+                    sr[j] = 3 * CR[(size_t)cy * cp + cols[j]] + CR[(size_t)ny * cp + cols[j]];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 1 + (j >> 1);
+                    const int nbk = (j & 1) ? k + 1 : k - 1;
+                    const int bias = (j & 1) ? 7 : 8;
+                    cbv[j] = (3 * sb[k] + sb[nbk] + bias) >> 4;
+                    crv[j] = (3 * sr[k] + sr[nbk] + bias) >> 4;
+                }
+            }
+        }
+    }
+    uint8_t px[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int yy = Y[x0 + j < W ? x0 + j : W - 1];
+        int r = yy, gg = yy, b = yy;
+        if (g.ncomp == 3) {
+            const int cb = cbv[j] - 128, cr = crv[j] - 128;
+            r = clamp8(yy + ((kCrR * cr + ONE_HALF) >> SCALEBITS));
+            gg = clamp8(yy + ((-kCbG * cb + ONE_HALF - kCrG * cr) >> SCALEBITS));
+            b = clamp8(yy + ((kCbB * cb + ONE_HALF) >> SCALEBITS));
+        }
+        px[3 * j] = (uint8_t)(bgr ? b : r);
+        px[3 * j + 1] = (uint8_t)gg;
+        px[3 * j + 2] = (uint8_t)(bgr ? r : b);
+    }
+    if (x0 + 4 <= W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+        o32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+        o32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+        o32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    } else {
+        const int nb = 3 * (W - x0 < 4 ? W - x0 : 4);
+        for (int k = 0; k < nb; ++k) o[k] = px[k];
+    }
+}
+
+// One thread = 4 consecutive pixels of a row.
+template <int MODE>
+__global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restrict__ planes, JpegGeom g, int n, int bgr,
+                                                         uint8_t* __restrict__ out, long long out_stride) {
+    const int W = g.width, H = g.height;
+    const int groups = (W + 3) / 4;
+    const long long total = (long long)n * H * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(i % groups);
+        const long long t = i / groups;
+        const int y = (int)(t % H), img = (int)(t / H);
+        color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 4, bgr,
+                          out + (size_t)img * out_stride + ((size_t)y * W + gx * 4) * 3);
+    }
+}
+
+}  // namespace
+
+#ifndef FB_JPEG_HOST_TEST
+size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, int vs0, int restart_interval, long long max_scan_bytes) {
+    const int hmax = hs0, vmax = vs0;
+    const long long mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+    long long blocks = mcux * hmax * mcuy * vmax + (ncomp == 3 ? 2 * mcux * mcuy : 0);
+    const long long total_mcus = mcux * mcuy;
+    const long long n_iv = restart_interval > 0 ? (total_mcus + restart_interval - 1) / restart_interval : 1;
+    const long long chunks = (max_scan_bytes + kScanChunk - 1) / kScanChunk + 1;
+    auto al = [](long long x) { return (x + 255) & ~255ll; };
+    return (size_t)(al(blocks * 128 * n) + al(blocks * 64 * n) + al(n_iv * 4 * n) + al(chunks * 4 * n) + 256);
+}
+
+int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, const long long* d_scan_len, const int* d_table_slot,
+                       const void* d_tables, int n, int width, int height, int ncomp, const int* hs, const int* vs, const int* tq,
+                       const int* td, const int* ta, int restart_interval, long long max_scan_bytes, int bgr, void* d_workspace,
+                       size_t workspace_bytes, uint8_t* d_out, long long out_stride, int* d_status, cudaStream_t stream) {
+    FB_REQUIRE(d_bytes && d_scan_off && d_scan_len && d_table_slot && d_tables && d_workspace && d_out && d_status, "fb_jpeg_decode: null pointer");
+    FB_REQUIRE(n >= 1 && width >= 1 && height >= 1 && width <= 65535 && height <= 65535, "fb_jpeg_decode: bad size %dx%d", width, height);
+    FB_REQUIRE(ncomp == 1 || ncomp == 3, "fb_jpeg_decode: %d components (1 or 3)", ncomp);
+    FB_REQUIRE(out_stride >= (long long)width * height * 3, "fb_jpeg_decode: out_stride smaller than one frame");
+    JpegGeom g;
+    g.width = width;
+    g.height = height;
+    g.ncomp = ncomp;
+    for (int c = 0; c < 3; ++c) {
+        g.hs[c] = c < ncomp ? hs[c] : 1;
+        g.vs[c] = c < ncomp ? vs[c] : 1;
+        g.tq[c] = c < ncomp ? tq[c] : 0;
+        g.td[c] = c < ncomp ? td[c] : 0;
+        g.ta[c] = c < ncomp ? ta[c] : 0;
+        FB_REQUIRE(g.tq[c] >= 0 && g.tq[c] < 4 && g.td[c] >= 0 && g.td[c] < 4 && g.ta[c] >= 0 && g.ta[c] < 4, "fb_jpeg_decode: table id out of range");
+    }
+    const int hmax = g.hs[0], vmax = g.vs[0];
+    FB_REQUIRE((hmax == 1 && vmax == 1) || (hmax == 2 && vmax == 1) || (hmax == 2 && vmax == 2), "fb_jpeg_decode: luma sampling %dx%d", hmax, vmax);
+    FB_REQUIRE(ncomp == 1 || (g.hs[1] == 1 && g.vs[1] == 1 && g.hs[2] == 1 && g.vs[2] == 1), "fb_jpeg_decode: chroma sampling must be 1x1");
+    FB_REQUIRE(ncomp == 3 || (hmax == 1 && vmax == 1), "fb_jpeg_decode: a grayscale scan has 8x8 MCUs");
+    g.restart_interval = restart_interval > 0 ? restart_interval : 0;
+    g.mcux = (width + 8 * hmax - 1) / (8 * hmax);
+    g.mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+    const long long total_mcus = (long long)g.mcux * g.mcuy;
+    g.n_intervals = g.restart_interval ? (int)((total_mcus + g.restart_interval - 1) / g.restart_interval) : 1;
+    long long blocks = 0;
+    for (int c = 0; c < 3; ++c) {
+        g.blocks_w[c] = c < ncomp ? g.mcux * g.hs[c] : 0;
+        g.blocks_h[c] = c < ncomp ? g.mcuy * g.vs[c] : 0;
+        g.coef_comp_off[c] = blocks * 64;
+        g.plane_comp_off[c] = blocks * 64;
+        blocks += (long long)g.blocks_w[c] * g.blocks_h[c];
+    }
+    g.coef_image_stride = blocks * 64;
+    g.plane_image_stride = blocks * 64;
+    FB_REQUIRE(workspace_bytes >= jpeg_workspace_bytes(n, width, height, ncomp, hmax, vmax, restart_interval, max_scan_bytes),
+               "fb_jpeg_decode: workspace too small");
+    FB_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "fb_jpeg_decode: workspace must be 256-byte aligned");
+    auto al = [](long long x) { return (x + 255) & ~255ll; };
+    uint8_t* w = reinterpret_cast<uint8_t*>(d_workspace);
+    int16_t* coef = reinterpret_cast<int16_t*>(w);
+    w += al(blocks * 128 * n);
+    uint8_t* planes = w;
+    w += al(blocks * 64 * n);
+    uint32_t* starts = reinterpret_cast<uint32_t*>(w);
+    w += al((long long)g.n_intervals * 4 * n);
+    int* counts = reinterpret_cast<int*>(w);
+    const int chunks = (int)((max_scan_bytes + kScanChunk - 1) / kScanChunk + 1);
+
+    FB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int) * n, stream));
+    if (g.n_intervals > 1) {
+        dim3 grid(chunks, n);
+        jpeg_restart_scan_kernel<false><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
+        jpeg_restart_prefix_kernel<<<n, 256, 0, stream>>>(counts, chunks, g.n_intervals, starts, d_status);
+        jpeg_restart_scan_kernel<true><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
+    } else {
+        FB_CUDA_OK(cudaMemsetAsync(starts, 0, sizeof(uint32_t) * n, stream));
+    }
+    {
+        dim3 grid((g.n_intervals + kHuffThreads - 1) / kHuffThreads, n);
+        jpeg_huffman_kernel<<<grid, kHuffThreads, sizeof(JpegTableSet), stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot,
+                                                                                reinterpret_cast<const JpegTableSet*>(d_tables), starts, g, coef,
+                                                                                d_status);
+    }
+    {
+        const long long total = blocks * n;
+        long long gb = (total + 127) / 128;
+        if (gb > (long long)sm_count() * 32) gb = (long long)sm_count() * 32;
+        jpeg_idct_kernel<<<(unsigned)gb, 128, 0, stream>>>(coef, d_table_slot, reinterpret_cast<const JpegTableSet*>(d_tables), g, n, planes);
+    }
+    {
+        const long long total = (long long)n * height * ((width + 3) / 4);
+        long long gb = (total + 255) / 256;
+        if (gb > (long long)sm_count() * 32) gb = (long long)sm_count() * 32;
+        const int mode = ncomp == 1 ? 0 : (hmax == 1 ? 0 : (vmax == 1 ? 1 : 2));
+        if (mode == 0) jpeg_color_kernel<0><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        else if (mode == 1) jpeg_color_kernel<1><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        else jpeg_color_kernel<2><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+    }
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+#endif  // FB_JPEG_HOST_TEST
+
+}  // namespace fb

@@ -68,6 +68,11 @@ int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be
                     float* emb, float* raw, float* sims, cudaStream_t stream);
 int launch_embedding_heads(const float* d_x, int n, const float* w1, const float* b1, const float* w2, const float* b2,
                            const float* tags, int ntags, float* raw, float* sims, cudaStream_t stream);
+size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, int vs0, int restart_interval, long long max_scan_bytes);
+int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, const long long* d_scan_len, const int* d_table_slot,
+                       const void* d_tables, int n, int width, int height, int ncomp, const int* hs, const int* vs, const int* tq,
+                       const int* td, const int* ta, int restart_interval, long long max_scan_bytes, int bgr, void* d_workspace,
+                       size_t workspace_bytes, uint8_t* d_out, long long out_stride, int* d_status, cudaStream_t stream);
 void count_launch(int k);
 
 // Optional per-category CUDA-event timing of the library's launches (bench.py roofline): when enabled every

@@ -462,3 +462,79 @@ def phash(images, rgb_order: bool = False, debug: bool = False, tensor_cores: bo
 def phash_hex(images, rgb_order: bool = False):
     """str(imagehash.phash(img)) for each frame: 16 lowercase hex digits."""
     return ["%016x" % int(v) for v in phash(images, rgb_order=rgb_order)]
+
+
+# ---- JPEG decoding (csrc/jpeg_decode.cu) -------------------------------------------------------------------------------
+def jpeg_decode_device(dev_bytes, slot_bytes: int, infos, bgr: bool = True, out=None):
+    """Decode n same-geometry JPEG streams whose file bytes already sit in `dev_bytes` (CUDA uint8, stream i at offset
+    i * slot_bytes).  infos: the `utils.jpeg.parse` results.  Returns (frames CUDA uint8 [n,H,W,3], status CUDA int32 [n]);
+    nothing is synchronised.  EXIF orientation is NOT applied (ops.orient does that)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    from .utils import jpeg as fj
+    n = len(infos)
+    i0 = infos[0]
+    key = i0.geometry_key()
+    if any(i.geometry_key() != key for i in infos[1:]):
+        raise ValueError("jpeg_decode_device takes streams of one geometry (size, components, sampling, restart interval)")
+    dev = dev_bytes.device
+    slots, blobs = {}, []
+    table_slot = np.empty(n, np.int32)
+    for k, inf in enumerate(infos):
+        blob = inf.packed_tables
+        s = slots.get(id(blob))
+        if s is None:
+            s = slots[id(blob)] = len(blobs)
+            blobs.append(blob)
+        table_slot[k] = s
+    scan_off = np.array([k * slot_bytes + inf.scan_offset for k, inf in enumerate(infos)], np.int64)
+    scan_len = np.array([inf.scan_end - inf.scan_offset for inf in infos], np.int64)
+    if int((scan_off + scan_len).max()) > dev_bytes.numel() or int(scan_len.min()) < 0:
+        raise ValueError("jpeg_decode_device: a stream does not fit its slot")
+    meta = torch.from_numpy(np.concatenate([scan_off, scan_len])).to(dev, non_blocking=True)
+    tslot = torch.from_numpy(table_slot).to(dev, non_blocking=True)
+    tables = torch.from_numpy(np.frombuffer(b"".join(blobs), np.uint8).copy()).to(dev, non_blocking=True)
+    hmax, vmax = i0.hs[0], i0.vs[0]
+    max_scan = int(scan_len.max())
+    ws_bytes = int(lib.fb_jpeg_workspace_bytes(n, i0.width, i0.height, i0.ncomp, hmax, vmax, i0.restart_interval, max_scan))
+    arr3 = lambda v, fill: (C.c_int32 * 3)(*((list(v) + [fill] * 3)[:3]))
+    with torch.cuda.device(dev):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        frames = out if out is not None else torch.empty((n, i0.height, i0.width, 3), dtype=torch.uint8, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        _lib.check(lib.fb_jpeg_decode(_ptr(dev_bytes), C.c_void_p(meta.data_ptr()), C.c_void_p(meta.data_ptr() + 8 * n), _ptr(tslot),
+                                      _ptr(tables), n, i0.width, i0.height, i0.ncomp, C.cast(arr3(i0.hs, 1), C.c_void_p),
+                                      C.cast(arr3(i0.vs, 1), C.c_void_p), C.cast(arr3(i0.tq, 0), C.c_void_p),
+                                      C.cast(arr3(i0.td, 0), C.c_void_p), C.cast(arr3(i0.ta, 0), C.c_void_p), i0.restart_interval,
+                                      max_scan, int(bool(bgr)), _ptr(ws), ws_bytes, _ptr(frames), i0.height * i0.width * 3,
+                                      _ptr(status), _lib.stream_ptr()), "fb_jpeg_decode")
+    return frames, status
+
+
+def jpeg_decode(streams, bgr: bool = True, apply_orientation: bool = True):
+    """Decode JPEG file contents on the GPU: the pixel work of `load_image_from_path` (utils/image_loading.py:90-106) —
+    byte-exact with `np.asarray(ImageOps.exif_transpose(Image.open(f)).convert('RGB'))` (reversed to BGR when `bgr`).
+    streams: list of bytes / 1-D uint8 arrays of ONE geometry.  Returns a CUDA uint8 tensor [n,H,W,3] ([n,W,H,3] after
+    a transposing EXIF orientation).  Raises utils.jpeg.UnsupportedJpeg for streams the device decoder does not take
+    and RuntimeError for corrupt entropy data."""
+    torch = _lib.require_cuda()
+    from .utils import jpeg as fj
+    infos = [fj.parse(s) for s in streams]
+    slot = (max(len(s) for s in streams) + 255) & ~255
+    dev = torch.device("cuda", torch.cuda.current_device())
+    buf = torch.empty(len(streams) * slot, dtype=torch.uint8, device=dev)
+    for k, s in enumerate(streams):
+        a = np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray, memoryview)) else np.ascontiguousarray(s, dtype=np.uint8).reshape(-1)
+        buf[k * slot:k * slot + a.size].copy_(torch.from_numpy(a.copy() if not a.flags.writeable else a), non_blocking=True)
+    frames, status = jpeg_decode_device(buf, slot, infos, bgr=bgr)
+    st = status.cpu().numpy()
+    if st.any():
+        bad = int(np.flatnonzero(st)[0])
+        raise RuntimeError(f"JPEG stream {bad}: " + ("restart markers do not match the DRI header" if st[bad] & 1 else "invalid Huffman data"))
+    if apply_orientation:
+        codes = {i.orientation for i in infos}
+        if codes != {1}:
+            if len(codes) != 1:
+                raise ValueError("jpeg_decode: streams of one call must share their EXIF orientation")
+            frames = orient(frames, codes.pop())
+    return frames
