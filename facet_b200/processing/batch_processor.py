@@ -170,10 +170,13 @@ class BatchProcessor:
         of one blocking pass per batch — the role of the reference's loader threads / GPU thread / result queue
         (batch_processor.py:123-167, 362-455):
 
-          copy stream     each item's frame goes host -> device (async when the array is in pinned memory) into one of two
-                          `chunk`-frame staging buffers while the previous chunk is being processed
-          compute stream  technical pass + pHash + CLIP preprocess per chunk; the ViT tower + heads once `vit_batch`
-                          frames have been preprocessed (frames of different shapes share a ViT launch)
+          copy stream     each item's frame — or, for items that carry `jpeg` (the FILE BYTES: bytes or a uint8 array, e.g. a
+                          view of a pinned read buffer), its compressed stream — goes host -> device (async from pinned
+                          memory) into one of two `chunk`-slot staging buffers while the previous chunk is being processed
+          compute stream  JPEG chunks are decoded on the device first (fb_jpeg_decode + fb_orient for the EXIF orientation:
+                          the pixel work of utils/image_loading.py:90-106); then technical pass + pHash + CLIP preprocess per
+                          chunk; the ViT tower + heads once `vit_batch` frames have been preprocessed (frames of different
+                          shapes share a ViT launch)
           D2H stream      ONE packed record per image (histogram, sums, hash, embedding, aesthetic, tag similarities;
                           about 5 KB) into pinned host memory per ViT batch
           worker thread   closed-form metric dicts, tag selection, aggregate + category, the result columns
@@ -181,7 +184,8 @@ class BatchProcessor:
         `self.metrics` gains h2d_bytes / d2h_bytes of the call."""
         import queue
         import threading
-        from .. import _lib
+        from .. import _lib, ops
+        from ..utils import jpeg as fj
         torch = _lib.require_cuda()
         scorer = self.scorer
         dev = scorer.device
@@ -207,13 +211,17 @@ class BatchProcessor:
                 der = a[:, 1056:1088].view(np.float64).copy()
                 hashes = a[:, 1088:1096].view(np.uint64).reshape(-1).copy()
                 raw = a[:, 1096:1100].view(np.float32).reshape(-1).copy()
+                status = a[:, 1100:1104].view(np.int32).reshape(-1).copy()
                 emb = a[:, 1104:1104 + 3072].view(np.float32).copy()
                 sims = a[:, 1104 + 3072:].view(np.float32).copy() if n_tags else None
             finally:
                 st["free_packs"].put(pack)
             by_shape = defaultdict(list)
             for k, (pos, item, h, w) in enumerate(metas):
-                by_shape[(h, w)].append(k)
+                if status[k]:             # fb_jpeg_decode flagged the stream (utils/image_loading.py returns None for unreadable files)
+                    results[pos] = {"path": item.get("path"), "error": "Failed to load image (corrupt JPEG data)"}
+                else:
+                    by_shape[(h, w)].append(k)
             for (h, w), ks in by_shape.items():
                 sel = np.asarray(ks)
                 try:
@@ -238,7 +246,7 @@ class BatchProcessor:
         th = threading.Thread(target=worker, daemon=True)
         th.start()
 
-        cur = {"shape": None, "slot": 0, "metas": [], "bufs": None}
+        cur = {"shape": None, "slot": 0, "metas": [], "bufs": None, "infos": None, "slot_bytes": 0}
         acc = {"px": [], "metas": []}         # preprocessed chunks waiting for the ViT launch
 
         def flush_vit():
@@ -252,7 +260,7 @@ class BatchProcessor:
                 m = len(metas)
                 parts = [cat("hist256").view(torch.uint8).reshape(m, 1024), cat("sums").view(torch.uint8).reshape(m, 32),
                          cat("derived").view(torch.uint8).reshape(m, 32), cat("phash").reshape(m, 1).view(torch.uint8),
-                         vit["aesthetic_raw"].reshape(m, 1).view(torch.uint8), torch.zeros((m, 4), dtype=torch.uint8, device=dev),
+                         vit["aesthetic_raw"].reshape(m, 1).view(torch.uint8), cat("status").reshape(m, 1).view(torch.uint8),
                          vit["embedding"].view(torch.uint8).reshape(m, 3072)]
                 if n_tags:
                     parts.append(vit["tag_sims"].contiguous().view(torch.uint8).reshape(m, 4 * n_tags))
@@ -278,10 +286,22 @@ class BatchProcessor:
                 return
             slot, bufs = cur["slot"], cur["bufs"]
             cur["metas"], cur["shape"] = [], None
+            cur_infos = cur["infos"]
             try:
                 bufs["ready"][slot].record(copy_s)
                 compute.wait_event(bufs["ready"][slot])
-                px = scorer.pixel_passes_device(bufs["frames"][slot][:len(metas)], rgb_order=rgb_order)
+                if cur_infos is not None:
+                    # file bytes -> frames on the device (entropy decoding, IDCT, upsampling, colour conversion, EXIF transpose)
+                    frames, status = ops.jpeg_decode_device(bufs["frames"][slot], cur["slot_bytes"], cur_infos, bgr=not rgb_order)
+                    code = cur_infos[0].orientation
+                    if code != 1:
+                        frames = ops.orient(frames, code)
+                    metas = [(pos, item, int(frames.shape[1]), int(frames.shape[2])) for pos, item, _h, _w in metas]
+                else:
+                    frames = bufs["frames"][slot][:len(metas)]
+                    status = torch.zeros((len(metas),), dtype=torch.int32, device=dev)
+                px = scorer.pixel_passes_device(frames, rgb_order=rgb_order)
+                px["status"] = status
                 bufs["free"][slot].record(compute)
                 bufs["used"][slot] = True
                 acc["px"].append(px)
@@ -302,26 +322,61 @@ class BatchProcessor:
             if "error" in item:
                 results[pos] = {"path": item.get("path"), "error": item["error"]}
                 continue
-            if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
-                results[pos] = {"path": item.get("path"), "error": "Failed to load image"}
-                continue
-            h, w = int(img.shape[0]), int(img.shape[1])
-            if h < 2 or w < 2:
-                results[pos] = {"path": item.get("path"), "error": "image smaller than 2x2"}
-                continue
-            if cur["metas"] and (cur["shape"] != (h, w) or len(cur["metas"]) == chunk):
+            info = None
+            if item.get("jpeg") is not None:
+                # the loader handed over file bytes: decode on the device unless the stream is of a kind only the CPU loader takes
+                try:
+                    info = fj.parse(item["jpeg"])
+                except fj.UnsupportedJpeg as exc:
+                    if img is None:
+                        results[pos] = {"path": item.get("path"), "error": f"Failed to load image ({exc})"}
+                        continue
+            if info is not None:
+                data = item["jpeg"]
+                nbytes = len(data)
+                key = ("jpeg",) + info.geometry_key() + (info.orientation,)
+                h, w = info.height, info.width
+                if h < 2 or w < 2:
+                    results[pos] = {"path": item.get("path"), "error": "image smaller than 2x2"}
+                    continue
+            else:
+                if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+                    results[pos] = {"path": item.get("path"), "error": "Failed to load image"}
+                    continue
+                h, w = int(img.shape[0]), int(img.shape[1])
+                if h < 2 or w < 2:
+                    results[pos] = {"path": item.get("path"), "error": "image smaller than 2x2"}
+                    continue
+                key = ("raw", h, w)
+            if cur["metas"] and (cur["shape"] != key or len(cur["metas"]) == chunk or
+                                 (info is not None and nbytes > cur["slot_bytes"])):
                 flush_chunk()
             if not cur["metas"]:
-                bufs = self._chunk_buffers(torch, dev, h, w, chunk)
+                if info is not None:
+                    # slots of a power-of-two size >= the stream (streams of one camera setting vary by a few 10 %)
+                    slot_bytes = max(1 << 20, 1 << int(nbytes * 5 // 4).bit_length())
+                    bufs = self._chunk_buffers(torch, dev, ("jpeg", slot_bytes, chunk), (chunk * slot_bytes,))
+                    cur.update(infos=[], slot_bytes=slot_bytes)
+                else:
+                    bufs = self._chunk_buffers(torch, dev, ("raw", h, w, chunk), (chunk, h, w, 3))
+                    cur.update(infos=None, slot_bytes=0)
                 slot = bufs["next"]
                 bufs["next"] = slot ^ 1
-                cur.update(shape=(h, w), slot=slot, bufs=bufs)
+                cur.update(shape=key, slot=slot, bufs=bufs)
                 if bufs["used"][slot]:
                     copy_s.wait_event(bufs["free"][slot])         # the compute stream is done with this staging buffer
             k = len(cur["metas"])
             with torch.cuda.stream(copy_s):
-                cur["bufs"]["frames"][cur["slot"]][k].copy_(torch.from_numpy(np.ascontiguousarray(img)), non_blocking=True)
-            self.metrics["h2d_bytes"] += h * w * 3
+                if info is not None:
+                    src = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.asarray(data, np.uint8).reshape(-1)
+                    if not src.flags.writeable:
+                        src = src.copy()
+                    cur["bufs"]["frames"][cur["slot"]][k * cur["slot_bytes"]:k * cur["slot_bytes"] + nbytes].copy_(torch.from_numpy(src), non_blocking=True)
+                    cur["infos"].append(info)
+                    self.metrics["h2d_bytes"] += nbytes
+                else:
+                    cur["bufs"]["frames"][cur["slot"]][k].copy_(torch.from_numpy(np.ascontiguousarray(img)), non_blocking=True)
+                    self.metrics["h2d_bytes"] += h * w * 3
             cur["metas"].append((pos, item, h, w))
         flush_chunk()
         flush_vit()
@@ -344,15 +399,14 @@ class BatchProcessor:
             self._stream = st
         return st
 
-    def _chunk_buffers(self, torch, dev, h, w, chunk):
+    def _chunk_buffers(self, torch, dev, key, shape):
         chunks = self._stream["chunks"]
-        key = (h, w, chunk)
         if key not in chunks:
             if len(chunks) >= 4:                       # bound the staging memory when many frame shapes go by
                 torch.cuda.current_stream(dev).synchronize()
                 self._stream["copy"].synchronize()
                 chunks.clear()
-            chunks[key] = {"frames": [torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)],
+            chunks[key] = {"frames": [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(2)],
                            "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
                            "used": [False, False], "next": 0}
             # the caching allocator may hand out memory that kernels already queued on the compute stream still use

@@ -179,3 +179,47 @@ def test_batch_processor_streamed_path_equals_the_blocking_one(scorer):
             for k in w_:
                 assert g[k] == w_[k], (chunk, vb, w_.get("path"), k)
     assert bp.metrics["h2d_bytes"] == 3 * sum(h * w * 3 for h, w in shapes) and bp.metrics["d2h_bytes"] > 0
+
+
+def test_streamed_path_takes_jpeg_file_bytes(scorer):
+    """Items that carry the FILE BYTES (`jpeg`) are decoded on the device; results equal those of the same frames decoded
+    by Pillow on the host (the reference's loader, utils/image_loading.py:90-106) and passed as `img_cv`, EXIF orientation
+    included.  Progressive files fall back to the item's `img_cv`, corrupt ones become error items."""
+    import io
+    import torch
+    from PIL import Image, ImageOps
+    from facet_b200.processing.batch_processor import BatchProcessor
+    sc, tags, names = scorer
+    items_jpeg, items_raw = [], []
+    for i, (h, w, kw, code) in enumerate([(256, 384, {"quality": 90, "restart_marker_blocks": 6}, 1), (256, 384, {"quality": 90, "restart_marker_blocks": 6}, 1),
+                                          (200, 320, {"quality": 75, "subsampling": 0, "restart_marker_rows": 1}, 1),
+                                          (256, 384, {"quality": 90, "restart_marker_blocks": 6}, 6), (120, 131, {"quality": 85}, 1)]):
+        rgb = synth_image_bgr(70 + i, h, w)[:, :, ::-1].copy()
+        ex = Image.Exif()
+        ex[0x0112] = code
+        buf = io.BytesIO()
+        Image.fromarray(rgb).save(buf, "JPEG", exif=ex, **kw)
+        data = buf.getvalue()
+        decoded = np.asarray(ImageOps.exif_transpose(Image.open(io.BytesIO(data))).convert("RGB"))[:, :, ::-1].copy()
+        pinned = torch.empty(len(data), dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = np.frombuffer(data, np.uint8)
+        items_jpeg.append({"path": f"/x/j{i}.jpg", "jpeg": pinned.numpy() if i % 2 else data, "_keep": pinned})
+        items_raw.append({"path": f"/x/j{i}.jpg", "img_cv": decoded})
+    # progressive stream + host-decoded frame, corrupt stream, progressive stream without a frame
+    rgb = synth_image_bgr(90, 64, 96)[:, :, ::-1].copy()
+    buf = io.BytesIO()
+    Image.fromarray(rgb).save(buf, "JPEG", progressive=True)
+    items_jpeg.append({"path": "/x/prog.jpg", "jpeg": buf.getvalue(), "img_cv": rgb[:, :, ::-1].copy()})
+    items_raw.append({"path": "/x/prog.jpg", "img_cv": rgb[:, :, ::-1].copy()})
+    good = items_jpeg[0]["jpeg"]
+    items_jpeg.append({"path": "/x/corrupt.jpg", "jpeg": good[:len(good) // 2] + b"\xff\xd9"})
+    items_jpeg.append({"path": "/x/prog_only.jpg", "jpeg": buf.getvalue()})
+    bp = BatchProcessor(sc, batch_size=16)
+    want = bp.process_items_streamed(items_raw, chunk=4, vit_batch=8)
+    got = bp.process_items_streamed(items_jpeg, chunk=4, vit_batch=8)
+    assert len(got) == len(items_jpeg)
+    for g, w_ in zip(got[:len(want)], want):
+        assert "error" not in g, g
+        for k in w_:
+            assert g[k] == w_[k], (w_["path"], k)
+    assert "error" in got[-2] and "error" in got[-1]
