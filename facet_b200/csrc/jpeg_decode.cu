@@ -38,21 +38,12 @@ static_assert(sizeof(JpegHuff) == 1424 && sizeof(JpegTableSet) == 11904, "layout
 
 #define FB_HD __host__ __device__ __forceinline__
 
+__device__ const uint8_t d_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
+                                     13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
+                                     52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 static const uint8_t h_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
                                      13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
                                      52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-__constant__ uint8_t c_zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
-                                     13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
-                                     52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-FB_HD int zigzag_at(int k) {
-#ifdef __CUDA_ARCH__
-    return c_zigzag[k];
-#else
-    return h_zigzag[k];
-#endif
-}
-
 struct BitReader {
     const uint8_t* p;
     const uint8_t* end;
@@ -60,9 +51,34 @@ struct BitReader {
     int n;
 };
 
-// Top up to > 32 buffered bits.  Inside an interval the only 0xFF bytes are stuffed ones (followed by 0x00); past
-// the end zeros are fed (T.81 F.2.2.5).
+// Four bytes at p (any alignment) as a big-endian word.  The device version reads the two aligned words around p: up to 7
+// bytes past p + 3, so stream buffers carry 8 bytes of slack.
+FB_HD uint32_t load_be32(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t le = __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+    return __byte_perm(le, 0u, 0x0123);
+#else
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+#endif
+}
+
+// Top up to > 32 buffered bits.  Fast path: the next four bytes hold no 0xFF (true for ~98 % of the positions), so they
+// enter the buffer as one word.  Otherwise byte by byte: inside an interval the only 0xFF bytes are stuffed ones (followed
+// by 0x00); past the end zeros are fed (T.81 F.2.2.5).
 FB_HD void refill(BitReader& br) {
+    if (br.n > 32) return;
+    if (br.p + 4 <= br.end) {
+        const uint32_t w = load_be32(br.p);
+        const uint32_t x = ~w;                                   // a 0xFF byte of w is a zero byte of x
+        if (!((x - 0x01010101u) & ~x & 0x80808080u)) {
+            br.acc = (br.acc << 32) | w;
+            br.n += 32;
+            br.p += 4;
+            return;
+        }
+    }
     while (br.n <= 32) {
         uint32_t b = 0;
         if (br.p < br.end) {
@@ -109,45 +125,49 @@ struct JpegGeom {
 };
 
 // ---- restart scan ---------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256, kScanBytesPerThread = 64, kScanChunk = kScanThreads * kScanBytesPerThread;
+constexpr int kScanThreads = 256, kScanWarpBytes = 2048, kScanChunk = (kScanThreads / 32) * kScanWarpBytes;      // 16 KB per CTA
 
-__device__ __forceinline__ int count_markers(const uint8_t* s, long long len, long long lo, long long hi, uint32_t* out, int base) {
-    int c = 0;
-    for (long long p = lo; p < hi && p + 1 < len; ++p) {
-        if (s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0) {
-            if (out) out[base + c] = (uint32_t)(p + 2);
-            ++c;
-        }
-    }
-    return c;
-}
-
+// RSTn markers (0xFF 0xD0..0xD7) of one 16 KB chunk of one stream.  A warp walks its 2 KB in 32-byte steps (coalesced byte
+// loads); ballots keep the markers in stream order.  WRITE = false: counts[img][chunk] = number of markers; WRITE = true
+// (after the prefix kernel turned counts into exclusive offsets): starts[img][1 + k] = byte after the k-th marker.
 template <bool WRITE>
 __global__ void __launch_bounds__(kScanThreads) jpeg_restart_scan_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
                                                                          const long long* __restrict__ scan_len, int chunks, int n_intervals,
                                                                          int* __restrict__ counts, uint32_t* __restrict__ starts) {
-    __shared__ int s_cnt[kScanThreads];
-    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_warp[kScanThreads / 32];
+    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t* s = bytes + scan_off[img];
     const long long len = scan_len[img];
-    const long long lo = (long long)chunk * kScanChunk + (long long)tid * kScanBytesPerThread;
-    const long long hi = min(lo + kScanBytesPerThread, len);
-    const int mine = lo < len ? count_markers(s, len, lo, hi, nullptr, 0) : 0;
-    s_cnt[tid] = mine;
-    __syncthreads();
-    // inclusive scan over the block (Hillis-Steele; 256 entries)
-    for (int o = 1; o < kScanThreads; o <<= 1) {
-        const int v = tid >= o ? s_cnt[tid - o] : 0;
-        __syncthreads();
-        s_cnt[tid] += v;
-        __syncthreads();
+    const long long w0 = (long long)chunk * kScanChunk + (long long)warp * kScanWarpBytes;
+    int cnt = 0;
+    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
+        const long long p = w0 + it * 32 + lane;
+        const bool hit = p + 1 < len && s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0;
+        cnt += __popc(__ballot_sync(0xffffffffu, hit));
     }
+    if (lane == 0) s_warp[warp] = cnt;
+    __syncthreads();
     if (!WRITE) {
-        if (tid == kScanThreads - 1) counts[(size_t)img * chunks + chunk] = s_cnt[tid];
-    } else if (mine) {
-        const int base = counts[(size_t)img * chunks + chunk] + s_cnt[tid] - mine;       // exclusive position among the image's markers
-        if (base + mine <= n_intervals - 1)
-            count_markers(s, len, lo, hi, starts + (size_t)img * n_intervals + 1, base);
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < kScanThreads / 32; ++w) tot += s_warp[w];
+            counts[(size_t)img * chunks + chunk] = tot;
+        }
+        return;
+    }
+    int base = counts[(size_t)img * chunks + chunk];
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    if (cnt == 0) return;
+    uint32_t* out = starts + (size_t)img * n_intervals + 1;
+    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
+        const long long p = w0 + it * 32 + lane;
+        const bool hit = p + 1 < len && s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0;
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int k = base + __popc(m & ((1u << lane) - 1u));
+            if (k < n_intervals - 1) out[k] = (uint32_t)(p + 2);
+        }
+        base += __popc(m);
     }
 }
 
@@ -181,9 +201,11 @@ __global__ void __launch_bounds__(256) jpeg_restart_prefix_kernel(int* __restric
     }
 }
 
-// Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside).  Writes whole
-// 8x8 blocks (zeros included) of quantised coefficients in natural order.  Returns false on invalid Huffman data.
-FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, int16_t* cimg) {
+// Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside).  Non-zero
+// quantised coefficients are stored in natural order into the (pre-zeroed) coefficient area of the image; `zz` is the
+// zigzag table (shared memory on the device).  Returns false on invalid Huffman data.
+FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, const uint8_t* zz,
+                           int16_t* cimg) {
     BitReader br;
     br.p = p0;
     br.end = p1;
@@ -193,7 +215,6 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     const int m0 = g.restart_interval ? iv * g.restart_interval : 0;
     const int m1 = g.restart_interval ? (m0 + g.restart_interval < total_mcus ? m0 + g.restart_interval : total_mcus) : total_mcus;
     int pred[3] = {0, 0, 0};
-    __align__(16) int16_t blk[64];
     for (int m = m0; m < m1; ++m) {
         const int my = m / g.mcux, mx = m - my * g.mcux;
         for (int c = 0; c < g.ncomp; ++c) {
@@ -201,8 +222,8 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
             const JpegHuff& ha = T.ac[g.ta[c]];
             for (int by = 0; by < g.vs[c]; ++by) {
                 for (int bx = 0; bx < g.hs[c]; ++bx) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(blk)[i] = make_uint4(0u, 0u, 0u, 0u);
+                    const size_t b = (size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx);
+                    int16_t* blk = cimg + g.coef_comp_off[c] + b * 64;
                     refill(br);
                     const int t = decode_symbol(br, hd);
                     if (t < 0 || t > 15) return false;
@@ -210,7 +231,7 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
                         refill(br);
                         pred[c] += receive_extend(br, t);
                     }
-                    blk[0] = (int16_t)pred[c];
+                    if (pred[c]) blk[0] = (int16_t)pred[c];
                     int k = 1;
                     while (k < 64) {
                         refill(br);
@@ -224,13 +245,9 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
                         }
                         k += r;
                         if (k > 63) return false;
-                        blk[zigzag_at(k)] = (int16_t)receive_extend(br, sz);      // >= 16 bits are still buffered after the symbol
+                        blk[zz[k]] = (int16_t)receive_extend(br, sz);      // >= 16 bits are still buffered after the symbol
                         ++k;
                     }
-                    const size_t b = (size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx);
-                    uint4* dst = reinterpret_cast<uint4*>(cimg + g.coef_comp_off[c] + b * 64);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(blk)[i];
                 }
             }
         }
@@ -246,8 +263,10 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
                                                                     const JpegTableSet* __restrict__ tables, const uint32_t* __restrict__ starts,
                                                                     JpegGeom g, int16_t* __restrict__ coef, int* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ uint8_t s_zz[64];
     JpegTableSet* T = reinterpret_cast<JpegTableSet*>(s_raw);
     const int img = blockIdx.y, tid = threadIdx.x;
+    if (tid < 64) s_zz[tid] = d_zigzag[tid];
     {
         const uint4* src = reinterpret_cast<const uint4*>(tables + table_slot[img]);
         uint4* dst = reinterpret_cast<uint4*>(s_raw);
@@ -262,7 +281,7 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
     const uint32_t* st = starts + (size_t)img * g.n_intervals;
     const uint8_t* p0 = s + st[iv];
     const uint8_t* p1 = (iv + 1 < g.n_intervals) ? s + st[iv + 1] - 2 : s + len;     // up to the next RSTn marker
-    const bool bad = !decode_interval(p0, p1, iv, g, *T, coef + (size_t)img * g.coef_image_stride);
+    const bool bad = !decode_interval(p0, p1, iv, g, *T, s_zz, coef + (size_t)img * g.coef_image_stride);
     if (bad) atomicOr(status + img, 2);
 }
 
@@ -393,65 +412,86 @@ constexpr int kCrR = 91881, kCbB = 116130, kCrG = 46802, kCbG = 22554;        //
 
 FB_HD int clamp8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
-// MODE 0: chroma at full resolution (4:4:4); 1: h2v1 fancy; 2: h2v2 fancy.  Four consecutive pixels x0 .. x0+3 of row y
-// of one image (P = its planes) -> 12 bytes at o.
+// Six chroma samples of one plane row: columns c0-1 .. c0+4 (c0 a multiple of 4) clamped to [0, cw-1] — the replicated edge
+// columns reproduce libjpeg's first / last column special cases.  One aligned word + two bytes when the row has no edge here.
+FB_HD void chroma_cols(const uint8_t* row, int c0, int cw, int (&v)[6]) {
+    if (c0 >= 1 && c0 + 4 <= cw - 1) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(row + c0);
+        v[0] = row[c0 - 1];
+        v[1] = w & 255u;
+        v[2] = (w >> 8) & 255u;
+        v[3] = (w >> 16) & 255u;
+        v[4] = w >> 24;
+        v[5] = row[c0 + 4];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int c = c0 - 1 + j;
+            v[j] = row[c < 0 ? 0 : (c > cw - 1 ? cw - 1 : c)];
+        }
+    }
+}
+
+// MODE 0: chroma at full resolution (4:4:4); 1: h2v1 fancy; 2: h2v2 fancy.  Eight consecutive pixels x0 .. x0+7 (x0 a multiple
+// of 8) of row y of one image (P = its planes) -> 24 bytes at o.
 template <int MODE>
 FB_HD void color_group(const uint8_t* P, const JpegGeom& g, int y, int x0, int bgr, uint8_t* o) {
     const int W = g.width, H = g.height;
-    const int yp = g.blocks_w[0] * 8;                                   // plane pitches
+    const int yp = g.blocks_w[0] * 8;                                   // plane pitches (multiples of 8)
     const int cp = g.ncomp == 3 ? g.blocks_w[1] * 8 : 0;
     const int cw = MODE == 0 ? W : (W + 1) / 2;                         // downsampled chroma size (ceil(size * samp / max))
     const int ch = MODE == 2 ? (H + 1) / 2 : H;
-    const uint8_t* Y = P + g.plane_comp_off[0] + (size_t)y * yp;
-    int cbv[4] = {128, 128, 128, 128}, crv[4] = {128, 128, 128, 128};
+    int yy[8], cbv[8], crv[8];
+    {
+        const uint2 w = *reinterpret_cast<const uint2*>(P + g.plane_comp_off[0] + (size_t)y * yp + x0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            yy[j] = (w.x >> (8 * j)) & 255u;
+            yy[4 + j] = (w.y >> (8 * j)) & 255u;
+        }
+    }
     if (g.ncomp == 3) {
         const uint8_t* CB = P + g.plane_comp_off[1];
         const uint8_t* CR = P + g.plane_comp_off[2];
         if (MODE == 0) {
+            const uint2 wb = *reinterpret_cast<const uint2*>(CB + (size_t)y * cp + x0);
+            const uint2 wr = *reinterpret_cast<const uint2*>(CR + (size_t)y * cp + x0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int x = x0 + j < W ? x0 + j : W - 1;
-                cbv[j] = CB[(size_t)y * cp + x];
-                crv[j] = CR[(size_t)y * cp + x];
+                cbv[j] = (wb.x >> (8 * j)) & 255u;
+                cbv[4 + j] = (wb.y >> (8 * j)) & 255u;
+                crv[j] = (wr.x >> (8 * j)) & 255u;
+                crv[4 + j] = (wr.y >> (8 * j)) & 255u;
             }
         } else {
-            // chroma columns c0-1 .. c0+2 around the two samples this group of four pixels sits on, clamped: the
-            // replicated edge columns reproduce libjpeg's first / last column special cases
             const int c0 = x0 >> 1;
-            int cols[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 - 1 + j;
-                cols[j] = c < 0 ? 0 : (c > cw - 1 ? cw - 1 : c);
-            }
-            int sb[4], sr[4];                                   // per chroma column: the vertically filtered value
+            int sb[6], sr[6];                                   // per chroma column: the vertically filtered value
             if (MODE == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sb[j] = CB[(size_t)y * cp + cols[j]];
-                    sr[j] = CR[(size_t)y * cp + cols[j]];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = 1 + (j >> 1);                 // own chroma sample: column c0 (pixels 0,1) or c0+1 (pixels 2,3)
-                    const int nbk = (j & 1) ? k + 1 : k - 1;    // even pixel leans left (+1), odd pixel leans right (+2)
-                    const int bias = (j & 1) ? 2 : 1;
-                    cbv[j] = (3 * sb[k] + sb[nbk] + bias) >> 2;
-                    crv[j] = (3 * sr[k] + sr[nbk] + bias) >> 2;
-                }
+                chroma_cols(CB + (size_t)y * cp, c0, cw, sb);
+                chroma_cols(CR + (size_t)y * cp, c0, cw, sr);
             } else {
                 const int cy = y >> 1;
                 int ny = (y & 1) ? cy + 1 : cy - 1;             // replicated context row at the top / bottom (jdmainct.c)
                 ny = ny < 0 ? 0 : (ny > ch - 1 ? ch - 1 : ny);
+                int a[6], b[6];
+                chroma_cols(CB + (size_t)cy * cp, c0, cw, a);
+                chroma_cols(CB + (size_t)ny * cp, c0, cw, b);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sb[j] = 3 * CB[(size_t)cy * cp + cols[j]] + CB[(size_t)ny * cp + cols[j]];
-                    sr[j] = 3 * CR[(size_t)cy * cp + cols[j]] + CR[(size_t)ny * cp + cols[j]];
-                }
+                for (int j = 0; j < 6; ++j) sb[j] = 3 * a[j] + b[j];
+                chroma_cols(CR + (size_t)cy * cp, c0, cw, a);
+                chroma_cols(CR + (size_t)ny * cp, c0, cw, b);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = 1 + (j >> 1);
-                    const int nbk = (j & 1) ? k + 1 : k - 1;
+                for (int j = 0; j < 6; ++j) sr[j] = 3 * a[j] + b[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 1 + (j >> 1);                     // own chroma sample: column c0 + j / 2
+                const int nbk = (j & 1) ? k + 1 : k - 1;        // even pixel leans left, odd pixel leans right
+                if (MODE == 1) {
+                    const int bias = (j & 1) ? 2 : 1;
+                    cbv[j] = (3 * sb[k] + sb[nbk] + bias) >> 2;
+                    crv[j] = (3 * sr[k] + sr[nbk] + bias) >> 2;
+                } else {
                     const int bias = (j & 1) ? 7 : 8;
                     cbv[j] = (3 * sb[k] + sb[nbk] + bias) >> 4;
                     crv[j] = (3 * sr[k] + sr[nbk] + bias) >> 4;
@@ -459,45 +499,47 @@ FB_HD void color_group(const uint8_t* P, const JpegGeom& g, int y, int x0, int b
             }
         }
     }
-    uint8_t px[12];
+    uint32_t pk[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int yy = Y[x0 + j < W ? x0 + j : W - 1];
-        int r = yy, gg = yy, b = yy;
+    for (int j = 0; j < 8; ++j) {
+        int r = yy[j], gg = yy[j], b = yy[j];
         if (g.ncomp == 3) {
             const int cb = cbv[j] - 128, cr = crv[j] - 128;
-            r = clamp8(yy + ((kCrR * cr + ONE_HALF) >> SCALEBITS));
-            gg = clamp8(yy + ((-kCbG * cb + ONE_HALF - kCrG * cr) >> SCALEBITS));
-            b = clamp8(yy + ((kCbB * cb + ONE_HALF) >> SCALEBITS));
+            r = clamp8(yy[j] + ((kCrR * cr + ONE_HALF) >> SCALEBITS));
+            gg = clamp8(yy[j] + ((-kCbG * cb + ONE_HALF - kCrG * cr) >> SCALEBITS));
+            b = clamp8(yy[j] + ((kCbB * cb + ONE_HALF) >> SCALEBITS));
         }
-        px[3 * j] = (uint8_t)(bgr ? b : r);
-        px[3 * j + 1] = (uint8_t)gg;
-        px[3 * j + 2] = (uint8_t)(bgr ? r : b);
+        const int c3[3] = {bgr ? b : r, gg, bgr ? r : b};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int byte = 3 * j + e;
+            pk[byte >> 2] |= (uint32_t)c3[e] << (8 * (byte & 3));
+        }
     }
-    if (x0 + 4 <= W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-        o32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
-        o32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
-        o32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    if (x0 + 8 <= W && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+        uint2* o64 = reinterpret_cast<uint2*>(o);
+        o64[0] = make_uint2(pk[0], pk[1]);
+        o64[1] = make_uint2(pk[2], pk[3]);
+        o64[2] = make_uint2(pk[4], pk[5]);
     } else {
-        const int nb = 3 * (W - x0 < 4 ? W - x0 : 4);
-        for (int k = 0; k < nb; ++k) o[k] = px[k];
+        const int nb = 3 * (W - x0 < 8 ? W - x0 : 8);
+        for (int k = 0; k < nb; ++k) o[k] = (uint8_t)(pk[k >> 2] >> (8 * (k & 3)));
     }
 }
 
-// One thread = 4 consecutive pixels of a row.
+// One thread = 8 consecutive pixels of a row.
 template <int MODE>
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restrict__ planes, JpegGeom g, int n, int bgr,
                                                          uint8_t* __restrict__ out, long long out_stride) {
     const int W = g.width, H = g.height;
-    const int groups = (W + 3) / 4;
+    const int groups = (W + 7) / 8;
     const long long total = (long long)n * H * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int gx = (int)(i % groups);
         const long long t = i / groups;
         const int y = (int)(t % H), img = (int)(t / H);
-        color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 4, bgr,
-                          out + (size_t)img * out_stride + ((size_t)y * W + gx * 4) * 3);
+        color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 8, bgr,
+                          out + (size_t)img * out_stride + ((size_t)y * W + gx * 8) * 3);
     }
 }
 
@@ -569,6 +611,7 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
     const int chunks = (int)((max_scan_bytes + kScanChunk - 1) / kScanChunk + 1);
 
     FB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int) * n, stream));
+    FB_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)blocks * 128 * n, stream));      // the entropy decoder stores non-zero coefficients only
     if (g.n_intervals > 1) {
         dim3 grid(chunks, n);
         jpeg_restart_scan_kernel<false><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
@@ -590,7 +633,7 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         jpeg_idct_kernel<<<(unsigned)gb, 128, 0, stream>>>(coef, d_table_slot, reinterpret_cast<const JpegTableSet*>(d_tables), g, n, planes);
     }
     {
-        const long long total = (long long)n * height * ((width + 3) / 4);
+        const long long total = (long long)n * height * ((width + 7) / 8);
         long long gb = (total + 255) / 256;
         if (gb > (long long)sm_count() * 32) gb = (long long)sm_count() * 32;
         const int mode = ncomp == 1 ? 0 : (hmax == 1 ? 0 : (vmax == 1 ? 1 : 2));

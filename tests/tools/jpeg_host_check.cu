@@ -69,11 +69,12 @@ int main(int argc, char** argv) {
         return 3;
     }
     int16_t* coef = (int16_t*)aligned_alloc(16, (size_t)blocks * 128 + 16);
-    uint8_t* planes = (uint8_t*)aligned_alloc(16, (size_t)blocks * 64 + 16);
+    memset(coef, 0, (size_t)blocks * 128 + 16);
+    uint8_t* planes = (uint8_t*)aligned_alloc(256, ((size_t)blocks * 64 + 511) & ~(size_t)255);
     for (int iv = 0; iv < g.n_intervals; ++iv) {
         const uint8_t* p0 = scan.data() + starts[iv];
         const uint8_t* p1 = iv + 1 < g.n_intervals ? scan.data() + starts[iv + 1] - 2 : scan.data() + len;
-        if (!decode_interval(p0, p1, iv, g, *T, coef)) {
+        if (!decode_interval(p0, p1, iv, g, *T, h_zigzag, coef)) {
             fprintf(stderr, "bad Huffman data in interval %d\n", iv);
             return 4;
         }
@@ -85,10 +86,10 @@ int main(int argc, char** argv) {
             idct_block(coef + g.coef_comp_off[c] + b * 64, T->q[g.tq[c]], planes + g.plane_comp_off[c] + (size_t)brow * 8 * bw * 8 + (size_t)bcol * 8,
                        (size_t)bw * 8);
         }
-    std::vector<uint8_t> out((size_t)g.width * g.height * 3 + 16);
+    std::vector<uint8_t> out((size_t)g.width * g.height * 3 + 32);
     const int mode = g.ncomp == 1 ? 0 : (hmax == 1 ? 0 : (vmax == 1 ? 1 : 2));
     for (int y = 0; y < g.height; ++y)
-        for (int x0 = 0; x0 < g.width; x0 += 4) {
+        for (int x0 = 0; x0 < g.width; x0 += 8) {
             uint8_t* o = out.data() + ((size_t)y * g.width + x0) * 3;
             if (mode == 0) color_group<0>(planes, g, y, x0, bgr, o);
             else if (mode == 1) color_group<1>(planes, g, y, x0, bgr, o);
