@@ -256,7 +256,7 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
 }
 
 // ---- entropy decoding -----------------------------------------------------------------------------------------------
-constexpr int kHuffThreads = 64;
+constexpr int kHuffThreads = 128;
 
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
                                                                     const long long* __restrict__ scan_len, const int* __restrict__ table_slot,
@@ -527,20 +527,16 @@ FB_HD void color_group(const uint8_t* P, const JpegGeom& g, int y, int x0, int b
     }
 }
 
-// One thread = 8 consecutive pixels of a row.
+// One thread = 8 consecutive pixels of a row; blockIdx.x = image * H + row (no 64-bit divisions per thread).
 template <int MODE>
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restrict__ planes, JpegGeom g, int n, int bgr,
                                                          uint8_t* __restrict__ out, long long out_stride) {
     const int W = g.width, H = g.height;
-    const int groups = (W + 7) / 8;
-    const long long total = (long long)n * H * groups;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int gx = (int)(i % groups);
-        const long long t = i / groups;
-        const int y = (int)(t % H), img = (int)(t / H);
-        color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 8, bgr,
-                          out + (size_t)img * out_stride + ((size_t)y * W + gx * 8) * 3);
-    }
+    const int gx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (gx * 8 >= W) return;
+    const int img = (int)(blockIdx.x / (unsigned)H), y = (int)(blockIdx.x - (unsigned)img * (unsigned)H);
+    color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 8, bgr,
+                      out + (size_t)img * out_stride + ((size_t)y * W + gx * 8) * 3);
 }
 
 }  // namespace
@@ -633,13 +629,13 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         jpeg_idct_kernel<<<(unsigned)gb, 128, 0, stream>>>(coef, d_table_slot, reinterpret_cast<const JpegTableSet*>(d_tables), g, n, planes);
     }
     {
-        const long long total = (long long)n * height * ((width + 7) / 8);
-        long long gb = (total + 255) / 256;
-        if (gb > (long long)sm_count() * 32) gb = (long long)sm_count() * 32;
+        const int groups = (width + 7) / 8;
+        const int threads = groups >= 256 ? 256 : ((groups + 31) / 32) * 32;
+        dim3 grid((unsigned)((long long)n * height), (unsigned)((groups + threads - 1) / threads));
         const int mode = ncomp == 1 ? 0 : (hmax == 1 ? 0 : (vmax == 1 ? 1 : 2));
-        if (mode == 0) jpeg_color_kernel<0><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
-        else if (mode == 1) jpeg_color_kernel<1><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
-        else jpeg_color_kernel<2><<<(unsigned)gb, 256, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        if (mode == 0) jpeg_color_kernel<0><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        else if (mode == 1) jpeg_color_kernel<1><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        else jpeg_color_kernel<2><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
     }
     FB_CUDA_OK(cudaGetLastError());
     return 0;
