@@ -314,7 +314,7 @@ def main():
     from facet_b200.processing.batch_processor import BatchProcessor
     from facet_b200.processing.scorer import Facet
     from facet_b200.synth import synth_embeddings
-    from facet_b200.utils.duplicate import all_gather_embeddings
+    from facet_b200.utils.duplicate import all_gather_embeddings, cosine_pairs_sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -359,8 +359,7 @@ def main():
     def grouping(emb, hashes):
         """The duplicate-grouping stage over everything scored (configs[4]): ONE all-gather of the embedding shards and of
         the hashes, then every rank scans its balanced share of the pair triangle."""
-        e = all_gather_embeddings(emb) if world > 1 else emb
-        pairs, _ = ops.cosine_pairs(e, 0.90, part=rank, nparts=world)
+        pairs, _ = cosine_pairs_sharded(emb, 0.90)                 # bf16 gather -> scan, f32 gather overlapped -> recheck
         h = all_gather_embeddings(hashes.view(-1, 1)).view(-1) if world > 1 else hashes
         hp = ops.hamming_pairs(h, 6, part=rank, nparts=world)      # duplicate rule of utils/duplicate.py:94-119
         return pairs, hp
@@ -479,8 +478,7 @@ def main():
         e_loc = device_embeddings(n3, 768, 11 + rank, device)
 
         def sim():
-            e = all_gather_embeddings(e_loc) if world > 1 else e_loc
-            return ops.cosine_pairs(e, 0.90, part=rank, nparts=world)
+            return cosine_pairs_sharded(e_loc, 0.90)
 
         sim()
         barrier()
@@ -493,7 +491,8 @@ def main():
         configs["similarity"] = {"baseline_config": 3, "rows_per_gpu": n3, "rows_total": ntot, "dim": 768, "tau": 0.90, "ms": ms3,
                                  "pair_comparisons_per_s": ntot * (ntot - 1) / 2 / (ms3 * 1e-3),
                                  "TFLOP_s_total": ntot * (ntot - 1) * 768 / (ms3 * 1e-3) / 1e12,
-                                 "all_gather_bytes_per_rank": (world - 1) * n3 * 768 * 4 if world > 1 else 0}
+                                 "all_gather_bytes_per_rank": (world - 1) * n3 * 768 * (2 + 4) if world > 1 else 0,
+                                 "all_gather_note": "bf16 shards first (the scan starts on them), float32 shards on the NCCL stream during the scan"}
         del e_loc
 
     # ---- e2e: the reference-shaped call.  B items per step ({'path', 'img_cv'} with frames in pinned host memory)

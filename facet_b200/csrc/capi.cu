@@ -318,6 +318,33 @@ int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, i
     return rc;
 }
 
+int fb_cosine_candidates(const void* d_emb_bf16, int64_t n, int dim, float threshold, int64_t row_offset, int64_t rows,
+                         int32_t* d_cand, float* d_cand_sims, int64_t cand_cap, uint64_t* d_cand_count, void* stream) {
+    FB_REQUIRE(n >= 1 && n < (1ll << 31) && d_cand_count, "fb_cosine_candidates: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    FB_CUDA_OK(cudaMemsetAsync(d_cand_count, 0, sizeof(uint64_t), st));
+    if (rows <= 0 || n < 2) return 0;
+    ProfScope ps(PROF_COSINE, st);
+    int rc = launch_cosine_candidates(d_emb_bf16, dim, (int)n, (int)row_offset, (int)rows, dim, threshold, d_cand, d_cand_sims,
+                                      (long long)cand_cap, reinterpret_cast<unsigned long long*>(d_cand_count), st);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_cosine_recheck(const float* d_emb_f32, int dim, const int32_t* d_cand, const uint64_t* d_cand_count, int64_t cand_cap, float tau,
+                      int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count, void* stream) {
+    FB_REQUIRE(d_cand_count && d_count, "fb_cosine_recheck: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    FB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (cand_cap <= 0) return 0;
+    ProfScope ps(PROF_COSINE, st);
+    int rc = launch_cosine_recheck(d_emb_f32, dim, dim, d_cand, reinterpret_cast<const unsigned long long*>(d_cand_count),
+                                   (long long)cand_cap, tau, d_pairs, d_sims, (long long)cap,
+                                   reinterpret_cast<unsigned long long*>(d_count), st);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
 size_t fb_vit_workspace_bytes(int batch) { return vit_workspace_bytes(batch); }
 
 int fb_vit_forward(const fb_vit_weights* w, const float* d_clip_in, int batch, void* d_workspace, size_t workspace_bytes,

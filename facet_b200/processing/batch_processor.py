@@ -186,6 +186,7 @@ class BatchProcessor:
         import threading
         from .. import _lib, ops
         from ..utils import jpeg as fj
+        from ..utils.image_loading import decode_on_host
         torch = _lib.require_cuda()
         scorer = self.scorer
         dev = scorer.device
@@ -329,8 +330,12 @@ class BatchProcessor:
                     info = fj.parse(item["jpeg"])
                 except fj.UnsupportedJpeg as exc:
                     if img is None:
-                        results[pos] = {"path": item.get("path"), "error": f"Failed to load image ({exc})"}
-                        continue
+                        # not a stream the device decoder takes: the reference's own loader (Pillow) reads it
+                        img = decode_on_host(item["jpeg"])
+                        self.metrics["host_decoded"] = self.metrics.get("host_decoded", 0) + 1
+                        if img is None:
+                            results[pos] = {"path": item.get("path"), "error": f"Failed to load image ({exc})"}
+                            continue
             if info is not None:
                 data = item["jpeg"]
                 nbytes = len(data)

@@ -168,13 +168,37 @@ def all_gather_embeddings(local_emb, group=None):
     return out
 
 
+def cosine_pairs_sharded(local_emb, tau: float, group=None):
+    """This rank's share of the all-pairs cosine scan over the shards of every rank.  [n_local, d] float32 (equal n_local
+    everywhere) -> (pairs int32 [m,2] with global row indices, sims float32 [m]).
+
+    The bf16 copy of each shard is gathered first (half the bytes) and the tensor-core scan starts on it; the float32 rows,
+    which only the recheck of the few candidates needs, are gathered by NCCL on its own stream while the scan computes."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return ops.cosine_pairs(local_emb, tau)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    local = local_emb.contiguous()
+    n_local, d = local.shape
+    eb = torch.empty((world * n_local, d), dtype=torch.bfloat16, device=local.device)
+    dist.all_gather_into_tensor(eb, ops.to_bf16(local), group=group)
+    e32 = torch.empty((world * n_local, d), dtype=torch.float32, device=local.device)
+    work = dist.all_gather_into_tensor(e32, local, group=group, async_op=True)
+
+    def wait_f32():
+        work.wait()             # the compute stream waits for the NCCL stream; the host does not block
+        return e32
+
+    return ops.cosine_pairs_split(eb, wait_f32, tau, part=rank, nparts=world)
+
+
 def find_similar_groups(local_emb, aggregates, tau: float, group=None):
     """Cosine-threshold grouping: returns (group_id, is_lead) for the gathered rows on every rank."""
     import torch.distributed as dist
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-    emb = all_gather_embeddings(local_emb, group)
-    local_pairs, _ = ops.cosine_pairs(emb, tau, part=rank, nparts=world)
+    local_pairs, _ = cosine_pairs_sharded(local_emb, tau, group)
     pairs = gather_pairs(local_pairs, group)
-    return group_duplicates(emb.shape[0], pairs, aggregates)
+    return group_duplicates(world * local_emb.shape[0], pairs, aggregates)

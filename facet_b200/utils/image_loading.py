@@ -29,3 +29,38 @@ def orient_frames(frames_rgb, orientation: int = 1, to_bgr: bool = True):
     scoring pass takes (`img_cv`: upright, BGR).  Returns a CUDA uint8 tensor [n,H',W',3]."""
     from .. import ops
     return ops.orient(frames_rgb, orientation, swap_rb=to_bgr)
+
+
+def decode_on_host(data):
+    """The reference's own loader for one JPEG stream (utils/image_loading.py:90-106): Pillow decode, `exif_transpose`,
+    RGB, then the BGR copy the analyzers take.  Used by the streamed pass for streams the device decoder does not accept
+    (progressive, no restart markers, CMYK ...): file loading is outside the scoring path, exactly as in the reference.
+    Returns an [H,W,3] uint8 BGR array, or None when Pillow cannot read the data either."""
+    import io
+
+    import numpy as np
+    from PIL import Image, ImageOps
+    try:
+        img = Image.open(io.BytesIO(bytes(data)))
+        img = ImageOps.exif_transpose(img).convert("RGB")
+        return np.ascontiguousarray(np.asarray(img)[:, :, ::-1])
+    except Exception:
+        return None
+
+
+def read_jpeg_item(path, pinned: bool = False):
+    """One loader item for `BatchProcessor.process_items_streamed`: {'path', 'jpeg'} with the file's bytes (a view of pinned
+    host memory when `pinned`, so that the upload is asynchronous).  The bytes are not decoded here."""
+    import os
+
+    import numpy as np
+    size = os.path.getsize(path)
+    if pinned:
+        import torch
+        buf = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        arr = buf.numpy()
+        with open(path, "rb") as f:
+            f.readinto(memoryview(arr))
+        return {"path": str(path), "jpeg": arr, "_pinned": buf}
+    with open(path, "rb") as f:
+        return {"path": str(path), "jpeg": np.frombuffer(f.read(), np.uint8)}

@@ -21,6 +21,7 @@ ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 1
                    28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
                    54, 47, 55, 62, 63], dtype=np.int64)      # zigzag position -> natural (row-major) index
 
+MAX_SERIAL_MCUS = 4096       # largest stream without restart markers the device decoder accepts (about 1 MP at 4:2:0)
 LUT_BITS = 9
 # one Huffman table on the device: uint16 lut[512] | int32 maxcode[18] | int32 valptr[17] | uint8 values[256]  (see JpegHuff in
 # csrc/jpeg_decode.cu); a table set = uint16 q[4][64] + 4 DC + 4 AC tables
@@ -188,6 +189,12 @@ def parse(data, head_bytes: int = 1 << 16) -> JpegInfo:
                 if (info.tq[c] not in info.qtables or info.tq[c] > 3 or (0, info.td[c]) not in info.huff
                         or (1, info.ta[c]) not in info.huff or info.td[c] > 3 or info.ta[c] > 3):
                     raise UnsupportedJpeg("a table referenced by the scan is missing")
+            hmax, vmax = max(info.hs), max(info.vs)
+            mcus = -(-info.width // (8 * hmax)) * -(-info.height // (8 * vmax))
+            if info.restart_interval == 0 and mcus > MAX_SERIAL_MCUS:
+                # DC prediction chains every block of such a stream: its entropy decoding is one sequential pass (one GPU
+                # thread).  Small images are fine; big ones go to the caller's CPU loader, like every file of the reference
+                raise UnsupportedJpeg(f"no restart markers ({mcus} MCUs in one interval): sequential entropy decoding")
             info.scan_offset = pos + seglen
             # the entropy-coded segment ends at the EOI marker: normally the last two bytes of the file
             tail = bytes(memoryview(data)[max(info.scan_offset, total - 4096):total]) if not isinstance(data, (bytes, bytearray)) else None

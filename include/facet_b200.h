@@ -232,6 +232,16 @@ int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, i
                     uint64_t* d_cand_count, int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count,
                     void* stream);
 
+/* The two halves of fb_cosine_pairs as separate calls, for the multi-GPU flow (utils/duplicate.py `cosine_pairs_sharded`):
+ * the scan needs only the bf16 copy of the gathered matrix, so the all-gather of the float32 rows (twice the bytes) runs
+ * on the NCCL stream WHILE the scan computes; the recheck waits for it.  fb_cosine_candidates emits (i, j, bf16 sim) with
+ * sim >= threshold (= tau - band) for i in [row_offset, row_offset + rows), i < j; fb_cosine_recheck keeps the candidates
+ * whose float64-accumulated dot product of the float32 rows is >= tau. */
+int fb_cosine_candidates(const void* d_emb_bf16, int64_t n, int dim, float threshold, int64_t row_offset, int64_t rows,
+                         int32_t* d_cand, float* d_cand_sims, int64_t cand_cap, uint64_t* d_cand_count, void* stream);
+int fb_cosine_recheck(const float* d_emb_f32, int dim, const int32_t* d_cand, const uint64_t* d_cand_count, int64_t cand_cap, float tau,
+                      int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * CLIP ViT-L/14 image tower + heads — replaces `self.model.encode_image(inputs)`,
  * `F.normalize(features)`, `self.aesthetic_head(features.float())`

@@ -17,7 +17,7 @@ from facet_b200.utils import jpeg as fj  # noqa: E402
 H, W = 4000, 6000
 res = {}
 for name, gen in (("int", lambda i: synth_frame_int(i, H, W)), ("photo", lambda i: synth_image_bgr(2000 + i, H, W))):
-    for ri in (8, 25, 375, 0):
+    for ri in (8, 25, 375):
         kw = {"quality": 90}
         if ri:
             kw["restart_marker_blocks"] = ri

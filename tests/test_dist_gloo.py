@@ -34,7 +34,8 @@ def _worker(rank, world, port, ret):
     gid, lead = group_duplicates(n, pairs, aggs)
     wg, wl = og.cosine_groups(e, aggs, 0.9)
     assert gid.tolist() == wg.tolist() and lead.tolist() == wl.tolist()
-    # hamming row-tile dealing: tile t belongs to part t % nparts
+    # any disjoint dealing of the pair triangle over the ranks must union to the full set (the kernel deals upper-triangle
+    # tiles round-robin; here rows are dealt in blocks of 2048)
     h = synth_hashes(5000, seed=2, dup_fraction=0.3)
     hp = og.hamming_pairs(h, 6)
     mine = hp[((hp[:, 0] // 2048) % world) == rank]

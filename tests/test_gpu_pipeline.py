@@ -184,7 +184,7 @@ def test_batch_processor_streamed_path_equals_the_blocking_one(scorer):
 def test_streamed_path_takes_jpeg_file_bytes(scorer):
     """Items that carry the FILE BYTES (`jpeg`) are decoded on the device; results equal those of the same frames decoded
     by Pillow on the host (the reference's loader, utils/image_loading.py:90-106) and passed as `img_cv`, EXIF orientation
-    included.  Progressive files fall back to the item's `img_cv`, corrupt ones become error items."""
+    included.  Progressive files use the item's `img_cv` or the host loader, corrupt ones become error items."""
     import io
     import torch
     from PIL import Image, ImageOps
@@ -222,4 +222,6 @@ def test_streamed_path_takes_jpeg_file_bytes(scorer):
         assert "error" not in g, g
         for k in w_:
             assert g[k] == w_[k], (w_["path"], k)
-    assert "error" in got[-2] and "error" in got[-1]
+    assert "error" in got[-2]                                  # corrupt entropy data
+    assert "error" not in got[-1] and got[-1]["phash"] == got[len(want) - 1]["phash"]     # progressive: read by the host loader
+    assert bp.metrics.get("host_decoded") == 1
