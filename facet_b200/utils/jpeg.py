@@ -21,7 +21,7 @@ ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 1
                    28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
                    54, 47, 55, 62, 63], dtype=np.int64)      # zigzag position -> natural (row-major) index
 
-MAX_SERIAL_MCUS = 4096       # largest stream without restart markers the device decoder accepts (about 1 MP at 4:2:0)
+MAX_SERIAL_MCUS = 16384      # largest stream without restart markers the device decoder accepts (1 MP at 4:4:4, 4 MP at 4:2:0)
 LUT_BITS = 9
 # one Huffman table on the device: uint16 lut[512] | int32 maxcode[18] | int32 valptr[17] | uint8 values[256]  (see JpegHuff in
 # csrc/jpeg_decode.cu); a table set = uint16 q[4][64] + 4 DC + 4 AC tables
