@@ -57,7 +57,7 @@ def test_bgr_order_orientation_and_errors():
     with pytest.raises(fj.UnsupportedJpeg):
         ops.jpeg_decode([encode(rgb, quality=80, progressive=True)])
     with pytest.raises(fj.UnsupportedJpeg, match="restart markers"):      # a big stream without DRI is one sequential interval
-        fj.parse(encode(np.zeros((1200, 1600, 3), np.uint8), quality=80))
+        fj.parse(encode(np.zeros((2400, 3200, 3), np.uint8), quality=80))
     good = encode(rgb, quality=90, restart_marker_blocks=5)
     info = fj.parse(good)
     # a restart marker removed -> the marker count no longer matches the DRI header

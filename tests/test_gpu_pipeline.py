@@ -223,5 +223,7 @@ def test_streamed_path_takes_jpeg_file_bytes(scorer):
         for k in w_:
             assert g[k] == w_[k], (w_["path"], k)
     assert "error" in got[-2]                                  # corrupt entropy data
-    assert "error" not in got[-1] and got[-1]["phash"] == got[len(want) - 1]["phash"]     # progressive: read by the host loader
-    assert bp.metrics.get("host_decoded") == 1
+    assert bp.metrics.get("host_decoded") == 1                # progressive without a frame: read by the host loader (Pillow)
+    from facet_b200.utils.image_loading import decode_on_host
+    ref = bp.process_items_streamed([{"path": "/x/prog_only.jpg", "img_cv": decode_on_host(buf.getvalue())}])[0]
+    assert "error" not in got[-1] and all(got[-1][k] == ref[k] for k in ref)
