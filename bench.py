@@ -130,17 +130,17 @@ class ClockSampler:
         if self.nvml is not None:
             self.thread.join(timeout=2)
             n = self.nvml
-            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            # every bit NVML defines (nvml.h nvmlClocksEventReason*), so that a clock below the maximum always comes with its reason
+            names = {"gpu_idle": 0x1, "applications_clocks_setting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8, "sync_boost": 0x10,
+                     "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80,
+                     "display_clock_setting": 0x100}
             sm = sorted(s[0] for s in self.samples)
             mask = 0
             for _, r in self.samples:
                 mask |= r
             reasons = sorted(k for k, bit in names.items() if mask & bit)
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
-                    "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": "nvml"}
+                    "sm_max_mhz": self.max_mhz, "reasons": reasons, "reasons_mask": mask, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
