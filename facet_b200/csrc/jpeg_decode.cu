@@ -49,6 +49,7 @@ struct BitReader {
     const uint8_t* end;
     uint64_t acc;
     int n;
+    uint32_t nxt;       // the four bytes at p (big-endian), loaded one refill ahead so that their latency is off the critical path
 };
 
 // Four bytes at p (any alignment) as a big-endian word.  The device version reads the two aligned words around p: up to 7
@@ -67,15 +68,20 @@ FB_HD uint32_t load_be32(const uint8_t* p) {
 // Top up to > 32 buffered bits.  Fast path: the next four bytes hold no 0xFF (true for ~98 % of the positions), so they
 // enter the buffer as one word.  Otherwise byte by byte: inside an interval the only 0xFF bytes are stuffed ones (followed
 // by 0x00); past the end zeros are fed (T.81 F.2.2.5).
+FB_HD void prefetch_word(BitReader& br) {
+    if (br.p + 4 <= br.end) br.nxt = load_be32(br.p);
+}
+
 FB_HD void refill(BitReader& br) {
     if (br.n > 32) return;
     if (br.p + 4 <= br.end) {
-        const uint32_t w = load_be32(br.p);
+        const uint32_t w = br.nxt;
         const uint32_t x = ~w;                                   // a 0xFF byte of w is a zero byte of x
         if (!((x - 0x01010101u) & ~x & 0x80808080u)) {
             br.acc = (br.acc << 32) | w;
             br.n += 32;
             br.p += 4;
+            prefetch_word(br);                                   // needed four bytes of symbols from now
             return;
         }
     }
@@ -88,6 +94,7 @@ FB_HD void refill(BitReader& br) {
         br.acc = (br.acc << 8) | b;
         br.n += 8;
     }
+    prefetch_word(br);
 }
 FB_HD uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (br.n - k)) & ((1u << k) - 1u); }
 
@@ -211,6 +218,8 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     br.end = p1;
     br.acc = 0;
     br.n = 0;
+    br.nxt = 0;
+    prefetch_word(br);
     const int total_mcus = g.mcux * g.mcuy;
     const int m0 = g.restart_interval ? iv * g.restart_interval : 0;
     const int m1 = g.restart_interval ? (m0 + g.restart_interval < total_mcus ? m0 + g.restart_interval : total_mcus) : total_mcus;
