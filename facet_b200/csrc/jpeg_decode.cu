@@ -49,39 +49,45 @@ struct BitReader {
     const uint8_t* end;
     uint64_t acc;
     int n;
-    uint32_t nxt;       // the four bytes at p (big-endian), loaded one refill ahead so that their latency is off the critical path
+    uint32_t w0, w1;    // the aligned words around p, loaded one refill ahead
 };
 
-// Four bytes at p (any alignment) as a big-endian word.  The device version reads the two aligned words around p: up to 7
-// bytes past p + 3, so stream buffers carry 8 bytes of slack.
-FB_HD uint32_t load_be32(const uint8_t* p) {
+// The four bytes at p (any alignment) come from the two aligned words around p (up to 7 bytes past p + 3 are read: stream
+// buffers carry 8 bytes of slack).  The words are LOADED one refill ahead (`prefetch_words`) and only COMBINED when the next
+// refill needs them (`prefetched_be32`), so the load latency overlaps the decoding of the four bytes in between.
+FB_HD void prefetch_words(BitReader& br) {
+    if (br.p + 4 <= br.end) {
 #ifdef __CUDA_ARCH__
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t le = __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(br.p) & ~(uintptr_t)3);
+        br.w0 = w[0];
+        br.w1 = w[1];
+#else
+        br.w0 = ((uint32_t)br.p[0] << 24) | ((uint32_t)br.p[1] << 16) | ((uint32_t)br.p[2] << 8) | (uint32_t)br.p[3];
+#endif
+    }
+}
+FB_HD uint32_t prefetched_be32(const BitReader& br) {
+#ifdef __CUDA_ARCH__
+    const uint32_t le = __funnelshift_r(br.w0, br.w1, (uint32_t)(reinterpret_cast<uintptr_t>(br.p) & 3) * 8);
     return __byte_perm(le, 0u, 0x0123);
 #else
-    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    return br.w0;
 #endif
 }
 
 // Top up to > 32 buffered bits.  Fast path: the next four bytes hold no 0xFF (true for ~98 % of the positions), so they
 // enter the buffer as one word.  Otherwise byte by byte: inside an interval the only 0xFF bytes are stuffed ones (followed
 // by 0x00); past the end zeros are fed (T.81 F.2.2.5).
-FB_HD void prefetch_word(BitReader& br) {
-    if (br.p + 4 <= br.end) br.nxt = load_be32(br.p);
-}
-
 FB_HD void refill(BitReader& br) {
     if (br.n > 32) return;
     if (br.p + 4 <= br.end) {
-        const uint32_t w = br.nxt;
+        const uint32_t w = prefetched_be32(br);
         const uint32_t x = ~w;                                   // a 0xFF byte of w is a zero byte of x
         if (!((x - 0x01010101u) & ~x & 0x80808080u)) {
             br.acc = (br.acc << 32) | w;
             br.n += 32;
             br.p += 4;
-            prefetch_word(br);                                   // needed four bytes of symbols from now
+            prefetch_words(br);                                  // needed four bytes of symbols from now
             return;
         }
     }
@@ -94,7 +100,7 @@ FB_HD void refill(BitReader& br) {
         br.acc = (br.acc << 8) | b;
         br.n += 8;
     }
-    prefetch_word(br);
+    prefetch_words(br);
 }
 FB_HD uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (br.n - k)) & ((1u << k) - 1u); }
 
@@ -218,8 +224,8 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     br.end = p1;
     br.acc = 0;
     br.n = 0;
-    br.nxt = 0;
-    prefetch_word(br);
+    br.w0 = br.w1 = 0;
+    prefetch_words(br);
     const int total_mcus = g.mcux * g.mcuy;
     const int m0 = g.restart_interval ? iv * g.restart_interval : 0;
     const int m1 = g.restart_interval ? (m0 + g.restart_interval < total_mcus ? m0 + g.restart_interval : total_mcus) : total_mcus;
@@ -265,7 +271,7 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
 }
 
 // ---- entropy decoding -----------------------------------------------------------------------------------------------
-constexpr int kHuffThreads = 128;
+constexpr int kHuffThreads = 256;
 
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
                                                                     const long long* __restrict__ scan_len, const int* __restrict__ table_slot,
