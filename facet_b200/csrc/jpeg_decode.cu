@@ -49,47 +49,55 @@ struct BitReader {
     const uint8_t* end;
     uint64_t acc;
     int n;
-    uint32_t w0, w1;    // the aligned words around p, loaded one refill ahead
+    uint32_t w0, w1, w2;    // the aligned words at and after p, loaded ahead of their use
 };
 
-// The four bytes at p (any alignment) come from the two aligned words around p (up to 7 bytes past p + 3 are read: stream
-// buffers carry 8 bytes of slack).  The words are LOADED one refill ahead (`prefetch_words`) and only COMBINED when the next
-// refill needs them (`prefetched_be32`), so the load latency overlaps the decoding of the four bytes in between.
+// The four bytes at p (any alignment) come from the two aligned words around p.  Three consecutive aligned words are
+// kept in registers, so the word a refill needs was requested TWO refills (eight stream bytes) earlier and every fast
+// refill issues one load; up to 15 bytes past the end of a stream are read (stream buffers carry that slack).
 FB_HD void prefetch_words(BitReader& br) {
-    if (br.p + 4 <= br.end) {
 #ifdef __CUDA_ARCH__
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(br.p) & ~(uintptr_t)3);
-        br.w0 = w[0];
-        br.w1 = w[1];
-#else
-        br.w0 = ((uint32_t)br.p[0] << 24) | ((uint32_t)br.p[1] << 16) | ((uint32_t)br.p[2] << 8) | (uint32_t)br.p[3];
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(br.p) & ~(uintptr_t)3);
+    br.w0 = w[0];
+    br.w1 = w[1];
+    br.w2 = w[2];
 #endif
-    }
 }
-FB_HD uint32_t prefetched_be32(const BitReader& br) {
+FB_HD uint32_t next_be32(const BitReader& br) {
 #ifdef __CUDA_ARCH__
     const uint32_t le = __funnelshift_r(br.w0, br.w1, (uint32_t)(reinterpret_cast<uintptr_t>(br.p) & 3) * 8);
     return __byte_perm(le, 0u, 0x0123);
 #else
-    return br.w0;
+    uint32_t w = 0;
+    for (int i = 0; i < 4; ++i) w = (w << 8) | (br.p + i < br.end ? br.p[i] : 0u);
+    return w;
 #endif
 }
 
-// Top up to > 32 buffered bits.  Fast path: the next four bytes hold no 0xFF (true for ~98 % of the positions), so they
-// enter the buffer as one word.  Otherwise byte by byte: inside an interval the only 0xFF bytes are stuffed ones (followed
-// by 0x00); past the end zeros are fed (T.81 F.2.2.5).
+// Top up to > 32 buffered bits.  Fast path: the next four bytes (zeros past the end of the interval, T.81 F.2.2.5) hold no
+// 0xFF (true for ~98 % of the positions) and enter the buffer as one word.  Otherwise byte by byte: inside an interval the
+// only 0xFF bytes are stuffed ones, followed by 0x00.
 FB_HD void refill(BitReader& br) {
     if (br.n > 32) return;
-    if (br.p + 4 <= br.end) {
-        const uint32_t w = prefetched_be32(br);
-        const uint32_t x = ~w;                                   // a 0xFF byte of w is a zero byte of x
-        if (!((x - 0x01010101u) & ~x & 0x80808080u)) {
-            br.acc = (br.acc << 32) | w;
-            br.n += 32;
-            br.p += 4;
-            prefetch_words(br);                                  // needed four bytes of symbols from now
-            return;
-        }
+    const long long rem = br.end - br.p;
+    if (rem <= 0) {
+        br.acc <<= 32;
+        br.n += 32;
+        return;
+    }
+    uint32_t w = next_be32(br);
+    if (rem < 4) w &= 0xFFFFFFFFu << (8 * (4 - (int)rem));       // bytes past the end of the interval count as zeros
+    const uint32_t x = ~w;                                       // a 0xFF byte of w is a zero byte of x
+    if (!((x - 0x01010101u) & ~x & 0x80808080u)) {
+        br.acc = (br.acc << 32) | w;
+        br.n += 32;
+        br.p += 4;
+#ifdef __CUDA_ARCH__
+        br.w0 = br.w1;
+        br.w1 = br.w2;
+        br.w2 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(br.p) & ~(uintptr_t)3)[2];
+#endif
+        return;
     }
     while (br.n <= 32) {
         uint32_t b = 0;
@@ -224,7 +232,7 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     br.end = p1;
     br.acc = 0;
     br.n = 0;
-    br.w0 = br.w1 = 0;
+    br.w0 = br.w1 = br.w2 = 0;
     prefetch_words(br);
     const int total_mcus = g.mcux * g.mcuy;
     const int m0 = g.restart_interval ? iv * g.restart_interval : 0;

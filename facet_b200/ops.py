@@ -563,7 +563,7 @@ def jpeg_decode(streams, bgr: bool = True, apply_orientation: bool = True):
     infos = [fj.parse(s) for s in streams]
     slot = (max(len(s) for s in streams) + 255) & ~255
     dev = torch.device("cuda", torch.cuda.current_device())
-    buf = torch.empty(len(streams) * slot + 256, dtype=torch.uint8, device=dev)      # the bit reader may read 8 bytes past a stream
+    buf = torch.empty(len(streams) * slot + 256, dtype=torch.uint8, device=dev)      # the bit reader reads up to 15 bytes past a stream
     for k, s in enumerate(streams):
         a = np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray, memoryview)) else np.ascontiguousarray(s, dtype=np.uint8).reshape(-1)
         buf[k * slot:k * slot + a.size].copy_(torch.from_numpy(a.copy() if not a.flags.writeable else a), non_blocking=True)
