@@ -222,9 +222,26 @@ __global__ void __launch_bounds__(256) jpeg_restart_prefix_kernel(int* __restric
     }
 }
 
+// Blocks of one MCU in scan order, 4 bits each: component (2 bits), block row and column inside the MCU (1 bit each; the
+// supported sampling factors are 1 or 2).  At most 2*2 + 1 + 1 = 6 blocks.
+FB_HD uint64_t mcu_layout(const JpegGeom& g, int& nblk) {
+    uint64_t lay = 0;
+    nblk = 0;
+    for (int c = 0; c < g.ncomp; ++c)
+        for (int by = 0; by < g.vs[c]; ++by)
+            for (int bx = 0; bx < g.hs[c]; ++bx) {
+                lay |= (uint64_t)(c | (by << 2) | (bx << 3)) << (4 * nblk);
+                ++nblk;
+            }
+    return lay;
+}
+
 // Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside).  Non-zero
 // quantised coefficients are stored in natural order into the (pre-zeroed) coefficient area of the image; `zz` is the
 // zigzag table (shared memory on the device).  Returns false on invalid Huffman data.
+// The loop decodes ONE symbol per iteration whatever it is (DC size, AC run/size, EOB, ZRL): table, destination and the
+// state update are chosen by selects, so the lanes of a warp — each in its own interval — stay on the same instructions
+// instead of scattering over the branches of a nested MCU / component / block / coefficient loop nest.
 FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, const uint8_t* zz,
                            int16_t* cimg) {
     BitReader br;
@@ -235,47 +252,70 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     br.w0 = br.w1 = br.w2 = 0;
     prefetch_words(br);
     const int total_mcus = g.mcux * g.mcuy;
-    const int m0 = g.restart_interval ? iv * g.restart_interval : 0;
-    const int m1 = g.restart_interval ? (m0 + g.restart_interval < total_mcus ? m0 + g.restart_interval : total_mcus) : total_mcus;
-    int pred[3] = {0, 0, 0};
-    for (int m = m0; m < m1; ++m) {
-        const int my = m / g.mcux, mx = m - my * g.mcux;
-        for (int c = 0; c < g.ncomp; ++c) {
-            const JpegHuff& hd = T.dc[g.td[c]];
-            const JpegHuff& ha = T.ac[g.ta[c]];
-            for (int by = 0; by < g.vs[c]; ++by) {
-                for (int bx = 0; bx < g.hs[c]; ++bx) {
-                    const size_t b = (size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx);
-                    int16_t* blk = cimg + g.coef_comp_off[c] + b * 64;
-                    refill(br);
-                    const int t = decode_symbol(br, hd);
-                    if (t < 0 || t > 15) return false;
-                    if (t) {
-                        refill(br);
-                        pred[c] += receive_extend(br, t);
-                    }
-                    if (pred[c]) blk[0] = (int16_t)pred[c];
-                    int k = 1;
-                    while (k < 64) {
-                        refill(br);
-                        const int rs = decode_symbol(br, ha);
-                        if (rs < 0) return false;
-                        const int r = rs >> 4, sz = rs & 15;
-                        if (sz == 0) {
-                            if (r != 15) break;          // EOB
-                            k += 16;                     // ZRL
-                            continue;
-                        }
-                        k += r;
-                        if (k > 63) return false;
-                        blk[zz[k]] = (int16_t)receive_extend(br, sz);      // >= 16 bits are still buffered after the symbol
-                        ++k;
-                    }
+    int m = g.restart_interval ? iv * g.restart_interval : 0;
+    const int m1 = g.restart_interval ? (m + g.restart_interval < total_mcus ? m + g.restart_interval : total_mcus) : total_mcus;
+    if (m >= m1) return true;
+    int nblk;
+    const uint64_t lay = mcu_layout(g, nblk);
+    int my = m / g.mcux, mx = m - my * g.mcux;
+    int b = 0, k = 0;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    auto block_ptr = [&](int bi, int& c) -> int16_t* {
+        const int e = (int)(lay >> (4 * bi)) & 15;
+        c = e & 3;
+        const int row = my * g.vs[c] + ((e >> 2) & 1), col = mx * g.hs[c] + ((e >> 3) & 1);
+        return cimg + g.coef_comp_off[c] + ((size_t)row * g.blocks_w[c] + col) * 64;
+    };
+    int c;
+    int16_t* blk = block_ptr(0, c);
+    const JpegHuff* hd = &T.dc[g.td[c]];
+    const JpegHuff* ha = &T.ac[g.ta[c]];
+    for (;;) {
+        refill(br);
+        const bool isdc = k == 0;
+        const int sym = decode_symbol(br, isdc ? *hd : *ha);
+        if (sym < 0) return false;
+        const int run = isdc ? 0 : sym >> 4;
+        const int size = isdc ? sym : (sym & 15);
+        if (size > (isdc ? 11 : 15)) return false;
+        int val = 0;
+        if (size) {                                   // (predicated: a few instructions)
+            const int v = (int)peek(br, size);
+            br.n -= size;
+            val = v < (1 << (size - 1)) ? v - (1 << size) + 1 : v;
+        }
+        int pos = 0, store = val;
+        if (isdc) {
+            const int pr = (c == 0 ? pred0 : (c == 1 ? pred1 : pred2)) + val;
+            pred0 = c == 0 ? pr : pred0;
+            pred1 = c == 1 ? pr : pred1;
+            pred2 = c == 2 ? pr : pred2;
+            store = pr;
+            k = 1;
+        } else if (size == 0) {
+            k = run == 15 ? k + 16 : 64;              // ZRL : EOB
+        } else {
+            k += run;
+            if (k > 63) return false;
+            pos = zz[k];
+            ++k;
+        }
+        if (store) blk[pos] = (int16_t)store;
+        if (k >= 64) {                                // next block (next MCU after the last block of this one)
+            k = 0;
+            if (++b == nblk) {
+                b = 0;
+                if (++m == m1) return true;
+                if (++mx == g.mcux) {
+                    mx = 0;
+                    ++my;
                 }
             }
+            blk = block_ptr(b, c);
+            hd = &T.dc[g.td[c]];
+            ha = &T.ac[g.ta[c]];
         }
     }
-    return true;
 }
 
 // ---- entropy decoding -----------------------------------------------------------------------------------------------
