@@ -236,14 +236,18 @@ FB_HD uint64_t mcu_layout(const JpegGeom& g, int& nblk) {
     return lay;
 }
 
-// Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside).  Non-zero
-// quantised coefficients are stored in natural order into the (pre-zeroed) coefficient area of the image; `zz` is the
-// zigzag table (shared memory on the device).  Returns false on invalid Huffman data.
+// Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside); `zz` is the
+// zigzag table.  Quantised coefficients go out in natural order, one whole 8x8 block (128 bytes, zeros included) at a time:
+// the block is assembled in `stage` — 64 int16 of shared memory private to the thread — and copied to the image's
+// coefficient area with eight 16-byte stores when it is complete.  (Scattering the non-zero coefficients straight into a
+// pre-zeroed area was measured first: the 2-byte stores cost 44 % of the kernel in L2 read-modify-write traffic, plus the
+// memset.)  stage == nullptr (the host test tool): coefficients are stored directly into a pre-zeroed area.
+// Returns false on invalid Huffman data.
 // The loop decodes ONE symbol per iteration whatever it is (DC size, AC run/size, EOB, ZRL): table, destination and the
 // state update are chosen by selects, so the lanes of a warp — each in its own interval — stay on the same instructions
 // instead of scattering over the branches of a nested MCU / component / block / coefficient loop nest.
 FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, const uint8_t* zz,
-                           int16_t* cimg) {
+                           int16_t* cimg, int16_t* stage) {
     BitReader br;
     br.p = p0;
     br.end = p1;
@@ -300,8 +304,15 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
             pos = zz[k];
             ++k;
         }
-        if (store) blk[pos] = (int16_t)store;
+        if (store) (stage ? stage : blk)[pos] = (int16_t)store;
         if (k >= 64) {                                // next block (next MCU after the last block of this one)
+            if (stage) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    reinterpret_cast<uint4*>(blk)[i] = reinterpret_cast<const uint4*>(stage)[i];
+                    reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
             k = 0;
             if (++b == nblk) {
                 b = 0;
@@ -320,6 +331,8 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
 
 // ---- entropy decoding -----------------------------------------------------------------------------------------------
 constexpr int kHuffThreads = 256;
+constexpr int kStagePitch = 72;                 // int16 per staging row
+constexpr int kHuffSmem = (int)sizeof(JpegTableSet) + kHuffThreads * kStagePitch * 2;
 
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
                                                                     const long long* __restrict__ scan_len, const int* __restrict__ table_slot,
@@ -344,7 +357,12 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
     const uint32_t* st = starts + (size_t)img * g.n_intervals;
     const uint8_t* p0 = s + st[iv];
     const uint8_t* p1 = (iv + 1 < g.n_intervals) ? s + st[iv + 1] - 2 : s + len;     // up to the next RSTn marker
-    const bool bad = !decode_interval(p0, p1, iv, g, *T, s_zz, coef + (size_t)img * g.coef_image_stride);
+    // this thread's staging row: 64 coefficients at a pitch of 72 int16 (144 bytes: 16-byte aligned, and the eight lanes of a
+    // quarter warp cover all 32 banks in a 16-byte access)
+    int16_t* stage = reinterpret_cast<int16_t*>(s_raw + sizeof(JpegTableSet)) + tid * kStagePitch;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const bool bad = !decode_interval(p0, p1, iv, g, *T, s_zz, coef + (size_t)img * g.coef_image_stride, stage);
     if (bad) atomicOr(status + img, 2);
 }
 
@@ -670,7 +688,6 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
     const int chunks = (int)((max_scan_bytes + kScanChunk - 1) / kScanChunk + 1);
 
     FB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int) * n, stream));
-    FB_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)blocks * 128 * n, stream));      // the entropy decoder stores non-zero coefficients only
     if (g.n_intervals > 1) {
         dim3 grid(chunks, n);
         jpeg_restart_scan_kernel<false><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
@@ -681,7 +698,12 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
     }
     {
         dim3 grid((g.n_intervals + kHuffThreads - 1) / kHuffThreads, n);
-        jpeg_huffman_kernel<<<grid, kHuffThreads, sizeof(JpegTableSet), stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot,
+        static bool attr_set = false;
+        if (!attr_set) {
+            FB_CUDA_OK(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem));
+            attr_set = true;
+        }
+        jpeg_huffman_kernel<<<grid, kHuffThreads, kHuffSmem, stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot,
                                                                                 reinterpret_cast<const JpegTableSet*>(d_tables), starts, g, coef,
                                                                                 d_status);
     }
