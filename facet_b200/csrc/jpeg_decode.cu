@@ -22,6 +22,8 @@ namespace fb {
 namespace {
 
 constexpr int kLutBits = 9;
+constexpr int kStagePitch = 66;                 // int16 per staging row of the entropy decoder: 33 words, so that equal
+                                                // positions of the 32 rows of a warp fall into 32 different banks
 
 struct JpegHuff {
     uint16_t lut[1 << kLutBits];      // (length << 8) | symbol for codes of <= 9 bits, else 0
@@ -237,31 +239,34 @@ FB_HD uint64_t mcu_layout(const JpegGeom& g, int& nblk) {
 }
 
 // Entropy decoding of restart interval `iv` of one stream: bytes [p0, p1) hold its MCUs (no marker inside); `zz` is the
-// zigzag table.  Quantised coefficients go out in natural order, one whole 8x8 block (128 bytes, zeros included) at a time:
-// the block is assembled in `stage` — 64 int16 of shared memory private to the thread — and copied to the image's
-// coefficient area with eight 16-byte stores when it is complete.  (Scattering the non-zero coefficients straight into a
-// pre-zeroed area was measured first: the 2-byte stores cost 44 % of the kernel in L2 read-modify-write traffic, plus the
-// memset.)  stage == nullptr (the host test tool): coefficients are stored directly into a pre-zeroed area.
+// zigzag table.  The loop decodes ONE symbol per iteration whatever it is (DC size, AC run/size, EOB, ZRL): table, destination
+// and state update are chosen by selects, so the lanes of a warp — each in its own interval — stay on the same instructions.
+//
+// COOP = true (the kernel): quantised coefficients go out in natural order one whole 8x8 block (128 bytes, zeros included) at
+// a time.  A lane assembles its block in `stage_row` — 64 int16 of shared memory — and when it is complete the WHOLE WARP
+// copies it: 32 lanes x 4 bytes = one coalesced 128-byte store per block (the rows of all lanes start at `stage_warp`, pitch
+// kStagePitch).  Measured alternatives: 2-byte stores scattered into a pre-zeroed area cost 44 % of the kernel in L2
+// read-modify-write traffic (plus the memset); per-lane 16-byte copies of the staged block were slower still (32 partial lines
+// per store instruction).  Every lane of the warp must call this (inactive ones with active = false).
+// COOP = false (the host test tool): coefficients are stored directly into a pre-zeroed area.
 // Returns false on invalid Huffman data.
-// The loop decodes ONE symbol per iteration whatever it is (DC size, AC run/size, EOB, ZRL): table, destination and the
-// state update are chosen by selects, so the lanes of a warp — each in its own interval — stay on the same instructions
-// instead of scattering over the branches of a nested MCU / component / block / coefficient loop nest.
+template <bool COOP>
 FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const JpegGeom& g, const JpegTableSet& T, const uint8_t* zz,
-                           int16_t* cimg, int16_t* stage) {
+                           int16_t* cimg, bool active, int16_t* stage_warp, int lane) {
     BitReader br;
     br.p = p0;
     br.end = p1;
     br.acc = 0;
     br.n = 0;
     br.w0 = br.w1 = br.w2 = 0;
-    prefetch_words(br);
     const int total_mcus = g.mcux * g.mcuy;
     int m = g.restart_interval ? iv * g.restart_interval : 0;
     const int m1 = g.restart_interval ? (m + g.restart_interval < total_mcus ? m + g.restart_interval : total_mcus) : total_mcus;
-    if (m >= m1) return true;
+    bool done = !active || m >= m1, ok = true;
+    if (!done) prefetch_words(br);
     int nblk;
     const uint64_t lay = mcu_layout(g, nblk);
-    int my = m / g.mcux, mx = m - my * g.mcux;
+    int my = done ? 0 : m / g.mcux, mx = done ? 0 : m - my * g.mcux;
     int b = 0, k = 0;
     int pred0 = 0, pred1 = 0, pred2 = 0;
     auto block_ptr = [&](int bi, int& c) -> int16_t* {
@@ -272,66 +277,94 @@ FB_HD bool decode_interval(const uint8_t* p0, const uint8_t* p1, int iv, const J
     };
     int c;
     int16_t* blk = block_ptr(0, c);
+    int16_t* const stage_row = COOP ? stage_warp + lane * kStagePitch : nullptr;
     const JpegHuff* hd = &T.dc[g.td[c]];
     const JpegHuff* ha = &T.ac[g.ta[c]];
     for (;;) {
-        refill(br);
-        const bool isdc = k == 0;
-        const int sym = decode_symbol(br, isdc ? *hd : *ha);
-        if (sym < 0) return false;
-        const int run = isdc ? 0 : sym >> 4;
-        const int size = isdc ? sym : (sym & 15);
-        if (size > (isdc ? 11 : 15)) return false;
-        int val = 0;
-        if (size) {                                   // (predicated: a few instructions)
-            const int v = (int)peek(br, size);
-            br.n -= size;
-            val = v < (1 << (size - 1)) ? v - (1 << size) + 1 : v;
-        }
-        int pos = 0, store = val;
-        if (isdc) {
-            const int pr = (c == 0 ? pred0 : (c == 1 ? pred1 : pred2)) + val;
-            pred0 = c == 0 ? pr : pred0;
-            pred1 = c == 1 ? pr : pred1;
-            pred2 = c == 2 ? pr : pred2;
-            store = pr;
-            k = 1;
-        } else if (size == 0) {
-            k = run == 15 ? k + 16 : 64;              // ZRL : EOB
-        } else {
-            k += run;
-            if (k > 63) return false;
-            pos = zz[k];
-            ++k;
-        }
-        if (store) (stage ? stage : blk)[pos] = (int16_t)store;
-        if (k >= 64) {                                // next block (next MCU after the last block of this one)
-            if (stage) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    reinterpret_cast<uint4*>(blk)[i] = reinterpret_cast<const uint4*>(stage)[i];
-                    reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+#ifdef __CUDA_ARCH__
+        if (COOP) {
+            if (!__any_sync(0xffffffffu, !done)) break;
+        } else
+#endif
+        if (done) break;
+        int16_t* flush_blk = nullptr;
+        if (!done) {
+            refill(br);
+            const bool isdc = k == 0;
+            const int sym = decode_symbol(br, isdc ? *hd : *ha);
+            const int run = isdc ? 0 : sym >> 4;
+            const int size = isdc ? sym : (sym & 15);
+            if (sym < 0 || size > (isdc ? 11 : 15)) {
+                ok = false;
+                done = true;
+            } else {
+                int val = 0;
+                if (size) {
+                    const int v = (int)peek(br, size);
+                    br.n -= size;
+                    val = v < (1 << (size - 1)) ? v - (1 << size) + 1 : v;
+                }
+                int pos = 0, store = val;
+                if (isdc) {
+                    const int pr = (c == 0 ? pred0 : (c == 1 ? pred1 : pred2)) + val;
+                    pred0 = c == 0 ? pr : pred0;
+                    pred1 = c == 1 ? pr : pred1;
+                    pred2 = c == 2 ? pr : pred2;
+                    store = pr;
+                    k = 1;
+                } else if (size == 0) {
+                    k = run == 15 ? k + 16 : 64;              // ZRL : EOB
+                } else {
+                    k += run;
+                    if (k > 63) {
+                        ok = false;
+                        done = true;
+                        k = 63;
+                    }
+                    pos = zz[k];
+                    ++k;
+                }
+                if (store && ok) (COOP ? stage_row : blk)[pos] = (int16_t)store;
+                if (k >= 64 && ok) {                          // block complete: next block (next MCU after the last block of this one)
+                    flush_blk = blk;
+                    k = 0;
+                    if (++b == nblk) {
+                        b = 0;
+                        if (++m == m1) done = true;
+                        if (++mx == g.mcux) {
+                            mx = 0;
+                            ++my;
+                        }
+                    }
+                    if (!done) {
+                        blk = block_ptr(b, c);
+                        hd = &T.dc[g.td[c]];
+                        ha = &T.ac[g.ta[c]];
+                    }
                 }
             }
-            k = 0;
-            if (++b == nblk) {
-                b = 0;
-                if (++m == m1) return true;
-                if (++mx == g.mcux) {
-                    mx = 0;
-                    ++my;
-                }
-            }
-            blk = block_ptr(b, c);
-            hd = &T.dc[g.td[c]];
-            ha = &T.ac[g.ta[c]];
         }
+#ifdef __CUDA_ARCH__
+        if (COOP) {
+            // every completed block of the warp leaves as one 128-byte store; the copying lanes clear the row behind them
+            unsigned mask = __ballot_sync(0xffffffffu, flush_blk != nullptr);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(flush_blk), src));
+                uint32_t* row = reinterpret_cast<uint32_t*>(stage_warp + src * kStagePitch);
+                dst[lane] = row[lane];
+                row[lane] = 0u;
+            }
+            __syncwarp();
+        }
+#endif
     }
+    return ok;
 }
 
 // ---- entropy decoding -----------------------------------------------------------------------------------------------
 constexpr int kHuffThreads = 256;
-constexpr int kStagePitch = 72;                 // int16 per staging row
 constexpr int kHuffSmem = (int)sizeof(JpegTableSet) + kHuffThreads * kStagePitch * 2;
 
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
@@ -350,19 +383,18 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
     }
     __syncthreads();
     const int iv = blockIdx.x * kHuffThreads + tid;
-    if (iv >= g.n_intervals) return;
-    if (status[img] & 1) return;                  // restart markers do not match the header: nothing can be trusted
+    const bool active = iv < g.n_intervals && !(status[img] & 1);     // bit 0: restart markers do not match the header
     const uint8_t* s = bytes + scan_off[img];
     const long long len = scan_len[img];
     const uint32_t* st = starts + (size_t)img * g.n_intervals;
-    const uint8_t* p0 = s + st[iv];
-    const uint8_t* p1 = (iv + 1 < g.n_intervals) ? s + st[iv + 1] - 2 : s + len;     // up to the next RSTn marker
-    // this thread's staging row: 64 coefficients at a pitch of 72 int16 (144 bytes: 16-byte aligned, and the eight lanes of a
-    // quarter warp cover all 32 banks in a 16-byte access)
-    int16_t* stage = reinterpret_cast<int16_t*>(s_raw + sizeof(JpegTableSet)) + tid * kStagePitch;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
-    const bool bad = !decode_interval(p0, p1, iv, g, *T, s_zz, coef + (size_t)img * g.coef_image_stride, stage);
+    const uint8_t* p0 = active ? s + st[iv] : s;
+    const uint8_t* p1 = active ? ((iv + 1 < g.n_intervals) ? s + st[iv + 1] - 2 : s + len) : s;     // up to the next RSTn marker
+    // staging rows of this warp (zeroed; the cooperative copy clears them again)
+    int16_t* stage_warp = reinterpret_cast<int16_t*>(s_raw + sizeof(JpegTableSet)) + (tid & ~31) * kStagePitch;
+    for (int i = tid & 31; i < 32 * kStagePitch / 2; i += 32) reinterpret_cast<uint32_t*>(stage_warp)[i] = 0u;
+    __syncwarp();
+    const bool bad = !decode_interval<true>(p0, p1, active ? iv : 0, g, *T, s_zz, coef + (size_t)img * g.coef_image_stride, active,
+                                            stage_warp, tid & 31);
     if (bad) atomicOr(status + img, 2);
 }
 

@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
     for (int iv = 0; iv < g.n_intervals; ++iv) {
         const uint8_t* p0 = scan.data() + starts[iv];
         const uint8_t* p1 = iv + 1 < g.n_intervals ? scan.data() + starts[iv + 1] - 2 : scan.data() + len;
-        if (!decode_interval(p0, p1, iv, g, *T, h_zigzag, coef, nullptr)) {
+        if (!decode_interval<false>(p0, p1, iv, g, *T, h_zigzag, coef, true, nullptr, 0)) {
             fprintf(stderr, "bad Huffman data in interval %d\n", iv);
             return 4;
         }
