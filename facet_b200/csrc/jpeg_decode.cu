@@ -112,10 +112,12 @@ FB_HD void refill(BitReader& br) {
     }
     prefetch_words(br);
 }
-FB_HD uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (br.n - k)) & ((1u << k) - 1u); }
+template <class R>
+FB_HD uint32_t peek(const R& br, int k) { return (uint32_t)(br.acc >> (br.n - k)) & ((1u << k) - 1u); }
 
 // One Huffman symbol (>= 16 bits buffered).  Returns -1 for a code that is not in the table.
-FB_HD int decode_symbol(BitReader& br, const JpegHuff& h) {
+template <class R>
+FB_HD int decode_symbol(R& br, const JpegHuff& h) {
     const uint32_t e = h.lut[peek(br, kLutBits)];
     if (e) {
         br.n -= (int)(e >> 8);
@@ -398,6 +400,360 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
     if (bad) atomicOr(status + img, 2);
 }
 
+// ---- streams WITHOUT restart markers: self-synchronising parallel entropy decoding ---------------------------------------
+// DC prediction and the position inside the MCU chain every symbol of such a stream to its predecessors, but Huffman streams
+// SELF-SYNCHRONISE: a decoder started at a wrong bit / in a wrong state falls into step with the true symbol sequence after a
+// few dozen symbols.  Scheme (after Weissenberger & Schmidt, "Massively Parallel Huffman Decoding on GPUs"):
+//   1. the stuffed zero bytes are removed (jpeg_unstuff_*), so that positions are plain bit indices;
+//   2. the clean stream is cut into subsequences of kSubseqBytes; thread t decodes subsequence t from a guessed state and
+//      records the state at the first symbol boundary at or after the end of its subsequence (jpeg_sync_kernel, round 0);
+//   3. rounds: thread t decodes again, now from the end state thread t-1 recorded; a round that changes nothing means every
+//      thread started from the true state (thread 0 always does; the truth advances at least one subsequence per round, and in
+//      practice everywhere within two or three rounds because of the self-synchronisation);
+//   4. a prefix sum over the blocks completed per subsequence gives every thread its first block index; a last pass decodes once
+//      more and stores coefficients, the DC ones as DIFFERENCES (jpeg_sync_write_kernel);
+//   5. a prefix sum per component turns the DC differences into DC values (jpeg_dc_prefix_kernel).
+constexpr int kSubseqBytes = 512;
+#ifndef FB_SYNC_ROUNDS
+#define FB_SYNC_ROUNDS 16
+#endif
+constexpr int kSyncRounds = FB_SYNC_ROUNDS;           // rounds after round 0; a stream that still changes then is reported (status bit 2)
+
+struct SyncState {
+    long long pos;       // bit position in the clean stream (a symbol boundary)
+    int b, k;            // block inside the MCU, coefficient index (0 = the DC symbol comes next)
+};
+
+struct CleanReader {
+    const uint8_t* u;    // clean stream; at least 16 zero bytes follow its end
+    long long next;      // next byte to load
+    uint64_t acc;
+    int n;
+};
+FB_HD void cr_seek(CleanReader& r, long long pos_bits) {
+    r.next = pos_bits >> 3;
+    r.acc = 0;
+    r.n = 0;
+    const int skip = (int)(pos_bits & 7);
+    if (skip) {
+        r.acc = r.u[r.next++] & (0xFFu >> skip);
+        r.n = 8 - skip;
+    }
+}
+FB_HD void cr_refill(CleanReader& r) {
+    while (r.n <= 48) {
+        r.acc = (r.acc << 8) | r.u[r.next++];
+        r.n += 8;
+    }
+}
+FB_HD long long cr_pos(const CleanReader& r) { return 8 * r.next - r.n; }
+
+// Coefficient area address of block number q of the scan (MCU by MCU, blocks of an MCU in `lay` order).
+FB_HD int16_t* scan_block_ptr(int q, const JpegGeom& g, uint64_t lay, int nblk, int16_t* cimg) {
+    const int m = q / nblk, bi = q - m * nblk;
+    const int e = (int)(lay >> (4 * bi)) & 15, c = e & 3;
+    const int my = m / g.mcux, mx = m - my * g.mcux;
+    const int row = my * g.vs[c] + ((e >> 2) & 1), col = mx * g.hs[c] + ((e >> 3) & 1);
+    return cimg + g.coef_comp_off[c] + ((size_t)row * g.blocks_w[c] + col) * 64;
+}
+
+// Decode from state `st` up to the first symbol boundary at or after `limit_bits` (or the end of the data).
+// WRITE = false: only the state evolves (garbage from a wrong start state is tolerated: an invalid code skips one bit, an
+// overlong run ends the block).  WRITE = true: the start state is the true one; non-zero coefficients are stored into the
+// pre-zeroed coefficient area (DC as the decoded difference), block q is the first one touched; returns false on invalid data.
+template <bool WRITE>
+FB_HD bool span_decode(const uint8_t* u, long long len_bits, SyncState st, long long limit_bits, const JpegGeom& g, const JpegTableSet& T,
+                       const uint8_t* zz, uint64_t lay, int nblk, SyncState& out, int& blocks_done, int q, int total_blocks, int16_t* cimg) {
+    CleanReader r;
+    r.u = u;
+    cr_seek(r, st.pos);
+    int b = st.b, k = st.k;
+    blocks_done = 0;
+    bool ok = true;
+    int c = (int)(lay >> (4 * b)) & 3;
+    const JpegHuff* hd = &T.dc[g.td[c]];
+    const JpegHuff* ha = &T.ac[g.ta[c]];
+    int16_t* blk = (WRITE && q < total_blocks) ? scan_block_ptr(q, g, lay, nblk, cimg) : nullptr;
+    for (;;) {
+        const long long pos = cr_pos(r);
+        if (pos >= limit_bits || pos >= len_bits) break;
+        if (WRITE && q >= total_blocks) break;
+        cr_refill(r);
+        const bool isdc = k == 0;
+        const int sym = decode_symbol(r, isdc ? *hd : *ha);
+        if (sym < 0) {
+            if (WRITE) {
+                ok = false;
+                break;
+            }
+            r.n -= 1;
+            continue;
+        }
+        const int run = isdc ? 0 : sym >> 4;
+        const int size = isdc ? (sym & 15) : (sym & 15);
+        int val = 0;
+        if (size) {
+            const int v = (int)peek(r, size);
+            r.n -= size;
+            val = v < (1 << (size - 1)) ? v - (1 << size) + 1 : v;
+        }
+        if (isdc) {
+            if (WRITE && val) blk[0] = (int16_t)val;
+            k = 1;
+        } else if (size == 0) {
+            k = run == 15 ? k + 16 : 64;
+        } else {
+            k += run;
+            if (k > 63) {
+                if (WRITE) {
+                    ok = false;
+                    break;
+                }
+                k = 64;
+            } else {
+                if (WRITE) blk[zz[k]] = (int16_t)val;
+                ++k;
+            }
+        }
+        if (k >= 64) {
+            k = 0;
+            ++blocks_done;
+            b = b + 1 == nblk ? 0 : b + 1;
+            c = (int)(lay >> (4 * b)) & 3;
+            hd = &T.dc[g.td[c]];
+            ha = &T.ac[g.ta[c]];
+            if (WRITE) {
+                ++q;
+                if (q < total_blocks) blk = scan_block_ptr(q, g, lay, nblk, cimg);
+            }
+        }
+    }
+    out.pos = cr_pos(r);
+    out.b = b;
+    out.k = k;
+    return ok;
+}
+
+#ifndef FB_JPEG_HOST_TEST
+// stuffed zeros (0xFF 0x00) of one 16 KB chunk: WRITE = false counts them, WRITE = true copies the other bytes to their
+// position in the clean stream (counts then holds the exclusive prefix of the per-chunk counts)
+template <bool WRITE>
+__global__ void __launch_bounds__(kScanThreads) jpeg_unstuff_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
+                                                                    const long long* __restrict__ scan_len, int chunks, int* __restrict__ counts,
+                                                                    uint8_t* __restrict__ clean, long long clean_stride) {
+    __shared__ int s_cnt[kScanThreads];
+    constexpr int kPer = kScanChunk / kScanThreads;       // 64 bytes per thread
+    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* s = bytes + scan_off[img];
+    const long long len = scan_len[img];
+    const long long lo = (long long)chunk * kScanChunk + (long long)tid * kPer;
+    const long long hi = min(lo + kPer, len);
+    int mine = 0;
+    for (long long p = lo; p < hi; ++p) mine += (s[p] == 0x00 && p > 0 && s[p - 1] == 0xFF) ? 1 : 0;
+    s_cnt[tid] = mine;
+    __syncthreads();
+    for (int o = 1; o < kScanThreads; o <<= 1) {
+        const int v = tid >= o ? s_cnt[tid - o] : 0;
+        __syncthreads();
+        s_cnt[tid] += v;
+        __syncthreads();
+    }
+    if (!WRITE) {
+        if (tid == kScanThreads - 1) counts[(size_t)img * chunks + chunk] = s_cnt[tid];
+        return;
+    }
+    long long dst = lo - (counts[(size_t)img * chunks + chunk] + s_cnt[tid] - mine);
+    uint8_t* out = clean + (size_t)img * clean_stride;
+    for (long long p = lo; p < hi; ++p)
+        if (!(s[p] == 0x00 && p > 0 && s[p - 1] == 0xFF)) out[dst++] = s[p];
+}
+
+// exclusive prefix of the per-chunk counts of one image; clean_len[img] = scan_len - number of stuffed zeros
+__global__ void __launch_bounds__(256) jpeg_unstuff_prefix_kernel(int* __restrict__ counts, int chunks, const long long* __restrict__ scan_len,
+                                                                  long long* __restrict__ clean_len) {
+    __shared__ int s_part[256];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    int* c = counts + (size_t)img * chunks;
+    const int per = (chunks + 255) / 256;
+    const int lo = min(tid * per, chunks), hi = min(lo + per, chunks);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += c[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = c[i];
+        c[i] = run;
+        run += v;
+    }
+    if (tid == 255) clean_len[img] = scan_len[img] - s_part[255];
+}
+
+struct SyncArrays {
+    SyncState* state[2];     // [n][T] ping-pong: state at the end of every subsequence
+    int* blocks;             // [n][T] blocks completed inside the subsequence
+    int* first_block;        // [n][T] exclusive prefix of `blocks`
+    int* changed;            // [n][kSyncRounds + 1]
+    const long long* clean_len;
+    const uint8_t* clean;
+    long long clean_stride;
+    int T;
+};
+
+// round 0: every thread starts at the first bit of its subsequence in the guessed state (block 0, DC next) — true for thread 0.
+// round r >= 1: thread t starts from what thread t-1 recorded in round r-1; skipped (states copied) once a round changed nothing.
+__global__ void __launch_bounds__(128) jpeg_sync_kernel(SyncArrays A, const int* __restrict__ table_slot, const JpegTableSet* __restrict__ tables,
+                                                        JpegGeom g, int round) {
+    __shared__ __align__(16) uint8_t s_tab[sizeof(JpegTableSet)];
+    __shared__ uint8_t s_zz[64];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tables + table_slot[img]);
+        for (int i = tid; i < (int)(sizeof(JpegTableSet) / 16); i += blockDim.x) reinterpret_cast<uint4*>(s_tab)[i] = src[i];
+        if (tid < 64) s_zz[tid] = d_zigzag[tid];
+    }
+    __syncthreads();
+    const JpegTableSet& T = *reinterpret_cast<const JpegTableSet*>(s_tab);
+    const int t = blockIdx.x * blockDim.x + tid;
+    if (t >= A.T) return;
+    const long long len_bits = 8 * A.clean_len[img];
+    const SyncState* prev = A.state[(round + 1) & 1] + (size_t)img * A.T;
+    SyncState* cur = A.state[round & 1] + (size_t)img * A.T;
+    if (round >= 2 && A.changed[img * (kSyncRounds + 1) + round - 1] == 0) {
+        cur[t] = prev[t];                       // already stable
+        return;
+    }
+    const long long start = (long long)t * kSubseqBytes * 8, limit = start + (long long)kSubseqBytes * 8;
+    SyncState st;
+    if (start >= len_bits) {
+        st.pos = len_bits;
+        st.b = st.k = 0;
+        cur[t] = st;
+        A.blocks[(size_t)img * A.T + t] = 0;
+        return;
+    }
+    if (round == 0 || t == 0) {
+        st.pos = start;
+        st.b = st.k = 0;
+    } else {
+        st = prev[t - 1];
+    }
+    int nblk, done;
+    const uint64_t lay = mcu_layout(g, nblk);
+    SyncState out;
+    span_decode<false>(A.clean + (size_t)img * A.clean_stride, len_bits, st, limit, g, T, s_zz, lay, nblk, out, done, 0, 0, nullptr);
+    if (round >= 1) {
+        const SyncState old = prev[t];
+        if (old.pos != out.pos || old.b != out.b || old.k != out.k) atomicOr(A.changed + img * (kSyncRounds + 1) + round, 1);
+    }
+    cur[t] = out;
+    A.blocks[(size_t)img * A.T + t] = done;
+}
+
+// first_block[t] = number of blocks completed before subsequence t; status bit 2 when the rounds did not settle, bit 1 when the
+// stream holds fewer blocks than the frame needs
+__global__ void __launch_bounds__(1024) jpeg_sync_prefix_kernel(SyncArrays A, int total_blocks, int* __restrict__ status) {
+    __shared__ int s_part[1024];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int* nb = A.blocks + (size_t)img * A.T;
+    int* fb = A.first_block + (size_t)img * A.T;
+    const int per = (A.T + 1023) / 1024;
+    const int lo = min(tid * per, A.T), hi = min(lo + per, A.T);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += nb[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) {
+        fb[i] = run;
+        run += nb[i];
+    }
+    if (tid == 1023) {
+        if (s_part[1023] < total_blocks) atomicOr(status + img, 2);
+        if (A.changed[img * (kSyncRounds + 1) + kSyncRounds]) atomicOr(status + img, 4);
+    }
+}
+
+__global__ void __launch_bounds__(128) jpeg_sync_write_kernel(SyncArrays A, const int* __restrict__ table_slot, const JpegTableSet* __restrict__ tables,
+                                                              JpegGeom g, int total_blocks, int16_t* __restrict__ coef, int* __restrict__ status) {
+    __shared__ __align__(16) uint8_t s_tab[sizeof(JpegTableSet)];
+    __shared__ uint8_t s_zz[64];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tables + table_slot[img]);
+        for (int i = tid; i < (int)(sizeof(JpegTableSet) / 16); i += blockDim.x) reinterpret_cast<uint4*>(s_tab)[i] = src[i];
+        if (tid < 64) s_zz[tid] = d_zigzag[tid];
+    }
+    __syncthreads();
+    const JpegTableSet& T = *reinterpret_cast<const JpegTableSet*>(s_tab);
+    const int t = blockIdx.x * blockDim.x + tid;
+    if (t >= A.T || status[img]) return;
+    const long long len_bits = 8 * A.clean_len[img];
+    const long long start = (long long)t * kSubseqBytes * 8, limit = start + (long long)kSubseqBytes * 8;
+    if (start >= len_bits) return;
+    const SyncState* fin = A.state[kSyncRounds & 1] + (size_t)img * A.T;
+    SyncState st;
+    if (t == 0) {
+        st.pos = 0;
+        st.b = st.k = 0;
+    } else {
+        st = fin[t - 1];
+    }
+    int nblk, done;
+    const uint64_t lay = mcu_layout(g, nblk);
+    SyncState out;
+    const bool ok = span_decode<true>(A.clean + (size_t)img * A.clean_stride, len_bits, st, limit, g, T, s_zz, lay, nblk, out, done,
+                                      A.first_block[(size_t)img * A.T + t], total_blocks, coef + (size_t)img * g.coef_image_stride);
+    if (!ok) atomicOr(status + img, 2);
+}
+
+// DC differences -> DC values: inclusive prefix sum over the blocks of one component in scan order (one CTA per image and
+// component; every thread owns a contiguous run of blocks)
+__global__ void __launch_bounds__(1024) jpeg_dc_prefix_kernel(int16_t* __restrict__ coef, JpegGeom g) {
+    __shared__ int s_part[1024];
+    const int img = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    int16_t* base = coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c];
+    const int per_mcu = g.hs[c] * g.vs[c];
+    const int count = g.mcux * g.mcuy * per_mcu;
+    auto dc_ptr = [&](int j) -> int16_t* {
+        const int m = j / per_mcu, r = j - m * per_mcu;
+        const int by = r / g.hs[c], bx = r - by * g.hs[c];
+        const int my = m / g.mcux, mx = m - my * g.mcux;
+        return base + ((size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx)) * 64;
+    };
+    const int per = (count + 1023) / 1024;
+    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    int sum = 0;
+    for (int j = lo; j < hi; ++j) sum += *dc_ptr(j);
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int j = lo; j < hi; ++j) {
+        int16_t* p = dc_ptr(j);
+        run += *p;
+        *p = (int16_t)run;
+    }
+}
+#endif  // FB_JPEG_HOST_TEST
+
 // ---- inverse DCT (jidctint.c, jpeg_idct_islow) ------------------------------------------------------------------------
 constexpr int CONST_BITS = 13, PASS1_BITS = 2;
 #define FIX_0_298631336 2446
@@ -655,6 +1011,11 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restri
 }  // namespace
 
 #ifndef FB_JPEG_HOST_TEST
+constexpr int kSerialMcus = 1024;        // streams without restart markers up to this size take the one-thread-per-stream path
+
+static long long selfsync_subsequences(long long max_scan_bytes) { return (max_scan_bytes + kSubseqBytes - 1) / kSubseqBytes + 1; }
+static long long selfsync_clean_stride(long long max_scan_bytes) { return (max_scan_bytes + 64 + 255) & ~255ll; }
+
 size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, int vs0, int restart_interval, long long max_scan_bytes) {
     const int hmax = hs0, vmax = vs0;
     const long long mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
@@ -663,7 +1024,13 @@ size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, in
     const long long n_iv = restart_interval > 0 ? (total_mcus + restart_interval - 1) / restart_interval : 1;
     const long long chunks = (max_scan_bytes + kScanChunk - 1) / kScanChunk + 1;
     auto al = [](long long x) { return (x + 255) & ~255ll; };
-    return (size_t)(al(blocks * 128 * n) + al(blocks * 64 * n) + al(n_iv * 4 * n) + al(chunks * 4 * n) + 256);
+    long long total = al(blocks * 128 * n) + al(blocks * 64 * n) + al(n_iv * 4 * n) + al(chunks * 4 * n) + 256;
+    if (restart_interval <= 0 && total_mcus > kSerialMcus) {
+        const long long T = selfsync_subsequences(max_scan_bytes);
+        total += al(selfsync_clean_stride(max_scan_bytes) * n) + al(8ll * n) + 2 * al((long long)sizeof(SyncState) * T * n) +
+                 2 * al(4 * T * n) + al(4ll * (kSyncRounds + 1) * n);
+    }
+    return (size_t)total;
 }
 
 int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, const long long* d_scan_len, const int* d_table_slot,
@@ -719,25 +1086,61 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
     int* counts = reinterpret_cast<int*>(w);
     const int chunks = (int)((max_scan_bytes + kScanChunk - 1) / kScanChunk + 1);
 
+    w += al((long long)chunks * 4 * n);
+    const bool selfsync = g.restart_interval == 0 && total_mcus > kSerialMcus;
+    const JpegTableSet* tables = reinterpret_cast<const JpegTableSet*>(d_tables);
+
     FB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int) * n, stream));
-    if (g.n_intervals > 1) {
-        dim3 grid(chunks, n);
-        jpeg_restart_scan_kernel<false><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
-        jpeg_restart_prefix_kernel<<<n, 256, 0, stream>>>(counts, chunks, g.n_intervals, starts, d_status);
-        jpeg_restart_scan_kernel<true><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
+    if (selfsync) {
+        // no restart markers: unstuff, find the true decoder state at every subsequence boundary, decode, integrate the DC
+        SyncArrays A;
+        A.T = (int)selfsync_subsequences(max_scan_bytes);
+        A.clean_stride = selfsync_clean_stride(max_scan_bytes);
+        uint8_t* clean = w;
+        w += al(A.clean_stride * n);
+        long long* clean_len = reinterpret_cast<long long*>(w);
+        w += al(8ll * n);
+        for (int i = 0; i < 2; ++i) {
+            A.state[i] = reinterpret_cast<SyncState*>(w);
+            w += al((long long)sizeof(SyncState) * A.T * n);
+        }
+        A.blocks = reinterpret_cast<int*>(w);
+        w += al(4ll * A.T * n);
+        A.first_block = reinterpret_cast<int*>(w);
+        w += al(4ll * A.T * n);
+        A.changed = reinterpret_cast<int*>(w);
+        A.clean = clean;
+        A.clean_len = clean_len;
+        const int total_blocks = (int)(blocks);
+        FB_REQUIRE(blocks < (1ll << 31), "fb_jpeg_decode: frame too large");
+        FB_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)blocks * 128 * n, stream));
+        FB_CUDA_OK(cudaMemsetAsync(clean, 0, (size_t)A.clean_stride * n, stream));
+        FB_CUDA_OK(cudaMemsetAsync(A.changed, 0, sizeof(int) * (kSyncRounds + 1) * n, stream));
+        dim3 cgrid(chunks, n);
+        jpeg_unstuff_kernel<false><<<cgrid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, counts, clean, A.clean_stride);
+        jpeg_unstuff_prefix_kernel<<<n, 256, 0, stream>>>(counts, chunks, d_scan_len, clean_len);
+        jpeg_unstuff_kernel<true><<<cgrid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, counts, clean, A.clean_stride);
+        dim3 sgrid((A.T + 127) / 128, n);
+        for (int round = 0; round <= kSyncRounds; ++round) jpeg_sync_kernel<<<sgrid, 128, 0, stream>>>(A, d_table_slot, tables, g, round);
+        jpeg_sync_prefix_kernel<<<n, 1024, 0, stream>>>(A, total_blocks, d_status);
+        jpeg_sync_write_kernel<<<sgrid, 128, 0, stream>>>(A, d_table_slot, tables, g, total_blocks, coef, d_status);
+        jpeg_dc_prefix_kernel<<<dim3(n, ncomp), 1024, 0, stream>>>(coef, g);
     } else {
-        FB_CUDA_OK(cudaMemsetAsync(starts, 0, sizeof(uint32_t) * n, stream));
-    }
-    {
+        if (g.n_intervals > 1) {
+            dim3 grid(chunks, n);
+            jpeg_restart_scan_kernel<false><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
+            jpeg_restart_prefix_kernel<<<n, 256, 0, stream>>>(counts, chunks, g.n_intervals, starts, d_status);
+            jpeg_restart_scan_kernel<true><<<grid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, g.n_intervals, counts, starts);
+        } else {
+            FB_CUDA_OK(cudaMemsetAsync(starts, 0, sizeof(uint32_t) * n, stream));
+        }
         dim3 grid((g.n_intervals + kHuffThreads - 1) / kHuffThreads, n);
         static bool attr_set = false;
         if (!attr_set) {
             FB_CUDA_OK(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem));
             attr_set = true;
         }
-        jpeg_huffman_kernel<<<grid, kHuffThreads, kHuffSmem, stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot,
-                                                                                reinterpret_cast<const JpegTableSet*>(d_tables), starts, g, coef,
-                                                                                d_status);
+        jpeg_huffman_kernel<<<grid, kHuffThreads, kHuffSmem, stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot, tables, starts, g, coef, d_status);
     }
     {
         const long long total = blocks * n;

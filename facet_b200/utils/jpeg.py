@@ -7,9 +7,9 @@ quantisation and Huffman tables out for csrc/jpeg_decode.cu.  Entropy decoding, 
 colour conversion all run on the device (`ops.jpeg_decode`), byte-exact with Pillow's output.
 
 Supported: baseline / extended sequential Huffman, 8 bit, 1 or 3 components in one interleaved scan, luma sampling
-1x1, 2x1 or 2x2 with 1x1 chroma (4:4:4, 4:2:2, 4:2:0) — what cameras and Pillow write.  Progressive, arithmetic-coded,
-12-bit, CMYK and multi-scan files raise `UnsupportedJpeg` (the caller keeps its CPU loader for those, as the
-reference does for RAW files).
+1x1, 2x1 or 2x2 with 1x1 chroma (4:4:4, 4:2:2, 4:2:0) — what cameras and Pillow write — with restart markers (one thread
+per restart interval) or without (self-synchronising parallel decoding).  Progressive, arithmetic-coded, 12-bit, CMYK and
+multi-scan files raise `UnsupportedJpeg` (the caller keeps its CPU loader for those, as the reference does for RAW files).
 """
 from __future__ import annotations
 
@@ -21,7 +21,8 @@ ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 1
                    28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
                    54, 47, 55, 62, 63], dtype=np.int64)      # zigzag position -> natural (row-major) index
 
-MAX_SERIAL_MCUS = 16384      # largest stream without restart markers the device decoder accepts (1 MP at 4:4:4, 4 MP at 4:2:0)
+SERIAL_MCUS = 1024           # streams without restart markers up to this many MCUs are decoded by one thread; larger ones by the
+                             # self-synchronising scheme of csrc/jpeg_decode.cu (kSerialMcus there)
 LUT_BITS = 9
 # one Huffman table on the device: uint16 lut[512] | int32 maxcode[18] | int32 valptr[17] | uint8 values[256]  (see JpegHuff in
 # csrc/jpeg_decode.cu); a table set = uint16 q[4][64] + 4 DC + 4 AC tables
@@ -189,12 +190,6 @@ def parse(data, head_bytes: int = 1 << 16) -> JpegInfo:
                 if (info.tq[c] not in info.qtables or info.tq[c] > 3 or (0, info.td[c]) not in info.huff
                         or (1, info.ta[c]) not in info.huff or info.td[c] > 3 or info.ta[c] > 3):
                     raise UnsupportedJpeg("a table referenced by the scan is missing")
-            hmax, vmax = max(info.hs), max(info.vs)
-            mcus = -(-info.width // (8 * hmax)) * -(-info.height // (8 * vmax))
-            if info.restart_interval == 0 and mcus > MAX_SERIAL_MCUS:
-                # DC prediction chains every block of such a stream: its entropy decoding is one sequential pass (one GPU
-                # thread).  Small images are fine; big ones go to the caller's CPU loader, like every file of the reference
-                raise UnsupportedJpeg(f"no restart markers ({mcus} MCUs in one interval): sequential entropy decoding")
             info.scan_offset = pos + seglen
             # the entropy-coded segment ends at the EOI marker: normally the last two bytes of the file
             tail = bytes(memoryview(data)[max(info.scan_offset, total - 4096):total]) if not isinstance(data, (bytes, bytearray)) else None

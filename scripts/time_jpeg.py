@@ -17,11 +17,11 @@ from facet_b200.utils import jpeg as fj  # noqa: E402
 H, W = 4000, 6000
 res = {}
 for name, gen in (("int", lambda i: synth_frame_int(i, H, W)), ("photo", lambda i: synth_image_bgr(2000 + i, H, W))):
-    for ri in (8, 25, 375):
+    for ri in (8, 25, 375, 0):
         kw = {"quality": 90}
         if ri:
             kw["restart_marker_blocks"] = ri
-        if ri in (0, 375) and name == "photo":
+        if ri == 375 and name == "photo":
             continue
         datas = []
         t0 = time.perf_counter()
@@ -33,7 +33,7 @@ for name, gen in (("int", lambda i: synth_frame_int(i, H, W)), ("photo", lambda 
         t0 = time.perf_counter()
         Image.open(io.BytesIO(datas[0].tobytes())).convert("RGB").load()
         pil_ms = (time.perf_counter() - t0) * 1e3
-        n = (32 if ri == 8 else 16) if ri else 2
+        n = 32 if ri in (0, 8) else 16
         streams = [datas[i % 2] for i in range(n)]
         infos = [fj.parse(s) for s in streams]
         slot = (max(len(s) for s in streams) + 255) & ~255

@@ -56,8 +56,6 @@ def test_bgr_order_orientation_and_errors():
         assert got.shape == want.shape and np.array_equal(got[:, :, ::-1], want), code
     with pytest.raises(fj.UnsupportedJpeg):
         ops.jpeg_decode([encode(rgb, quality=80, progressive=True)])
-    with pytest.raises(fj.UnsupportedJpeg, match="restart markers"):      # a big stream without DRI is one sequential interval
-        fj.parse(encode(np.zeros((2400, 3200, 3), np.uint8), quality=80))
     good = encode(rgb, quality=90, restart_marker_blocks=5)
     info = fj.parse(good)
     # a restart marker removed -> the marker count no longer matches the DRI header
@@ -69,6 +67,24 @@ def test_bgr_order_orientation_and_errors():
         ops.jpeg_decode([good, encode(rgb[:64], quality=90, restart_marker_blocks=5)])
 
 
+@pytest.mark.parametrize("shape", [(300, 420), (683, 1024), (1200, 1600), (2000, 3008)])
+def test_streams_without_restart_markers(shape):
+    """No DRI: above 1024 MCUs the self-synchronising scheme runs (unstuff, guessed-state rounds, block prefix, DC integration);
+    below, one thread per stream.  Photo-like and pure-noise content, every sampling mode, optimised tables, grayscale."""
+    from facet_b200 import ops
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    photo = synth_image_bgr(9, h, w)[:, :, ::-1].copy()
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for kw in ({"quality": 85}, {"quality": 95, "subsampling": 0}, {"quality": 40, "subsampling": 1}, {"quality": 92, "optimize": True}):
+        datas = [encode(photo, **kw), encode(noise, **kw)]
+        got = ops.jpeg_decode(datas, bgr=False).cpu().numpy()
+        for g, d in zip(got, datas):
+            assert np.array_equal(g, pil_rgb(d)), (shape, kw)
+    d = encode(photo[:, :, 1].copy(), quality=80)
+    assert np.array_equal(ops.jpeg_decode([d], bgr=False).cpu().numpy()[0], pil_rgb(d))
+
+
 def test_full_size_frame_24mp():
     """6000 x 4000 4:2:0 with restart intervals of 25 MCUs (the loader setting the bench uses) against Pillow."""
     from facet_b200 import ops
@@ -77,3 +93,7 @@ def test_full_size_frame_24mp():
     want = pil_rgb(data)
     got = ops.jpeg_decode([data, data], bgr=True).cpu().numpy()
     assert np.array_equal(got[0][:, :, ::-1], want) and np.array_equal(got[1], got[0])
+    # the same frame as a camera would write it: no restart markers (self-synchronising path)
+    data = encode(rgb, quality=90)
+    got = ops.jpeg_decode([data], bgr=False).cpu().numpy()
+    assert np.array_equal(got[0], pil_rgb(data))

@@ -99,7 +99,7 @@ def host_tool():
     return exe
 
 
-def run_host_tool(exe, data, tmp_path, bgr=0):
+def run_host_tool(exe, data, tmp_path, bgr=0, selfsync=0):
     info = fj.parse(data)
     pad = lambda v: (list(v) + [1, 1, 1])[:3] if v is info.hs or v is info.vs else (list(v) + [0, 0, 0])[:3]
     hdr = np.zeros(32, np.int32)
@@ -107,6 +107,7 @@ def run_host_tool(exe, data, tmp_path, bgr=0):
     hdr[3:6], hdr[6:9], hdr[9:12], hdr[12:15] = pad(info.hs), pad(info.vs), pad(info.tq), pad(info.td)
     hdr[15], hdr[16], hdr[17] = info.restart_interval, bgr, info.scan_end - info.scan_offset
     hdr[18:21] = pad(info.ta)
+    hdr[21] = selfsync
     req, out = tmp_path / "req.bin", tmp_path / "out.bin"
     req.write_bytes(hdr.tobytes() + fj.pack_tables(info) + data[info.scan_offset:info.scan_end])
     subprocess.check_call([exe, str(req), str(out)])
@@ -121,3 +122,22 @@ def test_device_function_bodies_match_pillow_on_the_host(host_tool, tmp_path):
         assert np.array_equal(got, want), (arr.shape, kw, int(np.abs(got.astype(int) - want).max()))
     data = encode(synth_image_bgr(2, 97, 131)[:, :, ::-1].copy(), quality=90, restart_marker_blocks=5)
     assert np.array_equal(run_host_tool(host_tool, data, tmp_path, bgr=1), pil_rgb(data)[:, :, ::-1])
+
+
+def test_self_synchronising_decode_matches_pillow_on_the_host(host_tool, tmp_path):
+    """Streams WITHOUT restart markers through the self-synchronising scheme (subsequences decoded from guessed states, rounds
+    until the boundary states are stable, block-index prefix sum, DC differences integrated afterwards), executed sequentially
+    by the host tool with the kernels' own functions."""
+    rng = np.random.default_rng(5)
+    for (h, w) in [(64, 80), (250, 331), (683, 1024), (1200, 1600)]:
+        photo = synth_image_bgr(4, h, w)[:, :, ::-1].copy()
+        noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for arr in (photo, noise):
+            for kw in ({"quality": 85}, {"quality": 95, "subsampling": 0}, {"quality": 40, "subsampling": 1}, {"quality": 92, "optimize": True}):
+                data = encode(arr, **kw)
+                assert fj.parse(data).restart_interval == 0
+                got = run_host_tool(host_tool, data, tmp_path, selfsync=1)
+                assert np.array_equal(got, pil_rgb(data)), (arr.shape, kw)
+    gray = synth_image_bgr(5, 500, 700)[:, :, 0].copy()
+    data = encode(gray, quality=80)
+    assert np.array_equal(run_host_tool(host_tool, data, tmp_path, selfsync=1), pil_rgb(data))
