@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
 //   5. a prefix sum per component turns the DC differences into DC values (jpeg_dc_prefix_kernel).
 constexpr int kSubseqBytes = 512;
 #ifndef FB_SYNC_ROUNDS
-#define FB_SYNC_ROUNDS 16
+#define FB_SYNC_ROUNDS 48
 #endif
 constexpr int kSyncRounds = FB_SYNC_ROUNDS;           // rounds after round 0; a stream that still changes then is reported (status bit 2)
 
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) jpeg_unstuff_prefix_kernel(int* __restric
 }
 
 struct SyncArrays {
-    SyncState* state[2];     // [n][T] ping-pong: state at the end of every subsequence
+    SyncState* state[3];     // [n][T], rotating over the rounds: state at the end of every subsequence
     int* blocks;             // [n][T] blocks completed inside the subsequence
     int* first_block;        // [n][T] exclusive prefix of `blocks`
     int* changed;            // [n][kSyncRounds + 1]
@@ -623,10 +623,23 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(SyncArrays A, const int*
     const int t = blockIdx.x * blockDim.x + tid;
     if (t >= A.T) return;
     const long long len_bits = 8 * A.clean_len[img];
-    const SyncState* prev = A.state[(round + 1) & 1] + (size_t)img * A.T;
-    SyncState* cur = A.state[round & 1] + (size_t)img * A.T;
+    const SyncState* prev = A.state[(round + 2) % 3] + (size_t)img * A.T;        // round - 1
+    const SyncState* prev2 = A.state[(round + 1) % 3] + (size_t)img * A.T;       // round - 2
+    SyncState* cur = A.state[round % 3] + (size_t)img * A.T;
     if (round >= 2 && A.changed[img * (kSyncRounds + 1) + round - 1] == 0) {
-        cur[t] = prev[t];                       // already stable
+        cur[t] = prev[t];                       // the whole stream is already stable
+        return;
+    }
+    if (round >= 2 && t >= 1) {
+        // same start state as in the previous round -> same result (only the front of corrections is decoded again)
+        const SyncState a = prev[t - 1], b2 = prev2[t - 1];
+        if (a.pos == b2.pos && a.b == b2.b && a.k == b2.k) {
+            cur[t] = prev[t];
+            return;
+        }
+    }
+    if (round >= 1 && t == 0) {
+        cur[0] = prev[0];
         return;
     }
     const long long start = (long long)t * kSubseqBytes * 8, limit = start + (long long)kSubseqBytes * 8;
@@ -703,7 +716,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_write_kernel(SyncArrays A, cons
     const long long len_bits = 8 * A.clean_len[img];
     const long long start = (long long)t * kSubseqBytes * 8, limit = start + (long long)kSubseqBytes * 8;
     if (start >= len_bits) return;
-    const SyncState* fin = A.state[kSyncRounds & 1] + (size_t)img * A.T;
+    const SyncState* fin = A.state[kSyncRounds % 3] + (size_t)img * A.T;
     SyncState st;
     if (t == 0) {
         st.pos = 0;
@@ -1027,7 +1040,7 @@ size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, in
     long long total = al(blocks * 128 * n) + al(blocks * 64 * n) + al(n_iv * 4 * n) + al(chunks * 4 * n) + 256;
     if (restart_interval <= 0 && total_mcus > kSerialMcus) {
         const long long T = selfsync_subsequences(max_scan_bytes);
-        total += al(selfsync_clean_stride(max_scan_bytes) * n) + al(8ll * n) + 2 * al((long long)sizeof(SyncState) * T * n) +
+        total += al(selfsync_clean_stride(max_scan_bytes) * n) + al(8ll * n) + 3 * al((long long)sizeof(SyncState) * T * n) +
                  2 * al(4 * T * n) + al(4ll * (kSyncRounds + 1) * n);
     }
     return (size_t)total;
@@ -1100,7 +1113,7 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         w += al(A.clean_stride * n);
         long long* clean_len = reinterpret_cast<long long*>(w);
         w += al(8ll * n);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             A.state[i] = reinterpret_cast<SyncState*>(w);
             w += al((long long)sizeof(SyncState) * A.T * n);
         }
