@@ -565,52 +565,58 @@ def main():
             from PIL import Image
             n_src = min(16, eb)
             rgb = [host[i].numpy()[:, :, ::-1].copy() for i in range(n_src)]
-
-            def enc(a):
-                buf = io.BytesIO()
-                Image.fromarray(a).save(buf, "JPEG", quality=90, restart_marker_blocks=args.jpeg_restart_blocks)
-                return buf.getvalue()
-
-            t_enc = time.perf_counter()
-            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-                streams = list(ex.map(enc, rgb))
-            t_enc = time.perf_counter() - t_enc
-            t_dec = time.perf_counter()
-            Image.open(io.BytesIO(streams[0])).convert("RGB").load()
-            pil_decode_ms = (time.perf_counter() - t_dec) * 1e3
-            del rgb
-            pinned = []
-            for st_ in streams:
-                pt = torch.empty(len(st_), dtype=torch.uint8, pin_memory=True)
-                pt.numpy()[:] = np.frombuffer(st_, np.uint8)
-                pinned.append(pt)
-            jitems = [{"path": f"/bench/rank{rank}/jpg_{j:06d}.jpg", "jpeg": pinned[j % n_src].numpy()} for j in range(B * n_e2e)]
             jchunk = args.e2e_jpeg_chunk
-            bp.process_items_streamed(jitems[:max(2 * jchunk, vit_batch)], chunk=jchunk, vit_batch=vit_batch)        # warm-up
-            barrier()
-            bp.metrics["h2d_bytes"] = bp.metrics["d2h_bytes"] = 0
-            t0 = time.perf_counter()
-            jres = bp.process_items_streamed(jitems, chunk=jchunk, vit_batch=vit_batch)
-            assert all("error" not in r for r in jres), "e2e_jpeg: a stream failed"
-            emb = torch.from_numpy(np.frombuffer(b"".join(r["clip_embedding"] for r in jres), dtype=np.float32).reshape(-1, 768).copy()).to(device)
-            hh = torch.from_numpy(np.array([int(r["phash"], 16) for r in jres], dtype=np.uint64).view(np.int64)).to(device)
-            grouping(emb, hh)
-            barrier()
-            ms_j = (time.perf_counter() - t0) * 1e3
-            if world > 1:
-                t = torch.tensor([ms_j], device=device)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_j = float(t.item())
-            e2e["from_jpeg_bytes"] = {
-                "value": world * len(jitems) / (ms_j * 1e-3), "unit": "images/s", "images_per_gpu": len(jitems),
-                "input": f"{n_src} distinct 24 MP frames of the pool as baseline JPEG (Pillow, quality 90, 4:2:0, restart interval "
-                         f"{args.jpeg_restart_blocks} MCUs), {sum(len(x) for x in streams) / n_src / 1e6:.2f} MB each, in pinned host memory",
-                "h2d_bytes_per_step": bp.metrics["h2d_bytes"] // n_e2e, "d2h_bytes_per_step": bp.metrics["d2h_bytes"] // n_e2e,
-                "chunk_streams": jchunk, "pillow_decode_ms_per_image_one_core": pil_decode_ms, "pillow_encode_s_total": t_enc,
-                "note": "same call, items carry the file bytes instead of decoded frames: PCIe moves ~14x fewer bytes and the decode "
-                        "(byte-exact with Pillow, tests/test_gpu_jpeg.py) runs on the GPU; the reference arm starts from decoded frames, "
-                        "so the headline e2e above stays the raw-frame figure"}
-            del pinned
+
+            def jpeg_leg(restart_blocks):
+                def enc(a):
+                    buf = io.BytesIO()
+                    kw = {"restart_marker_blocks": restart_blocks} if restart_blocks else {}
+                    Image.fromarray(a).save(buf, "JPEG", quality=90, **kw)
+                    return buf.getvalue()
+
+                t_enc = time.perf_counter()
+                with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+                    streams = list(ex.map(enc, rgb))
+                t_enc = time.perf_counter() - t_enc
+                t_dec = time.perf_counter()
+                Image.open(io.BytesIO(streams[0])).convert("RGB").load()
+                pil_decode_ms = (time.perf_counter() - t_dec) * 1e3
+                pinned = []
+                for st_ in streams:
+                    pt = torch.empty(len(st_), dtype=torch.uint8, pin_memory=True)
+                    pt.numpy()[:] = np.frombuffer(st_, np.uint8)
+                    pinned.append(pt)
+                jitems = [{"path": f"/bench/rank{rank}/jpg_{j:06d}.jpg", "jpeg": pinned[j % n_src].numpy()} for j in range(B * n_e2e)]
+                bp.process_items_streamed(jitems[:max(2 * jchunk, vit_batch)], chunk=jchunk, vit_batch=vit_batch)        # warm-up
+                barrier()
+                bp.metrics["h2d_bytes"] = bp.metrics["d2h_bytes"] = 0
+                t0 = time.perf_counter()
+                jres = bp.process_items_streamed(jitems, chunk=jchunk, vit_batch=vit_batch)
+                assert all("error" not in r for r in jres), "e2e_jpeg: a stream failed"
+                emb = torch.from_numpy(np.frombuffer(b"".join(r["clip_embedding"] for r in jres), dtype=np.float32).reshape(-1, 768).copy()).to(device)
+                hh = torch.from_numpy(np.array([int(r["phash"], 16) for r in jres], dtype=np.uint64).view(np.int64)).to(device)
+                grouping(emb, hh)
+                barrier()
+                ms_j = (time.perf_counter() - t0) * 1e3
+                if world > 1:
+                    t = torch.tensor([ms_j], device=device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_j = float(t.item())
+                return {"value": world * len(jitems) / (ms_j * 1e-3), "unit": "images/s", "images_per_gpu": len(jitems),
+                        "input": f"{n_src} distinct 24 MP frames of the pool as baseline JPEG (Pillow, quality 90, 4:2:0, "
+                                 + (f"restart interval {restart_blocks} MCUs" if restart_blocks else "NO restart markers, as cameras write them")
+                                 + f"), {sum(len(x) for x in streams) / n_src / 1e6:.2f} MB each, in pinned host memory",
+                        "h2d_bytes_per_step": bp.metrics["h2d_bytes"] // n_e2e, "d2h_bytes_per_step": bp.metrics["d2h_bytes"] // n_e2e,
+                        "chunk_streams": jchunk, "pillow_decode_ms_per_image_one_core": pil_decode_ms, "pillow_encode_s_total": t_enc}
+
+            e2e["from_jpeg_bytes"] = jpeg_leg(args.jpeg_restart_blocks)
+            e2e["from_jpeg_bytes"]["note"] = (
+                "same call, items carry the file bytes instead of decoded frames: PCIe moves ~14x fewer bytes and the decode (byte-exact "
+                "with Pillow, tests/test_gpu_jpeg.py) runs on the GPU, one thread per restart interval; the reference arm starts from "
+                "decoded frames, so the headline e2e above stays the raw-frame figure")
+            e2e["from_jpeg_bytes_no_restart_markers"] = jpeg_leg(0)
+            e2e["from_jpeg_bytes_no_restart_markers"]["note"] = "entropy decoding by the self-synchronising scheme (csrc/jpeg_decode.cu)"
+            del rgb
         del host
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the same bounded sample `--impl reference` runs -------------
