@@ -571,7 +571,8 @@ def jpeg_decode(streams, bgr: bool = True, apply_orientation: bool = True):
     st = status.cpu().numpy()
     if st.any():
         bad = int(np.flatnonzero(st)[0])
-        raise RuntimeError(f"JPEG stream {bad}: " + ("restart markers do not match the DRI header" if st[bad] & 1 else "invalid Huffman data"))
+        raise RuntimeError(f"JPEG stream {bad}: " + ("restart markers do not match the DRI header" if st[bad] & 1 else
+                                                     "self-synchronisation did not settle" if st[bad] & 4 else "invalid Huffman data"))
     if apply_orientation:
         codes = {i.orientation for i in infos}
         if codes != {1}:

@@ -168,8 +168,9 @@ int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_st
 /* ---------------------------------------------------------------------------------------
  * JPEG decoding — replaces the decode of `load_image_from_path` (utils/image_loading.py:90-106: `Image.open(path)`,
  * `.convert('RGB')` through Pillow / libjpeg-turbo, `cv2.cvtColor(RGB2BGR)`), byte-exact with Pillow's output:
- * Huffman decoding (one thread per restart interval), dequantisation + libjpeg's `jpeg_idct_islow`, h2v1 / h2v2
- * "fancy" chroma upsampling, `ycc_rgb_convert`.  One call decodes a batch of streams of EQUAL geometry (size,
+ * Huffman decoding (one thread per restart interval; streams without restart markers above 1024 MCUs by
+ * self-synchronising parallel decoding), dequantisation + libjpeg's `jpeg_idct_islow`, h2v1 / h2v2 "fancy" chroma
+ * upsampling, `ycc_rgb_convert`.  One call decodes a batch of streams of EQUAL geometry (size,
  * components, sampling factors, restart interval); tables may differ per stream.
  *
  * d_bytes         the streams' bytes, concatenated anywhere in one device buffer
@@ -181,9 +182,10 @@ int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_st
  *                 length << 8 | symbol), int32 maxcode[18], int32 valptr[17], uint8 values[256], 4 bytes padding)
  * hs3 .. ta3      HOST arrays of 3 ints: sampling factors, quantisation / DC / AC table ids per component
  *                 (luma 1x1, 2x1 or 2x2 with 1x1 chroma; ncomp = 1 uses entry 0 with 1x1)
- * restart_interval  MCUs per restart interval (DRI), 0 = none: such a stream is ONE interval = one thread
+ * restart_interval  MCUs per restart interval (DRI), 0 = none
  * d_frames        [n][height][width][3] uint8, BGR when bgr_order (what the analyzers take) else RGB
- * d_status        [n] int32: 0 ok, bit 0 = restart markers do not match the header, bit 1 = invalid Huffman data
+ * d_status        [n] int32: 0 ok, bit 0 = restart markers do not match the header, bit 1 = invalid / truncated Huffman data,
+ *                 bit 2 = the self-synchronisation rounds did not settle (48 rounds)
  * The orientation (EXIF) is not applied here: fb_orient does that on the decoded frames. */
 size_t fb_jpeg_workspace_bytes(int n, int width, int height, int ncomp, int h0, int v0, int restart_interval, int64_t max_scan_bytes);
 int fb_jpeg_decode(const uint8_t* d_bytes, const int64_t* d_scan_offset, const int64_t* d_scan_bytes, const int32_t* d_table_slot,
