@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
 //   5. a prefix sum per component turns the DC differences into DC values (jpeg_dc_prefix_kernel).
 constexpr int kSubseqBytes = 512;
 #ifndef FB_SYNC_ROUNDS
-#define FB_SYNC_ROUNDS 48
+#define FB_SYNC_ROUNDS 24
 #endif
 constexpr int kSyncRounds = FB_SYNC_ROUNDS;           // rounds after round 0; a stream that still changes then is reported (status bit 2)
 
@@ -600,6 +600,7 @@ struct SyncArrays {
     int* blocks;             // [n][T] blocks completed inside the subsequence
     int* first_block;        // [n][T] exclusive prefix of `blocks`
     int* changed;            // [n][kSyncRounds + 1]
+    int* settled;            // [n]: 0, or 1 + the round that changed nothing (its states are the true ones)
     const long long* clean_len;
     const uint8_t* clean;
     long long clean_stride;
@@ -626,10 +627,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(SyncArrays A, const int*
     const SyncState* prev = A.state[(round + 2) % 3] + (size_t)img * A.T;        // round - 1
     const SyncState* prev2 = A.state[(round + 1) % 3] + (size_t)img * A.T;       // round - 2
     SyncState* cur = A.state[round % 3] + (size_t)img * A.T;
-    if (round >= 2 && A.changed[img * (kSyncRounds + 1) + round - 1] == 0) {
-        cur[t] = prev[t];                       // the whole stream is already stable
-        return;
-    }
+    if (round >= 2 && A.settled[img]) return;          // the whole stream is already stable: its final states stay where they are
     if (round >= 2 && t >= 1) {
         // same start state as in the previous round -> same result (only the front of corrections is decoded again)
         const SyncState a = prev[t - 1], b2 = prev2[t - 1];
@@ -669,6 +667,12 @@ __global__ void __launch_bounds__(128) jpeg_sync_kernel(SyncArrays A, const int*
     A.blocks[(size_t)img * A.T + t] = done;
 }
 
+// after round r >= 1: a round that changed nothing settles the stream; settled[img] = r + 1 (0 = not yet)
+__global__ void jpeg_sync_settle_kernel(SyncArrays A, int n, int round) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img < n && A.settled[img] == 0 && A.changed[img * (kSyncRounds + 1) + round] == 0) A.settled[img] = round + 1;
+}
+
 // first_block[t] = number of blocks completed before subsequence t; status bit 2 when the rounds did not settle, bit 1 when the
 // stream holds fewer blocks than the frame needs
 __global__ void __launch_bounds__(1024) jpeg_sync_prefix_kernel(SyncArrays A, int total_blocks, int* __restrict__ status) {
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(1024) jpeg_sync_prefix_kernel(SyncArrays A, in
     }
     if (tid == 1023) {
         if (s_part[1023] < total_blocks) atomicOr(status + img, 2);
-        if (A.changed[img * (kSyncRounds + 1) + kSyncRounds]) atomicOr(status + img, 4);
+        if (A.settled[img] == 0) atomicOr(status + img, 4);
     }
 }
 
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(128) jpeg_sync_write_kernel(SyncArrays A, cons
     const long long len_bits = 8 * A.clean_len[img];
     const long long start = (long long)t * kSubseqBytes * 8, limit = start + (long long)kSubseqBytes * 8;
     if (start >= len_bits) return;
-    const SyncState* fin = A.state[kSyncRounds % 3] + (size_t)img * A.T;
+    const SyncState* fin = A.state[(A.settled[img] - 1) % 3] + (size_t)img * A.T;
     SyncState st;
     if (t == 0) {
         st.pos = 0;
@@ -732,37 +736,75 @@ __global__ void __launch_bounds__(128) jpeg_sync_write_kernel(SyncArrays A, cons
     if (!ok) atomicOr(status + img, 2);
 }
 
-// DC differences -> DC values: inclusive prefix sum over the blocks of one component in scan order (one CTA per image and
-// component; every thread owns a contiguous run of blocks)
-__global__ void __launch_bounds__(1024) jpeg_dc_prefix_kernel(int16_t* __restrict__ coef, JpegGeom g) {
-    __shared__ int s_part[1024];
-    const int img = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
-    int16_t* base = coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c];
+// DC differences -> DC values: inclusive prefix sum over the blocks of one component in scan order, in segments of
+// kDcSeg blocks: (1) segment sums, (2) exclusive scan of the segment sums (one warp-sized loop per image and component),
+// (3) prefix inside each segment.  A thread owns 8 consecutive blocks, whose loads are issued together.
+constexpr int kDcPerThread = 8, kDcThreads = 256, kDcSeg = kDcPerThread * kDcThreads;
+
+__device__ __forceinline__ int16_t* dc_block_ptr(int16_t* base, const JpegGeom& g, int c, int j) {
     const int per_mcu = g.hs[c] * g.vs[c];
-    const int count = g.mcux * g.mcuy * per_mcu;
-    auto dc_ptr = [&](int j) -> int16_t* {
-        const int m = j / per_mcu, r = j - m * per_mcu;
-        const int by = r / g.hs[c], bx = r - by * g.hs[c];
-        const int my = m / g.mcux, mx = m - my * g.mcux;
-        return base + ((size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx)) * 64;
-    };
-    const int per = (count + 1023) / 1024;
-    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    const int m = j / per_mcu, r = j - m * per_mcu;
+    const int by = r / g.hs[c], bx = r - by * g.hs[c];
+    const int my = m / g.mcux, mx = m - my * g.mcux;
+    return base + ((size_t)(my * g.vs[c] + by) * g.blocks_w[c] + (mx * g.hs[c] + bx)) * 64;
+}
+
+// PHASE 0: seg_sum[img][c][seg] = sum of the segment's differences.  PHASE 1: the differences become values, starting from
+// seg_sum (then the exclusive prefix).  grid = (segments, n, ncomp)
+template <int PHASE>
+__global__ void __launch_bounds__(kDcThreads) jpeg_dc_segment_kernel(int16_t* __restrict__ coef, JpegGeom g, int segs, int* __restrict__ seg_sum) {
+    __shared__ int s_part[kDcThreads];
+    const int seg = blockIdx.x, img = blockIdx.y, c = blockIdx.z, tid = threadIdx.x;
+    int16_t* base = coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c];
+    const int count = g.mcux * g.mcuy * g.hs[c] * g.vs[c];
+    const int j0 = seg * kDcSeg + tid * kDcPerThread;
+    int16_t* ptr[kDcPerThread];
+    int v[kDcPerThread];
+#pragma unroll
+    for (int i = 0; i < kDcPerThread; ++i) {
+        ptr[i] = j0 + i < count ? dc_block_ptr(base, g, c, j0 + i) : nullptr;
+        v[i] = ptr[i] ? *ptr[i] : 0;
+    }
     int sum = 0;
-    for (int j = lo; j < hi; ++j) sum += *dc_ptr(j);
+#pragma unroll
+    for (int i = 0; i < kDcPerThread; ++i) sum += v[i];
     s_part[tid] = sum;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = tid >= o ? s_part[tid - o] : 0;
+    for (int o = 1; o < kDcThreads; o <<= 1) {
+        const int x = tid >= o ? s_part[tid - o] : 0;
         __syncthreads();
-        s_part[tid] += v;
+        s_part[tid] += x;
         __syncthreads();
     }
-    int run = s_part[tid] - sum;
-    for (int j = lo; j < hi; ++j) {
-        int16_t* p = dc_ptr(j);
-        run += *p;
-        *p = (int16_t)run;
+    int* ss = seg_sum + ((size_t)img * 3 + c) * segs;
+    if (PHASE == 0) {
+        if (tid == kDcThreads - 1) ss[seg] = s_part[tid];
+        return;
+    }
+    int run = ss[seg] + s_part[tid] - sum;
+#pragma unroll
+    for (int i = 0; i < kDcPerThread; ++i) {
+        run += v[i];
+        if (ptr[i]) *ptr[i] = (int16_t)run;
+    }
+}
+
+// exclusive scan of the segment sums of one image and component (a few hundred entries): one warp
+__global__ void jpeg_dc_scan_kernel(int* __restrict__ seg_sum, int segs) {
+    int* ss = seg_sum + (size_t)blockIdx.x * segs;
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < segs; base += 32) {
+        const int i = base + lane;
+        const int v = i < segs ? ss[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (i < segs) ss[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 #endif  // FB_JPEG_HOST_TEST
@@ -1041,7 +1083,8 @@ size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, in
     if (restart_interval <= 0 && total_mcus > kSerialMcus) {
         const long long T = selfsync_subsequences(max_scan_bytes);
         total += al(selfsync_clean_stride(max_scan_bytes) * n) + al(8ll * n) + 3 * al((long long)sizeof(SyncState) * T * n) +
-                 2 * al(4 * T * n) + al(4ll * (kSyncRounds + 1) * n);
+                 2 * al(4 * T * n) + al(4ll * (kSyncRounds + 1) * n) + al(4ll * ((n + 63) & ~63)) +
+                 al(4ll * 3 * n * ((total_mcus * hmax * vmax + 2047) / 2048 + 1));
     }
     return (size_t)total;
 }
@@ -1122,6 +1165,8 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         A.first_block = reinterpret_cast<int*>(w);
         w += al(4ll * A.T * n);
         A.changed = reinterpret_cast<int*>(w);
+        w += al(4ll * (kSyncRounds + 1) * n);
+        A.settled = reinterpret_cast<int*>(w);
         A.clean = clean;
         A.clean_len = clean_len;
         const int total_blocks = (int)(blocks);
@@ -1129,15 +1174,25 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         FB_CUDA_OK(cudaMemsetAsync(coef, 0, (size_t)blocks * 128 * n, stream));
         FB_CUDA_OK(cudaMemsetAsync(clean, 0, (size_t)A.clean_stride * n, stream));
         FB_CUDA_OK(cudaMemsetAsync(A.changed, 0, sizeof(int) * (kSyncRounds + 1) * n, stream));
+        FB_CUDA_OK(cudaMemsetAsync(A.settled, 0, sizeof(int) * n, stream));
         dim3 cgrid(chunks, n);
         jpeg_unstuff_kernel<false><<<cgrid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, counts, clean, A.clean_stride);
         jpeg_unstuff_prefix_kernel<<<n, 256, 0, stream>>>(counts, chunks, d_scan_len, clean_len);
         jpeg_unstuff_kernel<true><<<cgrid, kScanThreads, 0, stream>>>(d_bytes, d_scan_off, d_scan_len, chunks, counts, clean, A.clean_stride);
         dim3 sgrid((A.T + 127) / 128, n);
-        for (int round = 0; round <= kSyncRounds; ++round) jpeg_sync_kernel<<<sgrid, 128, 0, stream>>>(A, d_table_slot, tables, g, round);
+        for (int round = 0; round <= kSyncRounds; ++round) {
+            jpeg_sync_kernel<<<sgrid, 128, 0, stream>>>(A, d_table_slot, tables, g, round);
+            if (round >= 1) jpeg_sync_settle_kernel<<<(n + 127) / 128, 128, 0, stream>>>(A, n, round);
+        }
         jpeg_sync_prefix_kernel<<<n, 1024, 0, stream>>>(A, total_blocks, d_status);
         jpeg_sync_write_kernel<<<sgrid, 128, 0, stream>>>(A, d_table_slot, tables, g, total_blocks, coef, d_status);
-        jpeg_dc_prefix_kernel<<<dim3(n, ncomp), 1024, 0, stream>>>(coef, g);
+        {
+            const int segs = (int)((g.mcux * (long long)g.mcuy * g.hs[0] * g.vs[0] + kDcSeg - 1) / kDcSeg);
+            int* seg_sum = reinterpret_cast<int*>(A.settled + ((n + 63) & ~63));
+            jpeg_dc_segment_kernel<0><<<dim3(segs, n, ncomp), kDcThreads, 0, stream>>>(coef, g, segs, seg_sum);
+            jpeg_dc_scan_kernel<<<n * 3, 32, 0, stream>>>(seg_sum, segs);
+            jpeg_dc_segment_kernel<1><<<dim3(segs, n, ncomp), kDcThreads, 0, stream>>>(coef, g, segs, seg_sum);
+        }
     } else {
         if (g.n_intervals > 1) {
             dim3 grid(chunks, n);
