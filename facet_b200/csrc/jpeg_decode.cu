@@ -425,11 +425,20 @@ struct SyncState {
 };
 
 struct CleanReader {
-    const uint8_t* u;    // clean stream; at least 16 zero bytes follow its end
+    const uint8_t* u;    // clean stream (256-byte aligned); at least 16 zero bytes follow its end
     long long next;      // next byte to load
     uint64_t acc;
     int n;
+    uint32_t w0, w1, w2; // device: the aligned words at and after `next`, requested ahead of their use
 };
+FB_HD void cr_prefetch(CleanReader& r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(r.u + (r.next & ~3ll));
+    r.w0 = w[0];
+    r.w1 = w[1];
+    r.w2 = w[2];
+#endif
+}
 FB_HD void cr_seek(CleanReader& r, long long pos_bits) {
     r.next = pos_bits >> 3;
     r.acc = 0;
@@ -439,12 +448,25 @@ FB_HD void cr_seek(CleanReader& r, long long pos_bits) {
         r.acc = r.u[r.next++] & (0xFFu >> skip);
         r.n = 8 - skip;
     }
+    r.w0 = r.w1 = r.w2 = 0;
+    cr_prefetch(r);
 }
+// no stuffing in a clean stream: whenever 32 bits fit, the next four bytes enter as one word
 FB_HD void cr_refill(CleanReader& r) {
-    while (r.n <= 48) {
-        r.acc = (r.acc << 8) | r.u[r.next++];
-        r.n += 8;
-    }
+    if (r.n > 32) return;
+#ifdef __CUDA_ARCH__
+    const uint32_t le = __funnelshift_r(r.w0, r.w1, (uint32_t)(r.next & 3) * 8);
+    const uint32_t w = __byte_perm(le, 0u, 0x0123);
+    r.next += 4;
+    r.w0 = r.w1;
+    r.w1 = r.w2;
+    r.w2 = reinterpret_cast<const uint32_t*>(r.u + (r.next & ~3ll))[2];
+#else
+    const uint32_t w = ((uint32_t)r.u[r.next] << 24) | ((uint32_t)r.u[r.next + 1] << 16) | ((uint32_t)r.u[r.next + 2] << 8) | (uint32_t)r.u[r.next + 3];
+    r.next += 4;
+#endif
+    r.acc = (r.acc << 32) | w;
+    r.n += 32;
 }
 FB_HD long long cr_pos(const CleanReader& r) { return 8 * r.next - r.n; }
 
@@ -535,37 +557,46 @@ FB_HD bool span_decode(const uint8_t* u, long long len_bits, SyncState st, long 
 }
 
 #ifndef FB_JPEG_HOST_TEST
-// stuffed zeros (0xFF 0x00) of one 16 KB chunk: WRITE = false counts them, WRITE = true copies the other bytes to their
-// position in the clean stream (counts then holds the exclusive prefix of the per-chunk counts)
+// stuffed zeros (0xFF 0x00) of one 16 KB chunk.  A warp walks its 2 KB in 32-byte steps (coalesced byte loads); ballots keep
+// the bytes in order.  WRITE = false counts the stuffed zeros; WRITE = true copies every other byte to its position in the
+// clean stream (counts then holds the exclusive prefix of the per-chunk counts).
 template <bool WRITE>
 __global__ void __launch_bounds__(kScanThreads) jpeg_unstuff_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
                                                                     const long long* __restrict__ scan_len, int chunks, int* __restrict__ counts,
                                                                     uint8_t* __restrict__ clean, long long clean_stride) {
-    __shared__ int s_cnt[kScanThreads];
-    constexpr int kPer = kScanChunk / kScanThreads;       // 64 bytes per thread
-    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_warp[kScanThreads / 32];
+    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t* s = bytes + scan_off[img];
     const long long len = scan_len[img];
-    const long long lo = (long long)chunk * kScanChunk + (long long)tid * kPer;
-    const long long hi = min(lo + kPer, len);
-    int mine = 0;
-    for (long long p = lo; p < hi; ++p) mine += (s[p] == 0x00 && p > 0 && s[p - 1] == 0xFF) ? 1 : 0;
-    s_cnt[tid] = mine;
-    __syncthreads();
-    for (int o = 1; o < kScanThreads; o <<= 1) {
-        const int v = tid >= o ? s_cnt[tid - o] : 0;
-        __syncthreads();
-        s_cnt[tid] += v;
-        __syncthreads();
+    const long long w0 = (long long)chunk * kScanChunk + (long long)warp * kScanWarpBytes;
+    int cnt = 0;
+    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
+        const long long p = w0 + it * 32 + lane;
+        const bool stuffed = p < len && p > 0 && s[p] == 0x00 && s[p - 1] == 0xFF;
+        cnt += __popc(__ballot_sync(0xffffffffu, stuffed));
     }
+    if (lane == 0) s_warp[warp] = cnt;
+    __syncthreads();
     if (!WRITE) {
-        if (tid == kScanThreads - 1) counts[(size_t)img * chunks + chunk] = s_cnt[tid];
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < kScanThreads / 32; ++w) tot += s_warp[w];
+            counts[(size_t)img * chunks + chunk] = tot;
+        }
         return;
     }
-    long long dst = lo - (counts[(size_t)img * chunks + chunk] + s_cnt[tid] - mine);
+    long long removed = counts[(size_t)img * chunks + chunk];
+    for (int w = 0; w < warp; ++w) removed += s_warp[w];
     uint8_t* out = clean + (size_t)img * clean_stride;
-    for (long long p = lo; p < hi; ++p)
-        if (!(s[p] == 0x00 && p > 0 && s[p - 1] == 0xFF)) out[dst++] = s[p];
+    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
+        const long long p = w0 + it * 32 + lane;
+        const bool in = p < len;
+        const uint8_t v = in ? s[p] : 0;
+        const bool stuffed = in && p > 0 && v == 0x00 && s[p - 1] == 0xFF;
+        const uint32_t m = __ballot_sync(0xffffffffu, stuffed);
+        if (in && !stuffed) out[p - removed - __popc(m & ((1u << lane) - 1u))] = v;
+        removed += __popc(m);
+    }
 }
 
 // exclusive prefix of the per-chunk counts of one image; clean_len[img] = scan_len - number of stuffed zeros
