@@ -362,11 +362,11 @@ int launch_attention_tc(const void* d_qkv, int batch, void* d_out, int f16, cuda
     CUtensorMap tm;
     int rc = make_tmap_bf16_2d(&tm, d_qkv, (uint64_t)batch * kTok, 3 * kW, 3 * kW, 128, 64);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
         FB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttn));
-        attr_set = true;
+        attr_set.set();
     }
     const int n_pairs = batch * 16;
     int grid = (n_pairs + 1) / 2;

@@ -4,7 +4,22 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace fb {
+
+// A flag per device ordinal for "kernel attributes have been set" (cudaFuncSetAttribute is per device; one process may
+// drive several GPUs).  get() / set() are lock-free; setting attributes twice from two racing threads is harmless.
+struct PerDeviceFlag {
+    std::atomic<unsigned long long> mask{0ull};
+    static int device() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) d = 0;
+        return d;
+    }
+    bool get() const { return (mask.load(std::memory_order_acquire) >> device()) & 1ull; }
+    void set() { mask.fetch_or(1ull << device(), std::memory_order_release); }
+};
 
 // Thread-local last-error text behind fb_last_error().
 void set_error(const char* fmt, ...);

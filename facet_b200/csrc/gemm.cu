@@ -525,11 +525,11 @@ static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, l
     const int grid = tiles < sm_count() ? tiles : sm_count();
 #define FB_LAUNCH_MODE(MODE_)                                                                                          \
     case MODE_: {                                                                                                      \
-        static bool attr_set = false;                                                                                  \
-        if (!attr_set) {                                                                                               \
+        static PerDeviceFlag attr_set;                                                                                  \
+        if (!attr_set.get()) {                                                                                               \
             FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
             FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            attr_set = true;                                                                                           \
+            attr_set.set();                                                                                           \
         }                                                                                                              \
         if (p.f16) gemm_bf16_kernel<MODE_, true, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);            \
         else gemm_bf16_kernel<MODE_, false, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                 \

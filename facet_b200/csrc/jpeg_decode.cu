@@ -1234,10 +1234,10 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
             FB_CUDA_OK(cudaMemsetAsync(starts, 0, sizeof(uint32_t) * n, stream));
         }
         dim3 grid((g.n_intervals + kHuffThreads - 1) / kHuffThreads, n);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceFlag attr_set;
+        if (!attr_set.get()) {
             FB_CUDA_OK(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem));
-            attr_set = true;
+            attr_set.set();
         }
         jpeg_huffman_kernel<<<grid, kHuffThreads, kHuffSmem, stream>>>(d_bytes, d_scan_off, d_scan_len, d_table_slot, tables, starts, g, coef, d_status);
     }

@@ -198,10 +198,10 @@ int launch_phash(const uint8_t* d_images, int n, int H, int W, long long image_s
     if (tc == 1) {
         const size_t smem = (size_t)kRows * W;
         FB_REQUIRE(smem <= 200 * 1024, "fb_phash: image width %d exceeds shared memory staging", W);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceFlag attr_set;
+        if (!attr_set.get()) {
             FB_CUDA_OK(cudaFuncSetAttribute(luma_hresample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            attr_set.set();
         }
         dim3 gh((H + kRows - 1) / kRows, n);
         luma_hresample_kernel<<<gh, 256, smem, stream>>>(d_images, image_stride, H, W, rgb_order, d_hbounds, d_hcoef, hk, d_tmp);

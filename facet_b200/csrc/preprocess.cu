@@ -205,10 +205,10 @@ int launch_clip_preprocess(const uint8_t* d_images, int n, int H, int W, long lo
                "fb_clip_preprocess: horizontal span must start and end on multiples of 16 pixels");
     const size_t smem = (size_t)kRowsPerBlock * h_span_px * 3;
     FB_REQUIRE(smem <= 200 * 1024, "fb_clip_preprocess: row span %d px exceeds shared memory staging", h_span_px);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         FB_CUDA_OK(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set.set();
     }
     // horizontal pass: exact int8 tensor-core product when the layout allows it, CUDA cores otherwise
     int tc = launch_resample_h_tc(d_images, n, H, W, image_stride, out_size, d_tc_coef, tc_kw, tc_limbs, d_tc_kb0, row0, rows,

@@ -253,11 +253,11 @@ int launch_resample_h_tc(const uint8_t* d_images, int n, int H, int W, long long
     ResampleTcArgs p;
     p.n_img = n; p.H = H; p.row0 = row0; p.rows = rows; p.out = out_size; p.kblocks = kw / RKB; p.limbs = limbs;
     p.kb0 = d_kb0; p.tmp = d_tmp;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.get()) {
         FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, RCfg<3>::kSmem));
         FB_CUDA_OK(cudaFuncSetAttribute(resample_h_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RCfg<1>::kSmem));
-        attr_set = true;
+        attr_set.set();
     }
     const int tiles = n * ((rows + RM - 1) / RM) * (out_size / kNB);
     const int grid = tiles < sm_count() ? tiles : sm_count();

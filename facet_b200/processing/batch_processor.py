@@ -421,6 +421,48 @@ class BatchProcessor:
             self._stream["copy"].wait_event(fence)
         return chunks[key]
 
+    # -- paths in, database rows out -------------------------------------------------------------------------
+    def process_files(self, photo_paths, db_path=None, show_metrics=True, batch_save_size=50, chunk=16, vit_batch=64,
+                      thumbnails=True):
+        """The reference's `process_files(photo_paths)` (batch_processor.py:362-455): load every path, score it, save the rows
+        every `batch_save_size` results.  Loader threads (`num_workers`) read the FILE BYTES of JPEG files (decoded on the device;
+        RAW / PNG / other formats go through the host loader, utils/image_loading.load_any); the rows go to `db_path` (a database
+        with the reference's schema) through `db_sink.PhotoSink`; with db_path=None the result dicts are returned instead.
+        Errors are printed and skipped like the reference does (`Error on <path>: <message>`)."""
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+        from ..utils.image_loading import load_item
+        from .db_sink import PhotoSink
+        paths = list(photo_paths)
+        if not paths:
+            return [] if db_path is None else 0
+        start = time.time()
+        self.metrics["start_time"] = start
+        with ThreadPoolExecutor(max_workers=max(1, self.num_workers)) as pool:
+            items = list(pool.map(load_item, paths))              # file reads overlap each other; bytes stay undecoded
+        results = self.process_items_streamed(items, chunk=chunk, vit_batch=vit_batch)
+        for r in results:
+            if "error" in r:
+                print(f"Error on {r.get('path', 'unknown')}: {r['error']}")
+        self.metrics["elapsed_time"] = time.time() - start
+        if db_path is None:
+            return results
+        with PhotoSink(db_path, batch_save_size=batch_save_size) as sink:
+            for item, res in zip(items, results):
+                if "error" in res:
+                    continue
+                image = None
+                if thumbnails:                                    # scorer.py:1681-1686: 640-px thumbnail of the upright frame
+                    image = item.get("img_cv")
+                    if image is None and item.get("jpeg") is not None:
+                        from .. import ops
+                        image = ops.jpeg_decode([item["jpeg"]], bgr=True)[0]
+                sink.add(res, image)
+        if show_metrics:
+            dt = max(self.metrics["elapsed_time"], 1e-9)
+            print(f"[{sink.saved}/{len(paths)}] {len(paths) / dt:.1f} img/s")
+        return sink.saved
+
     def process_items(self, items):
         """Stream items through `_process_batch` in chunks of batch_size; yields results in order."""
         chunk = []

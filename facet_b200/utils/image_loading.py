@@ -64,3 +64,36 @@ def read_jpeg_item(path, pinned: bool = False):
         return {"path": str(path), "jpeg": arr, "_pinned": buf}
     with open(path, "rb") as f:
         return {"path": str(path), "jpeg": np.frombuffer(f.read(), np.uint8)}
+
+
+JPEG_EXTENSIONS = (".jpg", ".jpeg", ".jpe", ".jfif")
+
+
+def load_any(path):
+    """Host loader for files that are not baseline JPEG: what `load_image_from_path` (utils/image_loading.py:44-112) does
+    for them with Pillow — open, `exif_transpose`, RGB, BGR copy.  (RAW files need rawpy, which is outside this path.)
+    Returns an [H,W,3] uint8 BGR array or None."""
+    import numpy as np
+    from PIL import Image, ImageOps
+    try:
+        with Image.open(path) as img:
+            img = ImageOps.exif_transpose(img).convert("RGB")
+            return np.ascontiguousarray(np.asarray(img)[:, :, ::-1])
+    except Exception:
+        return None
+
+
+def load_item(path):
+    """One loader item for a path: JPEG files as undecoded bytes (`read_jpeg_item`), everything else decoded on the host;
+    unreadable files become error items like `_load_image` produces (batch_processor.py:92,110)."""
+    import os
+    p = str(path)
+    try:
+        if os.path.splitext(p)[1].lower() in JPEG_EXTENSIONS:
+            return read_jpeg_item(p)
+        img = load_any(p)
+        if img is None:
+            return {"path": p, "error": "Failed to load image"}
+        return {"path": p, "img_cv": img}
+    except Exception as exc:
+        return {"path": p, "error": str(exc)}

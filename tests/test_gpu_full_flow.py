@@ -69,3 +69,45 @@ def test_single_pass_flow_into_sqlite(tmp_path):
         assert len(gids) == 1 and None not in gids, "identical frames must share a duplicate group"
         assert sum(by_path[m][9] for m in members) == 1, "exactly one duplicate lead per group"
         assert sum(by_path[m][10] for m in members) == 1, "identical frames seconds apart are one burst with one lead"
+
+
+def test_process_files_from_paths_to_rows(tmp_path):
+    """`BatchProcessor.process_files(paths, db_path)`: JPEG files (with and without restart markers, one progressive, one
+    rotated by EXIF), a PNG, an unreadable file -> rows in a database with the reference's schema."""
+    from PIL import Image
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.processing.batch_processor import BatchProcessor
+    from facet_b200.processing.scorer import Facet
+    sc = Facet(random_state_dict(0))
+    paths = []
+    for i, kw in enumerate([{"quality": 90}, {"quality": 85, "restart_marker_blocks": 4}, {"quality": 80, "progressive": True}, {"quality": 92}]):
+        rgb = synth_image_bgr(100 + i, 300, 420)[:, :, ::-1].copy()
+        ex = Image.Exif()
+        ex[0x0112] = 6 if i == 3 else 1
+        p = tmp_path / f"photo_{i}.jpg"
+        Image.fromarray(rgb).save(p, "JPEG", exif=ex, **kw)
+        paths.append(str(p))
+    p = tmp_path / "drawing.png"
+    Image.fromarray(synth_image_bgr(110, 200, 200)[:, :, ::-1].copy()).save(p)
+    paths.append(str(p))
+    bad = tmp_path / "broken.jpg"
+    bad.write_bytes(b"not an image")
+    paths.append(str(bad))
+    db = str(tmp_path / "photos.db")
+    with open(os.path.join(GOLDEN_DIR, "db_sink_golden.json")) as f:
+        schema = json.load(f)["schema"]
+    with sqlite3.connect(db) as conn:
+        for sql in schema:
+            conn.execute(sql)
+    bp = BatchProcessor(sc, batch_size=8, num_workers=3)
+    assert bp.process_files(paths, db_path=db, show_metrics=False, batch_save_size=2, chunk=2, vit_batch=4) == 5
+    assert bp.metrics.get("host_decoded") == 1              # the progressive file
+    with sqlite3.connect(db) as conn:
+        rows = dict((os.path.basename(r[0]), r[1:]) for r in conn.execute(
+            "SELECT path, image_width, image_height, length(thumbnail), length(clip_embedding), phash FROM photos"))
+    assert set(rows) == {"photo_0.jpg", "photo_1.jpg", "photo_2.jpg", "photo_3.jpg", "drawing.png"}
+    assert rows["photo_0.jpg"][:2] == (420, 300) and rows["photo_3.jpg"][:2] == (300, 420)      # EXIF 6: rotated upright
+    assert all(r[2] > 500 and r[3] == 3072 and len(r[4]) == 16 for r in rows.values())
+    # without a database the dicts come back, in input order, the unreadable file as an error item
+    res = bp.process_files(paths, show_metrics=False)
+    assert [os.path.basename(r["path"]) for r in res] == [os.path.basename(p) for p in paths] and "error" in res[-1]
