@@ -332,10 +332,10 @@ class BatchProcessor:
                     if img is None:
                         # not a stream the device decoder takes: the reference's own loader (Pillow) reads it
                         img = decode_on_host(item["jpeg"])
-                        self.metrics["host_decoded"] = self.metrics.get("host_decoded", 0) + 1
                         if img is None:
                             results[pos] = {"path": item.get("path"), "error": f"Failed to load image ({exc})"}
                             continue
+                        self.metrics["host_decoded"] = self.metrics.get("host_decoded", 0) + 1
             if info is not None:
                 data = item["jpeg"]
                 nbytes = len(data)
