@@ -456,7 +456,12 @@ class BatchProcessor:
                     image = item.get("img_cv")
                     if image is None and item.get("jpeg") is not None:
                         from .. import ops
-                        image = ops.jpeg_decode([item["jpeg"]], bgr=True)[0]
+                        from ..utils.image_loading import decode_on_host
+                        from ..utils.jpeg import UnsupportedJpeg
+                        try:
+                            image = ops.jpeg_decode([item["jpeg"]], bgr=True)[0]
+                        except UnsupportedJpeg:
+                            image = decode_on_host(item["jpeg"])
                 sink.add(res, image)
         if show_metrics:
             dt = max(self.metrics["elapsed_time"], 1e-9)
