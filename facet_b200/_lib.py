@@ -30,6 +30,9 @@ _SIGNATURES = {
     "fb_tech_derive": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_tech_stats_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fb_gray_hsv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "fb_gray_plane": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "fb_canny_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "fb_canny": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "fb_roi_laplacian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "fb_clip_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
                                      _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int,

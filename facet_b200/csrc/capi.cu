@@ -204,6 +204,24 @@ int fb_gray_hsv(const uint8_t* d_image, int height, int width, int rgb_order, ui
     return rc;
 }
 
+int fb_gray_plane(const uint8_t* d_image, int height, int width, int rgb_order, uint8_t* d_gray, uint32_t* d_hist256,
+                  void* stream) {
+    int rc = launch_gray_plane(d_image, height, width, rgb_order, d_gray, d_hist256, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+size_t fb_canny_workspace_bytes(int height, int width) { return canny_workspace_bytes(height, width); }
+
+int fb_canny(const uint8_t* d_gray, int height, int width, int blur, int low, int high, void* d_workspace,
+             size_t workspace_bytes, uint8_t* d_edges, uint64_t* d_edge_count, void* stream) {
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    int rc = launch_canny(d_gray, height, width, blur, low, high, d_workspace, workspace_bytes, d_edges,
+                          reinterpret_cast<unsigned long long*>(d_edge_count), (cudaStream_t)stream);
+    if (rc == 0) count_launch(blur ? 5 : 4);
+    return rc;
+}
+
 int fb_roi_laplacian(const uint8_t* d_image, int height, int width, int rgb_order, const int32_t* d_boxes, int k,
                      int64_t* d_out, void* stream) {
     int rc = launch_roi_laplacian(d_image, height, width, rgb_order, d_boxes, k, reinterpret_cast<long long*>(d_out),

@@ -18,6 +18,11 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
                       uint8_t* d_luma, cudaStream_t stream);
 int launch_gray_hsv(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t* d_gray, uint8_t* d_hsv,
                     cudaStream_t stream);
+int launch_gray_plane(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t* d_gray, unsigned int* d_hist256,
+                      cudaStream_t stream);
+size_t canny_workspace_bytes(int H, int W);
+int launch_canny(const uint8_t* d_gray, int H, int W, int blur, int low, int high, void* d_ws, size_t ws_bytes,
+                 uint8_t* d_edges, unsigned long long* d_count, cudaStream_t stream);
 int launch_hs_derive(const unsigned int* d_hs_hist, int n, double* d_out, cudaStream_t stream);
 
 int launch_hamming_pairs(const unsigned long long* d_hashes, long long n, int max_distance, int part,

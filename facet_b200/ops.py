@@ -135,6 +135,47 @@ def gray_hsv_planes(image, rgb_order: bool = False):
     return gray.cpu().numpy(), hsv.cpu().numpy()
 
 
+def gray_plane(image, rgb_order: bool = False, want_hist: bool = False):
+    """CUDA uint8 [H,W] gray plane of one frame (cv2.cvtColor BGR2GRAY, composition.py:30,210) and, when
+    want_hist, its 256-bin histogram as a CUDA int32 tensor."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    t = to_device_u8(image)
+    if t.shape[0] != 1:
+        raise ValueError("gray_plane takes a single image")
+    _, h, w, _ = t.shape
+    with torch.cuda.device(t.device):
+        gray = torch.empty((h, w), dtype=torch.uint8, device=t.device)
+        hist = torch.empty(256, dtype=torch.int32, device=t.device) if want_hist else None
+        _lib.check(lib.fb_gray_plane(_ptr(t), h, w, int(bool(rgb_order)), _ptr(gray), _ptr(hist) if want_hist else None,
+                                     _lib.stream_ptr()), "fb_gray_plane")
+    return (gray, hist) if want_hist else gray
+
+
+def canny_edges(gray, low: int, high: int, blur: bool = False, want_count: bool = False):
+    """cv2.Canny(gray, low, high) of a uint8 [H,W] plane (numpy or CUDA tensor), after cv2.GaussianBlur(gray, (5, 5), 0)
+    when `blur` (composition.py:215-218, :36).  Returns the CUDA uint8 [H,W] edge map (0 / 255), bit-exact with OpenCV."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    if isinstance(gray, np.ndarray):
+        if gray.dtype != np.uint8 or gray.ndim != 2:
+            raise TypeError("gray must be a uint8 [H,W] plane")
+        g = torch.from_numpy(np.ascontiguousarray(gray)).cuda()
+    else:
+        if gray.dtype != torch.uint8 or gray.dim() != 2:
+            raise TypeError("gray must be a uint8 [H,W] plane")
+        g = (gray if gray.is_cuda else gray.cuda()).contiguous()
+    h, w = g.shape
+    with torch.cuda.device(g.device):
+        nbytes = int(lib.fb_canny_workspace_bytes(h, w))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+        edges = torch.empty((h, w), dtype=torch.uint8, device=g.device)
+        count = torch.zeros(1, dtype=torch.int64, device=g.device) if want_count else None
+        _lib.check(lib.fb_canny(_ptr(g), h, w, int(bool(blur)), int(low), int(high), _ptr(ws), nbytes, _ptr(edges),
+                                _ptr(count) if want_count else None, _lib.stream_ptr()), "fb_canny")
+    return (edges, count) if want_count else edges
+
+
 def roi_laplacian(image, boxes: Sequence[Sequence[int]], rgb_order: bool = False) -> np.ndarray:
     """[k,3] int64 (pixel count, sum L, sum L^2) for crops x1,y1,x2,y2 of one image."""
     torch = _lib.require_cuda()

@@ -80,6 +80,23 @@ int fb_tech_stats_host(const uint8_t* h_images, int n, int height, int width, in
 int fb_gray_hsv(const uint8_t* d_image, int height, int width, int rgb_order, uint8_t* d_gray,
                 uint8_t* d_hsv, void* stream);
 
+/* Edge maps of the rule-based composition analyzer (analyzers/composition.py; called per image at
+ * processing/batch_processor.py:245 `CompositionAnalyzer.detect_leading_lines(img_cv, cache=cache)` and, through
+ * `get_placement_data(..., img_cv=...)`, `detect_subject_region`).
+ *   fb_gray_plane  gray [H][W] uint8 = cv2.cvtColor(BGR2GRAY) (composition.py:30,210) and, when d_hist256 is not
+ *                  NULL, its 256-bin histogram (np.median(gray), composition.py:33, is a closed form of it)
+ *   fb_canny       blur != 0: cv2.GaussianBlur(gray, (5, 5), 0) first (composition.py:215); then
+ *                  cv2.Canny(src, low, high) (composition.py:218 with 50 / 150; :36 with the median-derived
+ *                  thresholds): aperture 3, L1 gradient.  d_edges [H][W] uint8, 0 or 255, bit-exact with OpenCV;
+ *                  d_edge_count (device uint64, may be NULL) receives the number of edge pixels.
+ *                  d_workspace: fb_canny_workspace_bytes(height, width) bytes, 256-byte aligned.
+ * The sequential geometry that follows (cv2.HoughLinesP, cv2.findContours) stays with the caller. */
+int fb_gray_plane(const uint8_t* d_image, int height, int width, int rgb_order, uint8_t* d_gray, uint32_t* d_hist256,
+                  void* stream);
+size_t fb_canny_workspace_bytes(int height, int width);
+int fb_canny(const uint8_t* d_gray, int height, int width, int blur, int low, int high, void* d_workspace,
+             size_t workspace_bytes, uint8_t* d_edges, uint64_t* d_edge_count, void* stream);
+
 /* Laplacian sums of image crops — analyzers/face.py:272-279 `_get_crop_sharpness`
  * (isolation bonus, processing/batch_processor.py:254-260).  Each crop is filtered with its
  * own reflect-101 border.  d_boxes [k][4] int32 = x1,y1,x2,y2 (exclusive end, clipped by the
