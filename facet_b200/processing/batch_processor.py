@@ -34,8 +34,12 @@ NO_FACES = {"face_count": 0, "face_quality": 0, "eye_sharpness": 0, "is_blink": 
 
 
 class BatchProcessor:
-    def __init__(self, scorer, batch_size=16, num_workers=4, finish=None, mono_threshold=None):
+    def __init__(self, scorer, batch_size=16, num_workers=4, finish=None, mono_threshold=None, leading_lines=False):
+        """leading_lines: run `CompositionAnalyzer.detect_leading_lines` per image like the reference's loop does
+        (batch_processor.py:245; blur + Canny on the device, OpenCV's probabilistic Hough on `num_workers` host threads)
+        for items that do not already carry a `leading_lines_score`."""
         self.scorer = scorer
+        self.leading_lines = bool(leading_lines)
         self.batch_size = int(batch_size)
         self.num_workers = int(num_workers)
         self.finish = finish
@@ -73,6 +77,11 @@ class BatchProcessor:
         for _shape, idxs in groups.items():
             try:
                 frames = np.stack([batch[i]["img_cv"] for i in idxs])
+                if self.leading_lines:
+                    for i in idxs:
+                        if batch[i].get("leading_lines_score") is None:
+                            batch[i] = dict(batch[i], leading_lines_score=CompositionAnalyzer.detect_leading_lines(
+                                batch[i]["img_cv"])["leading_lines_score"])
                 scored = self.scorer.score_images(frames, mono_threshold=self.mono_threshold, tag_threshold=thr, max_tags=max_tags)
                 scored = self._finish_group([batch[i] for i in idxs], scored)
                 for i, res in zip(idxs, scored):
@@ -155,7 +164,7 @@ class BatchProcessor:
                 "raw_eye_sharpness": float(face_res.get("raw_eye_sharpness", 0)),
                 "config_version": getattr(cfg, "version_hash", None),
                 "is_silhouette": is_sil, "is_group_portrait": face_res.get("is_group_portrait", 0),
-                "leading_lines_score": item.get("leading_lines_score", 0),
+                "leading_lines_score": item.get("leading_lines_score") or 0,
                 "face_confidence": face_res.get("max_face_confidence", 0),
                 "composition_explanation": comp.get("vlm_explanation"), "composition_pattern": None,
                 "face_details": face_res.get("face_details", []),
@@ -165,7 +174,7 @@ class BatchProcessor:
         return out
 
     # -- overlapped path ---------------------------------------------------------------------------------------
-    def process_items_streamed(self, items, chunk=16, vit_batch=64, rgb_order=False):
+    def process_items_streamed(self, items, chunk=16, vit_batch=64, rgb_order=False, thumbnails=False):
         """Same results as `process_items` (one dict per item, input order), produced by an overlapped pipeline instead
         of one blocking pass per batch — the role of the reference's loader threads / GPU thread / result queue
         (batch_processor.py:123-167, 362-455):
@@ -180,6 +189,11 @@ class BatchProcessor:
           D2H stream      ONE packed record per image (histogram, sums, hash, embedding, aesthetic, tag similarities;
                           about 5 KB) into pinned host memory per ViT batch
           worker thread   closed-form metric dicts, tag selection, aggregate + category, the result columns
+          side products   with `leading_lines` (constructor) the Canny edge map of every frame (csrc/canny.cu) and with
+                          `thumbnails` the 640-px LANCZOS thumbnail pixels of every frame (csrc/thumbnail.cu) are produced in
+                          the same visit of the frame on the compute stream, leave on the D2H stream, and `num_workers`
+                          host threads run OpenCV's Hough transform / Pillow's JPEG encoder on them; a result then carries
+                          `leading_lines_score` (batch_processor.py:245,334) / `thumbnail` (the JPEG bytes of scorer.py:1681-1686)
 
         `self.metrics` gains h2d_bytes / d2h_bytes of the call."""
         import queue
@@ -201,6 +215,78 @@ class BatchProcessor:
         self.metrics.setdefault("h2d_bytes", 0)
         self.metrics.setdefault("d2h_bytes", 0)
         jobs = queue.Queue()
+        side = {}                 # pos -> {"lines": future, "thumb": (future, k)}
+        want_lines = self.leading_lines
+        pool = None
+        if want_lines or thumbnails:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=max(1, self.num_workers))
+        pinned = {}               # (kind, shape) -> queue of pinned host buffers (back-pressure on the side products)
+
+        def pinned_get(kind, shape, count):
+            q = pinned.get((kind, shape))
+            if q is None:
+                q = pinned[(kind, shape)] = queue.Queue()
+                for _ in range(count):
+                    q.put(torch.empty(shape, dtype=torch.uint8, pin_memory=True))
+            return q, q.get()
+
+        def d2h_async(src, kind, count):
+            """src (device tensor, produced on the compute stream) -> a pinned buffer on the D2H stream."""
+            q, host = pinned_get(kind, tuple(src.shape), count)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(ready)
+                host.copy_(src, non_blocking=True)
+                done.record(d2h_s)
+            src.record_stream(d2h_s)
+            self.metrics["d2h_bytes"] += src.numel()
+            return q, host, done
+
+        def lines_job(q, host, done, h, w):
+            try:
+                done.synchronize()
+                return CompositionAnalyzer.score_lines(CompositionAnalyzer.lines_from_edges(host.numpy(), h, w), h, w)
+            finally:
+                q.put(host)
+
+        def thumbs_job(q, host, done, m):
+            from ..utils.image_transforms import _encode_jpeg
+            try:
+                done.synchronize()
+                px = host[:m].numpy().copy()
+            finally:
+                q.put(host)
+            return [_encode_jpeg(t, 80) for t in px]
+
+        def side_products(frames, metas):
+            if want_lines:
+                for k, (pos, item, h, w) in enumerate(metas):
+                    if item.get("leading_lines_score") is None:
+                        edges = ops.canny_edges(ops.gray_plane(frames[k], rgb_order=rgb_order), 50, 150, blur=True)
+                        side.setdefault(pos, {})["lines"] = pool.submit(lines_job, *d2h_async(edges, "edges", 2 * self.num_workers + 2), h, w)
+            if thumbnails:
+                px = ops.thumbnails(frames, rgb_order=rgb_order, to_rgb=True)
+                if px.shape[0] < chunk:          # one pinned shape per frame shape: pad short chunks
+                    px = torch.cat([px, px.new_zeros((chunk - px.shape[0],) + tuple(px.shape[1:]))])
+                fut = pool.submit(thumbs_job, *d2h_async(px, "thumbs", 4), len(metas))
+                for k, (pos, _item, _h, _w) in enumerate(metas):
+                    side.setdefault(pos, {})["thumb"] = (fut, k)
+
+        def with_side(pos, item):
+            """The item as `_finish_group` should see it, and the thumbnail bytes of its frame (or None)."""
+            extra = side.pop(pos, None)
+            if not extra:
+                return item, None
+            if "lines" in extra:
+                item = dict(item, leading_lines_score=extra["lines"].result()["leading_lines_score"])
+            thumb = None
+            if "thumb" in extra:
+                fut, k = extra["thumb"]
+                thumb = fut.result()[k]
+            return item, thumb
 
         def post(job):
             done, pack, metas = job
@@ -230,8 +316,11 @@ class BatchProcessor:
                                                       sims[sel] if sims is not None else None,
                                                       ["%016x" % int(v) for v in hashes[sel]], mono_threshold=self.mono_threshold,
                                                       tag_threshold=thr, max_tags=max_tags)
-                    scored = self._finish_group([metas[k][1] for k in ks], scored)
-                    for k, res in zip(ks, scored):
+                    sided = [with_side(metas[k][0], metas[k][1]) for k in ks]
+                    scored = self._finish_group([it for it, _ in sided], scored)
+                    for k, res, (_it, thumb) in zip(ks, scored, sided):
+                        if thumb is not None:
+                            res["thumbnail"] = thumb
                         results[metas[k][0]] = self.finish(metas[k][1], res) if self.finish is not None else res
                 except Exception as exc:
                     for k in ks:
@@ -303,6 +392,8 @@ class BatchProcessor:
                     status = torch.zeros((len(metas),), dtype=torch.int32, device=dev)
                 px = scorer.pixel_passes_device(frames, rgb_order=rgb_order)
                 px["status"] = status
+                if pool is not None:
+                    side_products(frames, metas)
                 bufs["free"][slot].record(compute)
                 bufs["used"][slot] = True
                 acc["px"].append(px)
@@ -387,6 +478,8 @@ class BatchProcessor:
         flush_vit()
         jobs.put(None)
         th.join()
+        if pool is not None:
+            pool.shutdown(wait=True)
         self.metrics["batches"] += 1
         out = [results[i] for i in range(n_items)]
         self.metrics["images_processed"] += sum(1 for r in out if "error" not in r)
@@ -440,7 +533,7 @@ class BatchProcessor:
         self.metrics["start_time"] = start
         with ThreadPoolExecutor(max_workers=max(1, self.num_workers)) as pool:
             items = list(pool.map(load_item, paths))              # file reads overlap each other; bytes stay undecoded
-        results = self.process_items_streamed(items, chunk=chunk, vit_batch=vit_batch)
+        results = self.process_items_streamed(items, chunk=chunk, vit_batch=vit_batch, thumbnails=bool(thumbnails and db_path is not None))
         for r in results:
             if "error" in r:
                 print(f"Error on {r.get('path', 'unknown')}: {r['error']}")
@@ -451,17 +544,8 @@ class BatchProcessor:
             for item, res in zip(items, results):
                 if "error" in res:
                     continue
+                # scorer.py:1681-1686: the 640-px thumbnail was made in the same visit of the frame (res['thumbnail'])
                 image = None
-                if thumbnails:                                    # scorer.py:1681-1686: 640-px thumbnail of the upright frame
-                    image = item.get("img_cv")
-                    if image is None and item.get("jpeg") is not None:
-                        from .. import ops
-                        from ..utils.image_loading import decode_on_host
-                        from ..utils.jpeg import UnsupportedJpeg
-                        try:
-                            image = ops.jpeg_decode([item["jpeg"]], bgr=True)[0]
-                        except UnsupportedJpeg:
-                            image = decode_on_host(item["jpeg"])
                 sink.add(res, image)
         if show_metrics:
             dt = max(self.metrics["elapsed_time"], 1e-9)

@@ -88,7 +88,8 @@ def save_photos_batch(db_path, results_with_images, conn=None):
         return 0
     # Phase 1: thumbnails, no DB lock held
     for res, img in pairs:
-        res["thumbnail"] = _thumbnail_bytes(img)
+        if img is not None or "thumbnail" not in res:       # a result of the streamed pass may already carry its JPEG
+            res["thumbnail"] = _thumbnail_bytes(img)
     # Phase 2: rows
     photo_rows = [tuple(res.get(c) for c in PHOTO_COLUMNS) for res, _ in pairs]
     faces = [row for res, _ in pairs for row in face_records(res)]

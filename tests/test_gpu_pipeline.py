@@ -227,3 +227,44 @@ def test_streamed_path_takes_jpeg_file_bytes(scorer):
     from facet_b200.utils.image_loading import decode_on_host
     ref = bp.process_items_streamed([{"path": "/x/prog_only.jpg", "img_cv": decode_on_host(buf.getvalue())}])[0]
     assert "error" not in got[-1] and all(got[-1][k] == ref[k] for k in ref)
+
+
+def test_streamed_side_products_leading_lines_and_thumbnails(scorer):
+    """With `leading_lines` every result carries the score OpenCV's own calls give on the same frame
+    (composition.py:190-261 restated with cv2 here), with `thumbnails` the JPEG bytes Pillow's
+    `thumbnail((640, 640), LANCZOS)` + `save(quality=80)` give (scorer.py:1681-1686); the blocking path agrees."""
+    import io
+    import cv2
+    from PIL import Image
+    from facet_b200.analyzers.composition import CompositionAnalyzer
+    from facet_b200.processing.batch_processor import BatchProcessor
+    sc, tags, names = scorer
+    shapes = [(700, 1050)] * 5 + [(1024, 683)] * 2 + [(97, 131)]
+    items = [{"path": f"/x/c{i}.jpg", "img_cv": synth_image_bgr(i, h, w)} for i, (h, w) in enumerate(shapes)]
+    items[3] = dict(items[3], leading_lines_score=4.25)               # supplied by the caller: kept as is
+    items.insert(2, {"path": "/x/broken.jpg", "error": "Failed to load image"})
+    bp = BatchProcessor(sc, batch_size=16, num_workers=3, leading_lines=True)
+    got = bp.process_items_streamed(items, chunk=3, vit_batch=4, thumbnails=True)
+    blocking = list(bp.process_items(items))
+    plain = BatchProcessor(sc, batch_size=16).process_items_streamed(items, chunk=3, vit_batch=4)
+    for it, g, b, p in zip(items, got, blocking, plain):
+        if "error" in it:
+            assert "error" in g
+            continue
+        img = it["img_cv"]
+        h, w = img.shape[:2]
+        if "leading_lines_score" in it:
+            want = it["leading_lines_score"]
+        else:
+            edges = cv2.Canny(cv2.GaussianBlur(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), (5, 5), 0), 50, 150)
+            want = CompositionAnalyzer.score_lines(CompositionAnalyzer.lines_from_edges(edges, h, w), h, w)["leading_lines_score"]
+        assert g["leading_lines_score"] == want == b["leading_lines_score"], (it["path"], g["leading_lines_score"], want)
+        thumb = Image.fromarray(img[:, :, ::-1].copy())
+        thumb.thumbnail((640, 640), Image.Resampling.LANCZOS)
+        buf = io.BytesIO()
+        thumb.save(buf, format="JPEG", quality=80)
+        assert g["thumbnail"] == buf.getvalue(), it["path"]
+        for k in p:                                                    # every other column as without the side products
+            if k != "leading_lines_score":
+                assert g[k] == p[k], (it["path"], k)
+        assert "thumbnail" not in p
