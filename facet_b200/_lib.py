@@ -27,6 +27,7 @@ _SIGNATURES = {
     "fb_profile_read": (C.c_int, [_P, _P, C.c_int]),
     "fb_tech_stats": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P]),
     "fb_tech_stats_luma": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "fb_tech_stats_fused": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "fb_tech_derive": (C.c_int, [_P, C.c_int, _P, _P]),
     "fb_tech_stats_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fb_gray_hsv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
@@ -42,6 +43,8 @@ _SIGNATURES = {
     "fb_orient": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "fb_thumbnail": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fb_thumbnail_from_reduced": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "fb_jpeg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "fb_jpeg_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int,
                                  _P, C.c_size_t, _P, C.c_int64, _P, _P]),

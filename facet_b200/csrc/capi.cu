@@ -123,7 +123,17 @@ int fb_tech_stats_luma(const uint8_t* d_images, int n, int height, int width, in
                        void* stream) {
     ProfScope ps(PROF_TECH, (cudaStream_t)stream);
     int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
-                               reinterpret_cast<long long*>(d_sums), force_generic, d_luma, (cudaStream_t)stream);
+                               reinterpret_cast<long long*>(d_sums), force_generic, d_luma, nullptr, nullptr, (cudaStream_t)stream);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
+int fb_tech_stats_fused(const uint8_t* d_images, int n, int height, int width, int64_t image_stride, int rgb_order,
+                        uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, uint8_t* d_luma, uint8_t* d_box4,
+                        const uint32_t* box_mult4, void* stream) {
+    ProfScope ps(PROF_TECH, (cudaStream_t)stream);
+    int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
+                               reinterpret_cast<long long*>(d_sums), 0, d_luma, d_box4, box_mult4, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }
@@ -132,7 +142,7 @@ int fb_tech_stats(const uint8_t* d_images, int n, int height, int width, int64_t
                   uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums, int force_generic, void* stream) {
     ProfScope ps(PROF_TECH, (cudaStream_t)stream);
     int rc = launch_tech_stats(d_images, n, height, width, (long long)image_stride, rgb_order, d_hist256, d_hs_hist,
-                               reinterpret_cast<long long*>(d_sums), force_generic, nullptr, (cudaStream_t)stream);
+                               reinterpret_cast<long long*>(d_sums), force_generic, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     if (rc == 0) count_launch(1);
     return rc;
 }
@@ -261,7 +271,18 @@ int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t 
                  uint8_t* d_out, void* stream) {
     ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
     return launch_thumbnail(d_images, n, height, width, (long long)image_stride, fx, fy, red_h, red_w, mult4, d_hbounds, d_hcoef, hk,
-                            d_vbounds, d_vcoef, vk, out_h, out_w, swap_rb, d_reduced, d_tmp, d_out, (cudaStream_t)stream);
+                            d_vbounds, d_vcoef, vk, out_h, out_w, swap_rb, d_reduced, d_tmp, d_out, 0, (cudaStream_t)stream);
+}
+
+int fb_thumbnail_from_reduced(const uint8_t* d_reduced, int n, int height, int width, int fx, int fy, int red_h, int red_w,
+                              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk, const int32_t* d_vbounds,
+                              const int32_t* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_tmp, uint8_t* d_out,
+                              void* stream) {
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    FB_REQUIRE(fx > 1 || fy > 1, "fb_thumbnail_from_reduced: no reduction in this plan");
+    return launch_thumbnail(nullptr, n, height, width, (long long)height * width * 3, fx, fy, red_h, red_w, nullptr, d_hbounds,
+                            d_hcoef, hk, d_vbounds, d_vcoef, vk, out_h, out_w, swap_rb, const_cast<uint8_t*>(d_reduced), d_tmp,
+                            d_out, 1, (cudaStream_t)stream);
 }
 
 int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_stride, int exif_orientation, int swap_rb,

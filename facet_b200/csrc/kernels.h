@@ -15,7 +15,9 @@ namespace fb {
 int tech_rows_per_unit(int n, int H, int W, int sms);
 int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
                       unsigned int* d_hist256, unsigned int* d_hs_hist, long long* d_sums, int force_generic,
-                      uint8_t* d_luma, cudaStream_t stream);
+                      uint8_t* d_luma, uint8_t* d_box4, const unsigned int* box_mult4, cudaStream_t stream);
+int launch_box_reduce(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
+                      const unsigned int* mult4, uint8_t* d_reduced, cudaStream_t stream);
 int launch_gray_hsv(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t* d_gray, uint8_t* d_hsv,
                     cudaStream_t stream);
 int launch_gray_plane(const uint8_t* d_image, int H, int W, int rgb_order, uint8_t* d_gray, unsigned int* d_hist256,
@@ -49,7 +51,7 @@ int launch_orient(const uint8_t* d_src, int n, int H, int W, long long src_strid
 int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
                      const unsigned int* mult4, const int* d_hbounds, const int* d_hcoef, int hk, const int* d_vbounds,
                      const int* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp,
-                     uint8_t* d_out, cudaStream_t stream);
+                     uint8_t* d_out, int reduced_ready, cudaStream_t stream);
 int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, const int* d_boxes, int k,
                          long long* d_out, cudaStream_t stream);
 

@@ -70,6 +70,8 @@ struct TechArgs {
     int gray_round;   // 1 << 14, passed through the constant bank so IMAD can take it as an addend
     uint8_t* luma;    // optional [n][H][W] Pillow luma plane (input of the pHash resampler), or nullptr
     int luma_round;   // 1 << 15
+    uint8_t* box;     // optional [n][ceil(H/4)][W/4][3] 4x4 box reduction (Pillow ImagingReduce, first step of the thumbnail)
+    unsigned int box_mult_full, box_mult_bottom;   // Pillow's multipliers for 16-pixel boxes / the shorter boxes of the last rows
 };
 
 __device__ __forceinline__ int sdiv_entry(int i) {   // round-half-even(255*4096 / i)
@@ -167,7 +169,9 @@ struct LaneCtx {
     uint32_t hs_unbias;   // minus the two float magic numbers (0x4B000000 * 4 + 0x4B400000 * 4 * kHsStride)
     int halo_delta;       // byte distance from the lane's first pixel to the aligned word with the halo pixel
     uint8_t* luma_lane;   // LUMA: address of (row 0, xl) in the luma plane
-    int W;
+    uint8_t* box_lane;    // BOX: address of the lane's two boxes in box row 0 of the image
+    unsigned int box_mult_full, box_mult_bottom;
+    int W, H;
 };
 
 template <bool NEED_HALO_CHECK = true>
@@ -280,6 +284,11 @@ __device__ __forceinline__ void hsv_bins(const HsvPair (&hp)[NP], const LaneCtx&
 
 enum RowMode { ROW_FIRST = 0, ROW_SECOND = 1, ROW_STEADY = 2, ROW_LAST = 3 };
 
+// Channel sums of the lane's 4-pixel-wide boxes over the rows of the current box row (BOX variant).
+struct BoxAcc {
+    unsigned int s[kGroups][3];
+};
+
 // One image row of the lane's pixel span.  Stencil state carried between rows (exact fp16 pairs; gray keeps
 // its +1024 bias, which cancels in every difference):
 //   g_p = gray of the previous row, p1 = g[y-2] - 2 g[y-1] - 1024, d_p = dxx of the previous row,
@@ -288,12 +297,12 @@ enum RowMode { ROW_FIRST = 0, ROW_SECOND = 1, ROW_STEADY = 2, ROW_LAST = 3 };
 //       SECOND = first owned row: histograms, vertical telescoped sum picks up g_p - g_c
 //       STEADY = owned row: histograms + Laplacian / Immerkaer response of the previous row
 //       LAST   = halo row below the unit: stencil of the last owned row, vertical sum picks up -(g_p - g_c)
-template <bool RGB, bool FULL, bool LUMA, int MODE>
+template <bool RGB, bool FULL, bool LUMA, bool BOX, int MODE>
 __device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const uint8_t* img, uint32_t next_off,
                                          bool need_halo, const LaneCtx& ln, int y,
                                          const __half2 (&g_p)[kPairs], __half2 (&g_c)[kPairs],
                                          const __half2 (&d_p)[kPairs], __half2 (&d_c)[kPairs], __half2 (&p1)[kPairs],
-                                         __half2 (&q1)[kPairs], WarpAcc& acc) {
+                                         __half2 (&q1)[kPairs], WarpAcc& acc, BoxAcc& bx) {
     constexpr bool hist = (MODE == ROW_SECOND || MODE == ROW_STEADY);
     constexpr bool sten = (MODE == ROW_STEADY || MODE == ROW_LAST);
 #ifdef FB_TECH_PREFETCH_EARLY
@@ -363,6 +372,37 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const
         }
     }
 
+    if (BOX && hist) {
+        // Pillow ImagingReduce(4, 4): channel sums of the 4-pixel groups with byte-selecting dot products, carried
+        // over the (up to) four rows of a box row; ((sum + n/2) * multiplier) >> 24 leaves when the box row is complete
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) {
+            const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];     // c0 c1 c2 c0 | c1 c2 c0 c1 | c2 c0 c1 c2
+            bx.s[q][0] = __dp4a(w0, 0x01000001u, __dp4a(w1, 0x00010000u, __dp4a(w2, 0x00000100u, bx.s[q][0])));
+            bx.s[q][1] = __dp4a(w0, 0x00000100u, __dp4a(w1, 0x01000001u, __dp4a(w2, 0x00010000u, bx.s[q][1])));
+            bx.s[q][2] = __dp4a(w0, 0x00010000u, __dp4a(w1, 0x00000100u, __dp4a(w2, 0x01000001u, bx.s[q][2])));
+        }
+        const int yr = y & 3;
+        if (yr == 3 || y == ln.H - 1) {          // warp-uniform
+            const unsigned int half_n = 2u * (unsigned int)(yr + 1);
+            const unsigned int m = yr == 3 ? ln.box_mult_full : ln.box_mult_bottom;
+            uint8_t* o = ln.box_lane + (size_t)(y >> 2) * (size_t)(ln.W >> 2) * 3;
+            uint16_t h16[3 * kGroups / 2];
+#pragma unroll
+            for (int i = 0; i < 3 * kGroups; i += 2) {
+                const unsigned int b0 = ((bx.s[i / 3][i % 3] + half_n) * m) >> 24;
+                const unsigned int b1 = ((bx.s[(i + 1) / 3][(i + 1) % 3] + half_n) * m) >> 24;
+                h16[i / 2] = (uint16_t)(b0 | (b1 << 8));
+            }
+            if (FULL || ln.active) {
+#pragma unroll
+                for (int i = 0; i < 3 * kGroups / 2; ++i) reinterpret_cast<uint16_t*>(o)[i] = h16[i];
+            }
+#pragma unroll
+            for (int q = 0; q < kGroups; ++q) bx.s[q][0] = bx.s[q][1] = bx.s[q][2] = 0u;
+        }
+    }
+
     // neighbours across lanes (both halves of the shuffled register are valid gray values)
     uint32_t from_left = __shfl_up_sync(0xffffffffu, h2_bits(g_c[kPairs - 1]), 1);     // .hi = last gray of lane-1
     uint32_t from_right = __shfl_down_sync(0xffffffffu, h2_bits(g_c[0]), 1);  // .lo = g[0] of lane+1
@@ -424,7 +464,7 @@ __device__ __forceinline__ void row_step(const RowRegs& cur, RowRegs& nxt, const
     }
 }
 
-template <bool RGB, bool FULL, bool LUMA>
+template <bool RGB, bool FULL, bool LUMA, bool BOX>
 __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* img, int tx, int uy, WarpAcc& acc) {
     const int lane = (int)lane_id();
     const int W = a.W, H = a.H;
@@ -445,7 +485,15 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     asm volatile("mov.b32 %0, 0x64646464;" : "=r"(ln.k64));
     asm volatile("mov.b32 %0, %1;" : "=r"(ln.hs_unbias) : "n"(0u - 4u * 0x4B000000u - (4u * kHsStride) * 0x4B400000u));
     ln.W = W;
+    ln.H = H;
     ln.luma_lane = LUMA ? (a.luma + ((size_t)(img - a.img) / 3) + xl) : nullptr;
+    // contiguous batch: image i's reduced plane starts at i * ceil(H/4) * (W/4) * 3
+    ln.box_lane = BOX ? (a.box + ((size_t)((img - a.img) / ((size_t)H * W * 3)) * (size_t)((H + 3) >> 2) * (size_t)(W >> 2) + (size_t)(xl >> 2)) * 3) : nullptr;
+    ln.box_mult_full = a.box_mult_full;
+    ln.box_mult_bottom = a.box_mult_bottom;
+    BoxAcc bx;
+#pragma unroll
+    for (int q = 0; q < kGroups; ++q) bx.s[q][0] = bx.s[q][1] = bx.s[q][2] = 0u;
 
     const uint32_t row_bytes = (uint32_t)W * 3u;
     const uint32_t lane_off = (uint32_t)xl * 3u;
@@ -466,20 +514,20 @@ __device__ __forceinline__ void process_unit(const TechArgs& a, const uint8_t* i
     // rows k = 0 .. rb+1 of the walk; row k prefetches row k+1.  Rows alternate between two register sets so
     // that (previous, current) swap by renaming instead of by moves.
     load_row(LA, img, row_off(0), need_halo, ln.halo_delta);
-    row_step<RGB, FULL, LUMA, ROW_FIRST>(LA, LB, img, row_off(1), need_halo, ln, r0 - 1, GB, GA, DB, DA, P1, Q1, acc);
-    row_step<RGB, FULL, LUMA, ROW_SECOND>(LB, LA, img, row_off(2), need_halo, ln, r0, GA, GB, DA, DB, P1, Q1, acc);
+    row_step<RGB, FULL, LUMA, BOX, ROW_FIRST>(LA, LB, img, row_off(1), need_halo, ln, r0 - 1, GB, GA, DB, DA, P1, Q1, acc, bx);
+    row_step<RGB, FULL, LUMA, BOX, ROW_SECOND>(LB, LA, img, row_off(2), need_halo, ln, r0, GA, GB, DA, DB, P1, Q1, acc, bx);
     bool odd_tail = false;
     int k = 2;
     for (; k <= rb; k += 2) {
-        row_step<RGB, FULL, LUMA, ROW_STEADY>(LA, LB, img, row_off(k + 1), need_halo, ln, r0 - 1 + k, GB, GA, DB, DA, P1, Q1, acc);
+        row_step<RGB, FULL, LUMA, BOX, ROW_STEADY>(LA, LB, img, row_off(k + 1), need_halo, ln, r0 - 1 + k, GB, GA, DB, DA, P1, Q1, acc, bx);
         if (k + 1 > rb) {
             odd_tail = true;
             break;
         }
-        row_step<RGB, FULL, LUMA, ROW_STEADY>(LB, LA, img, row_off(k + 2), need_halo, ln, r0 + k, GA, GB, DA, DB, P1, Q1, acc);
+        row_step<RGB, FULL, LUMA, BOX, ROW_STEADY>(LB, LA, img, row_off(k + 2), need_halo, ln, r0 + k, GA, GB, DA, DB, P1, Q1, acc, bx);
     }
-    if (odd_tail) row_step<RGB, FULL, LUMA, ROW_LAST>(LB, LA, img, 0u, need_halo, ln, r0 + rb, GA, GB, DA, DB, P1, Q1, acc);
-    else row_step<RGB, FULL, LUMA, ROW_LAST>(LA, LB, img, 0u, need_halo, ln, r0 + rb, GB, GA, DB, DA, P1, Q1, acc);
+    if (odd_tail) row_step<RGB, FULL, LUMA, BOX, ROW_LAST>(LB, LA, img, 0u, need_halo, ln, r0 + rb, GA, GB, DA, DB, P1, Q1, acc, bx);
+    else row_step<RGB, FULL, LUMA, BOX, ROW_LAST>(LA, LB, img, 0u, need_halo, ln, r0 + rb, GB, GA, DB, DA, P1, Q1, acc, bx);
 
     acc.l += (long long)__float2int_rn(acc.lf);
     acc.n += (unsigned long long)__float2uint_rn(acc.nf);
@@ -491,7 +539,7 @@ __global__ void smem_base_probe_kernel() {
     if (threadIdx.x == 0) g_smem_base_probe = (unsigned int)__cvta_generic_to_shared(fb_smem);
 }
 
-template <bool RGB, bool LUMA>
+template <bool RGB, bool LUMA, bool BOX>
 __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
     unsigned int* const smem = fb_smem;
     unsigned int* const s_hs = fb_smem;
@@ -535,8 +583,8 @@ __global__ void __launch_bounds__(kThreads, 1) tech_stats_kernel(TechArgs a) {
             if (u >= seg_end) break;
             const int ul = (int)(u - img_first);
             const int tx = ul % a.tiles_x;
-            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true, LUMA>(a, img, tx, ul / a.tiles_x, acc);
-            else process_unit<RGB, false, LUMA>(a, img, tx, ul / a.tiles_x, acc);
+            if ((tx + 1) * kTileW <= a.W) process_unit<RGB, true, LUMA, BOX>(a, img, tx, ul / a.tiles_x, acc);
+            else process_unit<RGB, false, LUMA, BOX>(a, img, tx, ul / a.tiles_x, acc);
         }
         const unsigned long long acc_l2 = warp_sum_u64(acc.l2);
         const unsigned long long acc_n = warp_sum_u64(acc.n);
@@ -770,7 +818,7 @@ static bool smem_base_matches() {
 
 int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long image_stride, int rgb_order,
                       unsigned int* d_hist256, unsigned int* d_hs_hist, long long* d_sums, int force_generic,
-                      uint8_t* d_luma, cudaStream_t stream) {
+                      uint8_t* d_luma, uint8_t* d_box4, const unsigned int* box_mult4, cudaStream_t stream) {
     FB_REQUIRE(d_images && d_hist256 && d_hs_hist && d_sums, "fb_tech_stats: null pointer");
     FB_REQUIRE(n >= 1 && H >= 2 && W >= 2, "fb_tech_stats: need n>=1 and images of at least 2x2 (got n=%d %dx%d)", n, H, W);
     FB_REQUIRE(image_stride >= (long long)H * W * 3, "fb_tech_stats: image_stride smaller than one image");
@@ -790,6 +838,12 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     a.gray_round = 1 << 14;
     a.luma = d_luma;
     a.luma_round = 1 << 15;
+    a.box = d_box4;
+    a.box_mult_full = box_mult4 ? box_mult4[0] : 0u;
+    a.box_mult_bottom = box_mult4 ? box_mult4[2] : 0u;
+    FB_REQUIRE(!d_box4 || box_mult4, "fb_tech_stats: the box reduction needs its multipliers");
+    FB_REQUIRE(!d_box4 || image_stride == (long long)H * W * 3, "fb_tech_stats: the box reduction needs a contiguous batch");
+    FB_REQUIRE(!d_box4 || (reinterpret_cast<uintptr_t>(d_box4) & 3) == 0, "fb_tech_stats: reduced plane must be 4-byte aligned");
     FB_REQUIRE(!d_luma || image_stride == (long long)H * W * 3, "fb_tech_stats: the luma plane needs a contiguous batch");
     FB_REQUIRE(!d_luma || (reinterpret_cast<uintptr_t>(d_luma) & 15) == 0, "fb_tech_stats: luma plane must be 16-byte aligned");
     constexpr int kAlign = kLanePx == 16 ? 16 : 8;     // vector width of the row loads
@@ -800,10 +854,15 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
     if (smem_base_ok) {
         a.tiles_x = (W + kTileW - 1) / kTileW;
         a.rows_per_unit = tech_rows_per_unit(n, H, W, sms);
+        if (d_box4) a.rows_per_unit = (a.rows_per_unit + 3) & ~3;       // units start on box rows
         a.units_y = (H + a.rows_per_unit - 1) / a.rows_per_unit;
         const size_t smem = kSmemWords * sizeof(unsigned int);
-        auto kern = d_luma ? (rgb_order ? tech_stats_kernel<true, true> : tech_stats_kernel<false, true>)
-                           : (rgb_order ? tech_stats_kernel<true, false> : tech_stats_kernel<false, false>);
+        using Kern = void (*)(TechArgs);
+        static const Kern table[8] = {tech_stats_kernel<false, false, false>, tech_stats_kernel<true, false, false>,
+                                      tech_stats_kernel<false, true, false>,  tech_stats_kernel<true, true, false>,
+                                      tech_stats_kernel<false, false, true>,  tech_stats_kernel<true, false, true>,
+                                      tech_stats_kernel<false, true, true>,   tech_stats_kernel<true, true, true>};
+        const Kern kern = table[(rgb_order ? 1 : 0) + (d_luma ? 2 : 0) + (d_box4 ? 4 : 0)];
         FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long total_units = (long long)a.tiles_x * a.units_y * n;
         int grid = (int)(total_units < sms ? total_units : sms);
@@ -816,6 +875,11 @@ int launch_tech_stats(const uint8_t* d_images, int n, int H, int W, long long im
         dim3 grid(gx, n);
         if (rgb_order) tech_stats_generic_kernel<true><<<grid, 256, 0, stream>>>(a);
         else tech_stats_generic_kernel<false><<<grid, 256, 0, stream>>>(a);
+        if (d_box4) {          // shapes the fast kernel does not take: the separate reduction pass of the thumbnail
+            FB_CUDA_OK(cudaGetLastError());
+            int rc = launch_box_reduce(d_images, n, H, W, image_stride, 4, 4, (H + 3) / 4, (W + 3) / 4, box_mult4, d_box4, stream);
+            if (rc) return rc;
+        }
     }
     FB_CUDA_OK(cudaGetLastError());
     return 0;

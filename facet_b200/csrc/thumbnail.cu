@@ -188,33 +188,45 @@ __global__ void __launch_bounds__(256) resample_v_u8_kernel(const uint8_t* __res
 
 }  // namespace
 
+int launch_box_reduce(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
+                      const unsigned int* mult4, uint8_t* d_reduced, cudaStream_t stream) {
+    FB_REQUIRE(d_images && d_reduced && mult4, "box reduction: null pointer");
+    FB_REQUIRE(red_h == (H + fy - 1) / fy && red_w == (W + fx - 1) / fx, "box reduction: reduced size does not match the factors");
+    FB_REQUIRE(n <= 65535 && red_h <= 65535, "box reduction: batch or height too large for one launch");
+    ReduceArgs a;
+    a.img = d_images; a.img_stride = image_stride; a.H = H; a.W = W; a.fx = fx; a.fy = fy; a.rh = red_h; a.rw = red_w;
+    for (int i = 0; i < 4; ++i) a.mult[i] = mult4[i];
+    a.out = d_reduced;
+    const bool vec4 = fx == 4 && W % 16 == 0 && image_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_images) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_reduced) & 3) == 0;
+    if (vec4) {
+        dim3 grid((red_w / 4 + 127) / 128, red_h, n);
+        box_reduce4_kernel<<<grid, 128, 0, stream>>>(a);
+    } else {
+        dim3 grid((red_w + 255) / 256, red_h, n);
+        box_reduce_kernel<<<grid, 256, 0, stream>>>(a);
+    }
+    FB_CUDA_OK(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
 int launch_thumbnail(const uint8_t* d_images, int n, int H, int W, long long image_stride, int fx, int fy, int red_h, int red_w,
                      const unsigned int* mult4, const int* d_hbounds, const int* d_hcoef, int hk, const int* d_vbounds,
                      const int* d_vcoef, int vk, int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp,
-                     uint8_t* d_out, cudaStream_t stream) {
-    FB_REQUIRE(d_images && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_out, "fb_thumbnail: null pointer");
+                     uint8_t* d_out, int reduced_ready, cudaStream_t stream) {
+    FB_REQUIRE((d_images || reduced_ready) && d_hbounds && d_hcoef && d_vbounds && d_vcoef && d_tmp && d_out, "fb_thumbnail: null pointer");
     FB_REQUIRE(n >= 1 && H >= 1 && W >= 1 && fx >= 1 && fy >= 1 && out_h >= 1 && out_w >= 1, "fb_thumbnail: bad sizes");
     FB_REQUIRE(red_h == (H + fy - 1) / fy && red_w == (W + fx - 1) / fx, "fb_thumbnail: reduced size does not match the factors");
     FB_REQUIRE(n <= 65535 && out_h <= 65535, "fb_thumbnail: batch or height too large for one launch");
     const uint8_t* src = d_images;
     long long src_stride = image_stride, src_pitch = (long long)W * 3;
     if (fx > 1 || fy > 1) {
-        FB_REQUIRE(d_reduced && mult4, "fb_thumbnail: the reduction needs its buffer and multipliers");
-        ReduceArgs a;
-        a.img = d_images; a.img_stride = image_stride; a.H = H; a.W = W; a.fx = fx; a.fy = fy; a.rh = red_h; a.rw = red_w;
-        for (int i = 0; i < 4; ++i) a.mult[i] = mult4[i];
-        a.out = d_reduced;
-        const bool vec4 = fx == 4 && W % 16 == 0 && image_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_images) & 15) == 0 &&
-                          (reinterpret_cast<uintptr_t>(d_reduced) & 3) == 0;
-        if (vec4) {
-            dim3 grid((red_w / 4 + 127) / 128, red_h, n);
-            box_reduce4_kernel<<<grid, 128, 0, stream>>>(a);
-        } else {
-            dim3 grid((red_w + 255) / 256, red_h, n);
-            box_reduce_kernel<<<grid, 256, 0, stream>>>(a);
+        FB_REQUIRE(d_reduced, "fb_thumbnail: the reduction needs its buffer");
+        if (!reduced_ready) {
+            int rc = launch_box_reduce(d_images, n, H, W, image_stride, fx, fy, red_h, red_w, mult4, d_reduced, stream);
+            if (rc) return rc;
         }
-        FB_CUDA_OK(cudaGetLastError());
-        count_launch(1);
         src = d_reduced;
         src_stride = (long long)red_h * red_w * 3;
         src_pitch = (long long)red_w * 3;

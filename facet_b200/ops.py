@@ -54,10 +54,19 @@ def to_device_u8(images, device=None):
     return t
 
 
-def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False, luma_out=None):
+def box4_multipliers(h: int, w: int) -> np.ndarray:
+    """Pillow's ImagingReduce multipliers of the (full, right-edge, bottom-edge, corner) boxes of a (4, 4) reduction."""
+    from .utils import thumbnail as th
+    return np.array([th.reduce_multiplier(max(1, a * b)) for a, b in
+                     ((4, 4), (w % 4 or 4, 4), (4, h % 4 or 4), (w % 4 or 4, h % 4 or 4))], dtype=np.uint32)
+
+
+def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False, luma_out=None, box_out=None):
     """Run the technical pass.  Returns CUDA tensors (hist256 u32->int32 view [n,256],
     hs_hist int32 [n,180,256], sums int64 [n,4], derived float64 [n,4]).  luma_out: optional CUDA uint8
-    [n,H,W] tensor that receives Pillow's luma plane in the same pass (input of `phash(..., luma=...)`)."""
+    [n,H,W] tensor that receives Pillow's luma plane in the same pass (input of `phash(..., luma=...)`); box_out:
+    optional CUDA uint8 [n,ceil(H/4),ceil(W/4),3] tensor that receives Pillow's (4, 4) box reduction of the frames
+    (input of `thumbnails(..., reduced=...)`)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     t = to_device_u8(images)
@@ -71,7 +80,14 @@ def tech_stats_raw(images, rgb_order: bool = False, force_generic: bool = False,
         sums = torch.empty((n, 4), dtype=torch.int64, device=dev)
         derived = torch.empty((n, 4), dtype=torch.float64, device=dev)
         st = _lib.stream_ptr()
-        if luma_out is not None:
+        if box_out is not None:
+            if tuple(box_out.shape) != (n, (h + 3) // 4, (w + 3) // 4, 3) or not box_out.is_contiguous():
+                raise ValueError("box_out must be a contiguous [n, ceil(H/4), ceil(W/4), 3] uint8 tensor")
+            mult = box4_multipliers(h, w)
+            _lib.check(lib.fb_tech_stats_fused(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
+                                               _ptr(sums), _ptr(luma_out) if luma_out is not None else None, _ptr(box_out),
+                                               mult.ctypes.data, st), "fb_tech_stats_fused")
+        elif luma_out is not None:
             _lib.check(lib.fb_tech_stats_luma(_ptr(t), n, h, w, h * w * 3, int(bool(rgb_order)), _ptr(hist), _ptr(hs),
                                               _ptr(sums), int(bool(force_generic)), _ptr(luma_out), st), "fb_tech_stats_luma")
         else:
@@ -459,10 +475,19 @@ def orient(images, exif_orientation: int = 1, swap_rb: bool = False):
 _THUMB_PLANS: dict = {}
 
 
-def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = True):
+def thumbnail_reduces_by_4(h: int, w: int, size: int = 640) -> bool:
+    """True when Pillow's thumbnail of an h x w frame starts with the (4, 4) box reduction `tech_stats_raw(box_out=)` emits."""
+    from .utils import thumbnail as th
+    p = th.plan(h, w, size)
+    return p is not None and p.fx == 4 and p.fy == 4
+
+
+def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = True, reduced=None):
     """Pillow `Image.thumbnail((size, size), LANCZOS)` of a same-shaped batch, bit-exact (the pixel work of
     utils/image_transforms.py:32-50).  images: uint8 [n,H,W,3] (BGR unless rgb_order).  Returns a CUDA uint8
-    tensor [n,h,w,3] in RGB order when to_rgb (what PIL would hold), else in the input's channel order."""
+    tensor [n,h,w,3] in RGB order when to_rgb (what PIL would hold), else in the input's channel order.
+    reduced: the (4, 4) box reduction of the frames from `tech_stats_raw(box_out=)` when `thumbnail_reduces_by_4`
+    (the frames are then not read at all)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     from .utils import thumbnail as th
@@ -470,6 +495,8 @@ def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = 
     n, h, w, _ = t.shape
     swap = bool(to_rgb) and not rgb_order
     p = th.plan(h, w, size)
+    if reduced is not None and not (p is not None and p.fx == 4 and p.fy == 4 and tuple(reduced.shape) == (n, p.red_h, p.red_w, 3)):
+        raise ValueError("reduced does not match the thumbnail plan of these frames")
     if p is None:                                   # Pillow leaves images that already fit unchanged
         return t.flip(-1).contiguous() if swap else t.clone()
     key = (h, w, size, str(t.device))
@@ -481,9 +508,14 @@ def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = 
                                             for a in (p.hbounds, p.hcoef, p.vbounds, p.vcoef))
     mult, hb, hc, vb, vc = _THUMB_PLANS[key]
     with torch.cuda.device(t.device):
-        reduced = torch.empty((n, p.red_h, p.red_w, 3), dtype=torch.uint8, device=t.device) if (p.fx > 1 or p.fy > 1) else None
         tmp = torch.empty((n, p.red_h, p.out_w, 3), dtype=torch.uint8, device=t.device)
         out = torch.empty((n, p.out_h, p.out_w, 3), dtype=torch.uint8, device=t.device)
+        if reduced is not None:
+            _lib.check(lib.fb_thumbnail_from_reduced(_ptr(reduced), n, h, w, p.fx, p.fy, p.red_h, p.red_w, _ptr(hb), _ptr(hc), p.hk,
+                                                     _ptr(vb), _ptr(vc), p.vk, p.out_h, p.out_w, int(swap), _ptr(tmp), _ptr(out),
+                                                     _lib.stream_ptr()), "fb_thumbnail_from_reduced")
+            return out
+        reduced = torch.empty((n, p.red_h, p.red_w, 3), dtype=torch.uint8, device=t.device) if (p.fx > 1 or p.fy > 1) else None
         _lib.check(lib.fb_thumbnail(_ptr(t), n, h, w, h * w * 3, p.fx, p.fy, p.red_h, p.red_w, mult.ctypes.data,
                                     _ptr(hb), _ptr(hc), p.hk, _ptr(vb), _ptr(vc), p.vk, p.out_h, p.out_w, int(swap),
                                     _ptr(reduced) if reduced is not None else None, _ptr(tmp), _ptr(out), _lib.stream_ptr()),

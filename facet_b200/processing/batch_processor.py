@@ -261,14 +261,14 @@ class BatchProcessor:
                 q.put(host)
             return [_encode_jpeg(t, 80) for t in px]
 
-        def side_products(frames, metas):
+        def side_products(frames, metas, thumbs):
             if want_lines:
                 for k, (pos, item, h, w) in enumerate(metas):
                     if item.get("leading_lines_score") is None:
                         edges = ops.canny_edges(ops.gray_plane(frames[k], rgb_order=rgb_order), 50, 150, blur=True)
                         side.setdefault(pos, {})["lines"] = pool.submit(lines_job, *d2h_async(edges, "edges", 2 * self.num_workers + 2), h, w)
-            if thumbnails:
-                px = ops.thumbnails(frames, rgb_order=rgb_order, to_rgb=True)
+            if thumbs is not None:
+                px = thumbs
                 if px.shape[0] < chunk:          # one pinned shape per frame shape: pad short chunks
                     px = torch.cat([px, px.new_zeros((chunk - px.shape[0],) + tuple(px.shape[1:]))])
                 fut = pool.submit(thumbs_job, *d2h_async(px, "thumbs", 4), len(metas))
@@ -390,10 +390,10 @@ class BatchProcessor:
                 else:
                     frames = bufs["frames"][slot][:len(metas)]
                     status = torch.zeros((len(metas),), dtype=torch.int32, device=dev)
-                px = scorer.pixel_passes_device(frames, rgb_order=rgb_order)
+                px = scorer.pixel_passes_device(frames, rgb_order=rgb_order, with_thumbnails=thumbnails)
                 px["status"] = status
                 if pool is not None:
-                    side_products(frames, metas)
+                    side_products(frames, metas, px.pop("thumbnails", None))
                 bufs["free"][slot].record(compute)
                 bufs["used"][slot] = True
                 acc["px"].append(px)

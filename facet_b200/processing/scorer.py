@@ -97,19 +97,29 @@ class Facet:
         return (cfg._scoring() if hasattr(cfg, "_scoring") else AggregateScorer(cfg)).category_of(m)
 
     # -- batched device-resident entry -------------------------------------------------------------------
-    def pixel_passes_device(self, images, rgb_order=False, with_phash=True):
+    def pixel_passes_device(self, images, rgb_order=False, with_phash=True, with_thumbnails=False):
         """The per-frame pixel work for a same-shaped CUDA uint8 batch [n,H,W,3]: technical pass (+ luma plane), perceptual
-        hash, CLIP preprocess.  Returns device tensors {hist256, sums, derived, phash, clip_in}; nothing is synchronised."""
+        hash, CLIP preprocess.  Returns device tensors {hist256, sums, derived, phash, clip_in}; nothing is synchronised.
+        with_thumbnails adds `thumbnails` (uint8 [n,h,w,3] RGB, Pillow's 640-px LANCZOS thumbnail, scorer.py:1681-1686):
+        when Pillow's plan starts with a (4, 4) box reduction (24 MP frames) the technical pass emits it from its own
+        read of the frame, so the thumbnail costs no further read."""
         n, h, w, _ = images.shape
         luma = None
+        box = None
+        if with_thumbnails and ops.thumbnail_reduces_by_4(h, w):
+            import torch
+            box = torch.empty((n, (h + 3) // 4, (w + 3) // 4, 3), dtype=torch.uint8, device=images.device)
         if with_phash and ops.phash_uses_luma_plane(h, w):
             # the technical pass also emits Pillow's luma plane, so the hash never re-reads the frame
             import torch
             luma = torch.empty((n, h, w), dtype=torch.uint8, device=images.device)
-        hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order, luma_out=luma)
+        hist, hs, sums, derived = ops.tech_stats_raw(images, rgb_order=rgb_order, luma_out=luma, box_out=box)
         hashes = ops.phash(images, rgb_order=rgb_order, device_only=True, luma=luma) if with_phash else None
         clip_in = ops.clip_preprocess(images, mean=self.mean, std=self.std, rgb_order=rgb_order)
-        return {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, "clip_in": clip_in}
+        out = {"hist256": hist, "sums": sums, "derived": derived, "phash": hashes, "clip_in": clip_in}
+        if with_thumbnails:
+            out["thumbnails"] = ops.thumbnails(images, rgb_order=rgb_order, to_rgb=True, reduced=box)
+        return out
 
     def score_images_device(self, images, rgb_order=False, with_phash=True):
         """images: CUDA uint8 [n,H,W,3].  Enqueues technical pass, perceptual hash, preprocess and ViT;

@@ -64,6 +64,17 @@ int fb_tech_stats_luma(const uint8_t* d_images, int n, int height, int width, in
                        int rgb_order, uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums,
                        int force_generic, uint8_t* d_luma, void* stream);
 
+/* Same pass with both side products of the single read of the frame (either may be NULL): d_luma as in
+ * fb_tech_stats_luma, and d_box4 [n][ceil(height/4)][width/4 rounded up][3] uint8 = Pillow's ImagingReduce by (4, 4) of
+ * the frame, ((sum + count/2) * multiplier) >> 24 per channel in the frame's channel order — the first step of
+ * `thumb.thumbnail((640, 640), LANCZOS)` on a 24 MP frame (utils/image_transforms.py:32-50, scorer.py:1681-1686), so the
+ * thumbnail needs no read of the frame of its own (fb_thumbnail_from_reduced finishes it).  box_mult4: HOST array of
+ * Pillow's multipliers for the (full, right-edge, bottom-edge, corner) boxes, as for fb_thumbnail.  Shapes the fused
+ * kernel does not take (width not a multiple of 8) run the separate reduction pass after the generic kernel. */
+int fb_tech_stats_fused(const uint8_t* d_images, int n, int height, int width, int64_t image_stride,
+                        int rgb_order, uint32_t* d_hist256, uint32_t* d_hs_hist, int64_t* d_sums,
+                        uint8_t* d_luma, uint8_t* d_box4, const uint32_t* box_mult4, void* stream);
+
 /* Per-image reductions of the H-S histogram — technical.py:97-104 (entropy) and :237
  * (mean saturation).  d_out [n][4] float64 = { entropy_bits, sum_saturation, nonzero_bins,
  * total_count }. */
@@ -171,6 +182,13 @@ int fb_thumbnail(const uint8_t* d_images, int n, int height, int width, int64_t 
                  const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
                  const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
                  int out_h, int out_w, int swap_rb, uint8_t* d_reduced, uint8_t* d_tmp, uint8_t* d_out, void* stream);
+
+/* The two Lanczos passes of fb_thumbnail on a reduced image that already exists (d_reduced [n][red_h][red_w][3], e.g.
+ * written by fb_tech_stats_fused with fx = fy = 4); height / width are those of the original frames. */
+int fb_thumbnail_from_reduced(const uint8_t* d_reduced, int n, int height, int width, int fx, int fy, int red_h, int red_w,
+                              const int32_t* d_hbounds, const int32_t* d_hcoef, int hk,
+                              const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
+                              int out_h, int out_w, int swap_rb, uint8_t* d_tmp, uint8_t* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Frame orientation — the pixel work of utils/image_loading.py:101-106 for frames already in device

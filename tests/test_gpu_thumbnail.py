@@ -51,3 +51,40 @@ def test_jpeg_bytes_equal_the_reference_call():
     thumb.save(buf, format="JPEG", quality=80)
     assert generate_photo_thumbnail(pil) == buf.getvalue()
     assert generate_photo_thumbnails(bgr[None])[0] == buf.getvalue()
+
+
+@pytest.mark.parametrize("shape", [(4000, 6000), (3001, 4504), (2667, 4000), (515, 1032), (402, 600)])
+def test_box_reduction_rides_the_technical_pass(shape):
+    """fb_tech_stats_fused: the (4, 4) box reduction (and the luma plane) written by the technical pass itself equal
+    Pillow's `reduce(4)`; the statistics are those of the plain pass; the thumbnail finished from the reduced plane
+    equals Pillow's `thumbnail((640, 640), LANCZOS)`.  Widths that are not multiples of 8 take the generic kernel and
+    the separate reduction pass behind the same call."""
+    import torch
+    from PIL import Image
+    from facet_b200 import ops
+    from facet_b200.synth import synth_image_bgr
+    h, w = shape
+    frames = np.stack([synth_image_bgr(i, h, w) for i in (4, 6)])
+    t = torch.from_numpy(frames).cuda()
+    for rgb_order in (False, True):
+        box = torch.empty((2, (h + 3) // 4, (w + 3) // 4, 3), dtype=torch.uint8, device="cuda")
+        luma = torch.empty((2, h, w), dtype=torch.uint8, device="cuda")
+        plain = ops.tech_stats_raw(t, rgb_order=rgb_order)
+        fused = ops.tech_stats_raw(t, rgb_order=rgb_order, box_out=box)
+        both = ops.tech_stats_raw(t, rgb_order=rgb_order, luma_out=luma, box_out=box.clone().zero_()) if w % 8 == 0 else None
+        for a, b in zip(plain[:3], fused[:3]):
+            assert torch.equal(a, b)
+        if both is not None:
+            for a, b in zip(plain[:3], both[:3]):
+                assert torch.equal(a, b)
+        got = box.cpu().numpy()
+        for i in range(2):
+            want = np.asarray(Image.fromarray(frames[i]).reduce(4))
+            assert np.array_equal(got[i], want), (shape, rgb_order, int((got[i] != want).sum()))
+        if ops.thumbnail_reduces_by_4(h, w):
+            th = ops.thumbnails(t, rgb_order=rgb_order, to_rgb=True, reduced=box).cpu().numpy()
+            assert np.array_equal(th, ops.thumbnails(t, rgb_order=rgb_order, to_rgb=True).cpu().numpy())
+            for i in range(2):
+                pil = Image.fromarray(frames[i] if rgb_order else frames[i][:, :, ::-1].copy())
+                pil.thumbnail((640, 640), Image.Resampling.LANCZOS)
+                assert np.array_equal(th[i], np.asarray(pil))
