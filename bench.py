@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sim-rows", type=int, default=262144, help="embeddings per GPU in the similarity leg (configs[3])")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per staging buffer of the streamed e2e path")
     ap.add_argument("--no-e2e-jpeg", action="store_true", help="skip the e2e leg that starts from JPEG file bytes")
+    ap.add_argument("--no-e2e-side", action="store_true", help="skip the e2e leg with leading-lines scores and thumbnails")
     ap.add_argument("--jpeg-restart-blocks", type=int, default=8, help="restart interval (MCUs) of the bench's JPEG streams")
     ap.add_argument("--e2e-jpeg-chunk", type=int, default=32, help="streams per decode launch in the JPEG e2e leg")
     ap.add_argument("--e2e-vit-batch", type=int, default=64, help="frames per ViT launch of the streamed e2e path")
@@ -556,6 +557,32 @@ def main():
                "ceiling_note": "copy-only leg: the same pinned frames into the same staging buffers on one copy stream, no kernels, all "
                                "ranks concurrently"}
         del stage
+
+        # ---- the same call with the two side products of the reference's loop switched on: leading-lines score per image
+        # (batch_processor.py:245) and the 640-px thumbnail JPEG (scorer.py:1681-1686).  Edge maps / thumbnail pixels come from
+        # the device in the same visit of the frame; OpenCV's Hough transform and Pillow's JPEG encoder run on host threads ----
+        if not args.no_e2e_side:
+            workers = max(2, min(16, (os.cpu_count() or 2) // max(1, world)))
+            bps = BatchProcessor(scorer, batch_size=B, num_workers=workers, leading_lines=True)
+            sitems = items[:min(len(items), 2 * B)]
+            bps.process_items_streamed(sitems[:max(chunk, 16)], chunk=chunk, vit_batch=vit_batch, thumbnails=True)      # warm-up
+            barrier()
+            bps.metrics["h2d_bytes"] = bps.metrics["d2h_bytes"] = 0
+            t0 = time.perf_counter()
+            sres = bps.process_items_streamed(sitems, chunk=chunk, vit_batch=vit_batch, thumbnails=True)
+            barrier()
+            ms_s = (time.perf_counter() - t0) * 1e3
+            assert all("error" not in r and r.get("thumbnail") for r in sres), "e2e side products: a frame failed"
+            if world > 1:
+                t = torch.tensor([ms_s], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_s = float(t.item())
+            e2e["with_leading_lines_and_thumbnails"] = {
+                "value": world * len(sitems) / (ms_s * 1e-3), "unit": "images/s", "images_per_gpu": len(sitems), "host_threads_per_gpu": workers,
+                "h2d_bytes_per_step": bps.metrics["h2d_bytes"] * B // len(sitems), "d2h_bytes_per_step": bps.metrics["d2h_bytes"] * B // len(sitems),
+                "note": "gray / 5x5 blur / Canny (csrc/canny.cu, bit-exact with OpenCV) and the thumbnail pixels (4x4 box sums emitted by the "
+                        "technical pass, csrc/thumbnail.cu) on the device; the 24 MB edge map and the thumbnail pixels leave on the D2H "
+                        "stream; cv2.HoughLinesP and the JPEG encoder on host threads bound this leg"}
 
         # ---- e2e from FILE BYTES: the same call with items that carry JPEG streams (what the reference's loader reads from
         # disk, utils/image_loading.py:90) in pinned host memory; decoding happens on the device (csrc/jpeg_decode.cu) ----

@@ -35,12 +35,28 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int kABytes = BM * BK * 2;     // 16 KB
 constexpr int kBBytes = BN * BK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kEpiPitch = 80;                               // bytes per staged row (64 B of bf16 + 16 B pad: conflict-free)
-constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch;  // per-warp 32x32 bf16 transpose buffers (20 KB)
-constexpr int kEpiBiasBytes = kEpiWarps * 512;              // per-warp copy of the 128 bias values of its columns
-constexpr int kSmemBytes = STAGES * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+// Epilogue warps per CTA.  The erf-GELU epilogue of the CTA-pair form is latency-bound with two warps per scheduler
+// (ncu: the MMA issuer waits for accumulator buffers while the tensor pipe idles 29 % of the time), so it runs 16
+// warps = four per scheduler, each on 64 of the tile's 256 columns, and gives one of the six TMA stages to their
+// staging buffers; every other epilogue keeps 8 warps on 128 columns each.
+#ifndef FB_GELU_EPI_WARPS
+#define FB_GELU_EPI_WARPS 16
+#endif
+#ifndef FB_GELU_EARLY_RELEASE
+#define FB_GELU_EARLY_RELEASE 1
+#endif
+#ifndef FB_GELU_STAGES
+#define FB_GELU_STAGES 5
+#endif
+__host__ __device__ constexpr int epi_warps(int mode, bool cl2) { return (mode == FB_GEMM_BIAS_GELU_BF16 && cl2) ? FB_GELU_EPI_WARPS : 8; }
+__host__ __device__ constexpr int gemm_threads(int mode, bool cl2) { return 64 + 32 * epi_warps(mode, cl2); }
+__host__ __device__ constexpr int gemm_stages(int mode, bool cl2) { return cl2 ? (epi_warps(mode, cl2) == 16 ? FB_GELU_STAGES : 6) : STAGES; }
+__host__ __device__ constexpr int gemm_stage_bytes(bool cl2) { return kABytes + (cl2 ? kBBytes / 2 : kBBytes); }
+__host__ __device__ constexpr int gemm_smem_bytes(int mode, bool cl2) {
+    return gemm_stages(mode, cl2) * gemm_stage_bytes(cl2) + epi_warps(mode, cl2) * (32 * kEpiPitch + 512) + 1024 /*alignment slack*/ +
+           256 /*barriers*/;
+}
 
 struct GemmArgs {
     int M, N, K;
@@ -64,6 +80,37 @@ struct GemmArgs {
 // i.e. fp32 noise; checked against scipy over [-8, 8]): 2 MUFU + 9 FMA instead of erff's ~45 instructions.
 //   0.5 x (1 + erf(x / sqrt 2)) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2)
 __device__ __forceinline__ float gelu_erf(float x) {
+#if defined(FB_GELU_KO) && FB_GELU_KO == 1      /* knock-out: the polynomial without the two MUFU operations */
+    {
+        const float z = fabsf(x) * 0.70710678118654752440f;
+        float t = fmaf(0.3275911f, z, 1.0f);
+        float p = fmaf(1.061405429f, t, -1.453152027f);
+        p = fmaf(p, t, 1.421413741f);
+        p = fmaf(p, t, -0.284496736f);
+        p = fmaf(p, t, 0.254829592f);
+        p *= t;
+        float e = -z * z * 1.4426950408889634f;
+        const float hx = 0.5f * x;
+        return fmaf(fabsf(hx), fmaf(-p, e, 1.0f), hx);
+    }
+#elif defined(FB_GELU_KO) && FB_GELU_KO == 2    /* knock-out: the two MUFU operations without the polynomial */
+    {
+        float t, e;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+        return t + e;
+    }
+#elif defined(FB_GELU_KO) && FB_GELU_KO == 3    /* knock-out: half the polynomial, one MUFU */
+    {
+        const float z = fabsf(x) * 0.70710678118654752440f;
+        float t;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+        float p = fmaf(1.061405429f, t, -1.453152027f);
+        p = fmaf(p, t, 1.421413741f);
+        const float hx = 0.5f * x;
+        return fmaf(fabsf(hx), p, hx);
+    }
+#endif
     const float z = fabsf(x) * 0.70710678118654752440f;
     float t;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
@@ -84,16 +131,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // both; its full barriers collect the bytes of both CTAs' loads, its commits free the stages and publish the
 // accumulators in both CTAs, and both CTAs' epilogue warps hand the accumulator back to the leader.
 template <int MODE, bool F16, bool CL2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE, CL2), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the shared pointer (a round trip through an integer would
     // make every later access a generic LD/ST instead of LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-    constexpr int NS = CL2 ? 6 : STAGES;                                   // pipeline stages
-    constexpr int kBPart = CL2 ? kBBytes / 2 : kBBytes;                    // bytes of B this CTA holds per stage
-    constexpr int SB = kABytes + kBPart;                                   // stage bytes (NS * SB = 192 KB either way)
-    static_assert(NS * SB == STAGES * kStageBytes, "stage ring must fill the same shared memory");
+    constexpr int kEpiWarps = epi_warps(MODE, CL2);
+    constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch;             // per-warp 32x32 bf16 transpose buffers
+    constexpr int kEpiBiasBytes = kEpiWarps * 512;                         // per-warp copy of the bias values of its columns
+    constexpr int kColsPerWarp = BN / (kEpiWarps / 4);                     // 128, or 64 with 16 epilogue warps
+    constexpr int kChunks = kColsPerWarp / 32;
+    constexpr int NS = gemm_stages(MODE, CL2);                             // pipeline stages
+    constexpr int SB = gemm_stage_bytes(CL2);                              // stage bytes
+    static_assert(gemm_smem_bytes(MODE, CL2) <= 227 * 1024, "shared memory budget");
     uint8_t* epi_stage = smem + NS * SB;
     uint8_t* epi_bias = epi_stage + kEpiStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * SB + kEpiStageBytes + kEpiBiasBytes);
@@ -232,7 +283,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===== epilogue =====
         const int ew = warp - 2;
         const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
-        const int half = ew >> 2;              // which 128 of the 256 accumulator columns
+        const int half = ew >> 2;              // which kColsPerWarp of the 256 accumulator columns
         uint8_t* stg = epi_stage + ew * (32 * kEpiPitch);
         float* bias_s = reinterpret_cast<float*>(epi_bias + ew * 512);
         constexpr bool bf16_out = (MODE == FB_GEMM_BIAS_BF16 || MODE == FB_GEMM_BIAS_GELU_BF16);
@@ -244,18 +295,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int rbase = m0 + quarter * 32;
             const int row = rbase + lane;
             const bool row_ok = row < p.M;
-            const int ncol0 = n0 + half * 128;
+            const int ncol0 = n0 + half * kColsPerWarp;
             // bias of this warp's 128 columns -> smem, while the MMAs of the tile are still running
             __syncwarp();
             {
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && ncol0 + lane * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + lane * 4));
-                *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+                if (p.bias && lane * 4 < kColsPerWarp && ncol0 + lane * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + lane * 4));
+                if (lane * 4 < kColsPerWarp) *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
             }
             __syncwarp();
             tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
 
             // coalesced residual prefetch for chunk c: lane -> row (lane>>2)+8j, 16-byte piece (lane&3) of each 64-byte half
             auto prefetch_res = [&](float4 (&rr)[8], int c) {
@@ -350,15 +401,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
 
-            if (MODE == FB_GEMM_BIAS_GELU_BF16) {
+            if (MODE == FB_GEMM_BIAS_GELU_BF16 && kChunks == 2 && FB_GELU_EARLY_RELEASE) {
+                // 16 warps x 64 columns: the whole slice of the accumulator fits in registers, so the TMEM buffer goes
+                // back to the MMA issuer before any of the erf-GELU math (the next-but-one tile no longer waits for it)
+                uint32_t va[32], vb[32];
+                float4 rz[8];
+                tc::tmem_ld_32x32(taddr, va);
+                tc::tmem_ld_32x32(taddr + 32, vb);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CL2) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tmem_empty[acc]), 0u));
+                    else tc::mbar_arrive(&tmem_empty[acc]);
+                }
+                process(va, 0, rz);
+                process(vb, 1, rz);
+            } else if (MODE == FB_GEMM_BIAS_GELU_BF16) {
                 // erf-GELU is register hungry: one register set, chunk after chunk
                 uint32_t va[32];
                 float4 rz[8];
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
                     tc::tmem_ld_32x32(taddr + 32 * c, va);
                     tc::tmem_ld_wait();
-                    if (c == 3) {
+                    if (c == kChunks - 1) {
                         tc::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -369,6 +436,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     process(va, c, rz);
                 }
             } else if (MODE == FB_GEMM_BIAS_RESIDUAL_F32) {
+                static_assert(MODE == FB_GEMM_BIAS_GELU_BF16 || kChunks == 4, "these epilogues walk four 32-column chunks");
                 // one accumulator register set, two residual sets: the (coalesced) residual loads of chunk
                 // c+1 are in flight while chunk c is added and stored
                 uint32_t va[32];
@@ -475,11 +543,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 // Clusters of two CTAs that can be co-resident for a kernel (the persistent grid must not exceed it).
 template <typename K>
-static int max_cluster_pairs(K kernel, int* out) {
+static int max_cluster_pairs(K kernel, int threads, int smem_bytes, int* out) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * sm_count(), 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -494,11 +562,12 @@ static int max_cluster_pairs(K kernel, int* out) {
 }
 
 template <typename K>
-static int launch_cluster2(K kernel, int pairs, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& p, cudaStream_t stream) {
+static int launch_cluster2(K kernel, int pairs, int threads, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& p,
+                           cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -526,33 +595,35 @@ static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, l
 #define FB_LAUNCH_MODE(MODE_)                                                                                          \
     case MODE_: {                                                                                                      \
         static PerDeviceFlag attr_set;                                                                                  \
+        constexpr int threads_ = gemm_threads(MODE_, false), smem_ = gemm_smem_bytes(MODE_, false);                    \
         if (!attr_set.get()) {                                                                                               \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_)); \
             attr_set.set();                                                                                           \
         }                                                                                                              \
-        if (p.f16) gemm_bf16_kernel<MODE_, true, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);            \
-        else gemm_bf16_kernel<MODE_, false, false><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);                 \
+        if (p.f16) gemm_bf16_kernel<MODE_, true, false><<<grid, threads_, smem_, stream>>>(ta, tb, p);                 \
+        else gemm_bf16_kernel<MODE_, false, false><<<grid, threads_, smem_, stream>>>(ta, tb, p);                      \
         break;                                                                                                         \
     }
 #define FB_LAUNCH_MODE_CL2(MODE_)                                                                                      \
     case MODE_: {                                                                                                      \
         static int max_pairs = -1;                                                                                     \
+        constexpr int threads_ = gemm_threads(MODE_, true), smem_ = gemm_smem_bytes(MODE_, true);                      \
         if (max_pairs < 0) {                                                                                           \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
-            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_)); \
+            FB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<MODE_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_)); \
             int a_ = 0, b_ = 0;                                                                                        \
-            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, false, true>, &a_);                                         \
+            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, false, true>, threads_, smem_, &a_);                        \
             if (rc) return rc;                                                                                         \
-            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, true, true>, &b_);                                          \
+            rc = max_cluster_pairs(gemm_bf16_kernel<MODE_, true, true>, threads_, smem_, &b_);                         \
             if (rc) return rc;                                                                                         \
             max_pairs = a_ < b_ ? a_ : b_;                                                                             \
         }                                                                                                              \
         const int work_ = ((tiles_m + 1) / 2) * tiles_n;                                                               \
         const int pairs_ = work_ < max_pairs ? work_ : max_pairs;                                                      \
         FB_REQUIRE(pairs_ >= 1, "fb_gemm_bf16: no cluster of two CTAs fits on this device");                          \
-        rc = p.f16 ? launch_cluster2(gemm_bf16_kernel<MODE_, true, true>, pairs_, ta, tb, p, stream)                   \
-                   : launch_cluster2(gemm_bf16_kernel<MODE_, false, true>, pairs_, ta, tb, p, stream);                 \
+        rc = p.f16 ? launch_cluster2(gemm_bf16_kernel<MODE_, true, true>, pairs_, threads_, smem_, ta, tb, p, stream)  \
+                   : launch_cluster2(gemm_bf16_kernel<MODE_, false, true>, pairs_, threads_, smem_, ta, tb, p, stream);\
         if (rc) return rc;                                                                                             \
         break;                                                                                                         \
     }
