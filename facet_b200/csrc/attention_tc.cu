@@ -17,7 +17,10 @@
 //   tcgen05  O = P V               A operand from TMEM, V as an MN-major B operand straight from
 //            the TMA tile; M=128, N=64, K=256; accumulator in TMEM columns [64,128)
 //   the 257th token is handled on the CUDA cores: as a key (one extra score per row folded into the
-//   softmax, one rank-1 update in the epilogue) and as a query (one row against all 257 keys)
+//   softmax, one rank-1 update in the epilogue) and as a query (one row against all 257 keys).  The query
+//   part runs while the group's P V products are in flight (scores and softmax of the row behind P V of
+//   tile 0, its output row behind P V of tile 1), with mixed-precision FMAs straight on the 16-bit
+//   operands (FHFMA: fp16 x fp16 + fp32, no conversions); its q / k / v rows are fetched one pair ahead
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -41,10 +44,11 @@ constexpr int kWgBytes = 98304 + 8192;
 constexpr int kSmemAttn = 2 * kWgBytes + 1024;
 
 struct XArea {
-    float q256[64], k256[64], v256[64];
+    uint32_t q256h[32], k256h[32];   // q / k rows of the 257th token as 16-bit pairs
+    float v256[64];
     float cls_p[264];
     float cls_red[16];
-    float cls_o[4][64];
+    float cls_o[64];
     float s256[2][128];      // score of query row r of tile t against key 256
     float xmax[2][128];      // row maximum / sum of each column half
     float xsum[2][128];
@@ -57,17 +61,50 @@ __device__ __forceinline__ const uint4* sw_chunk(const uint8_t* tile, int r, int
     return reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// acc + lo(a) lo(b) + hi(a) hi(b) on 16-bit pairs: fp16 products are exact in fp32, so the mixed-precision FMA
+// (FHFMA with half selectors) gives what convert-then-fmaf gives, without the conversions
 template <bool F16>
-__device__ __forceinline__ float dot64_row(const uint8_t* tile, int r, const float* vec) {
+__device__ __forceinline__ float mac2(uint32_t a, uint32_t b, float acc) {
+    if (F16) {
+        asm("{.reg .b16 al, ah, bl, bh;\n\t"
+            "mov.b32 {al, ah}, %1;\n\t"
+            "mov.b32 {bl, bh}, %2;\n\t"
+            "fma.rn.f32.f16 %0, al, bl, %0;\n\t"
+            "fma.rn.f32.f16 %0, ah, bh, %0;}"
+            : "+f"(acc) : "r"(a), "r"(b));
+        return acc;
+    }
+    acc = fmaf(tc::lo16<false>(a), tc::lo16<false>(b), acc);
+    return fmaf(tc::hi16<false>(a), tc::hi16<false>(b), acc);
+}
+// acc[0], acc[1] += p * (lo(v), hi(v)); p16 = p as an fp16 pair (F16) — the precision P has in the tensor-core product
+template <bool F16>
+__device__ __forceinline__ void axpy2(float p, uint32_t p16, uint32_t v, float& a0, float& a1) {
+    if (F16) {
+        asm("{.reg .b16 pl, ph, vl, vh;\n\t"
+            "mov.b32 {pl, ph}, %2;\n\t"
+            "mov.b32 {vl, vh}, %3;\n\t"
+            "fma.rn.f32.f16 %0, pl, vl, %0;\n\t"
+            "fma.rn.f32.f16 %1, pl, vh, %1;}"
+            : "+f"(a0), "+f"(a1) : "r"(p16), "r"(v));
+        return;
+    }
+    a0 = fmaf(p, tc::lo16<false>(v), a0);
+    a1 = fmaf(p, tc::hi16<false>(v), a1);
+}
+
+// dot product of row r of a swizzled [rows][64] tile with a 64-element vector held as 32 words of 16-bit pairs
+template <bool F16>
+__device__ __forceinline__ float dot64_row(const uint8_t* tile, int r, const uint32_t* vec) {
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const uint4 w = *sw_chunk(tile, r, c);
-        const float* v = vec + 8 * c;
-        acc = fmaf(tc::lo16<F16>(w.x), v[0], acc); acc = fmaf(tc::hi16<F16>(w.x), v[1], acc);
-        acc = fmaf(tc::lo16<F16>(w.y), v[2], acc); acc = fmaf(tc::hi16<F16>(w.y), v[3], acc);
-        acc = fmaf(tc::lo16<F16>(w.z), v[4], acc); acc = fmaf(tc::hi16<F16>(w.z), v[5], acc);
-        acc = fmaf(tc::lo16<F16>(w.w), v[6], acc); acc = fmaf(tc::hi16<F16>(w.w), v[7], acc);
+        const uint4 v = *reinterpret_cast<const uint4*>(vec + 4 * c);
+        acc = mac2<F16>(w.x, v.x, acc);
+        acc = mac2<F16>(w.y, v.y, acc);
+        acc = mac2<F16>(w.z, v.z, acc);
+        acc = mac2<F16>(w.w, v.w, acc);
     }
     return acc;
 }
@@ -158,17 +195,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
         issue_v(first);
     }
 
+    // this thread's word (two values) of the 257th token's q / k / v rows, fetched one pair ahead
+    auto load256 = [&](int pair) -> uint32_t {
+        const int b = pair >> 4, h = pair & 15;
+        return __ldg(reinterpret_cast<const uint32_t*>(qkv + ((size_t)b * kTok + 256) * (3 * kW) + (wt >> 5) * kW + h * kD + (wt & 31) * 2));
+    };
+    uint32_t pre256 = 0;
+    if (wt < 96 && first < n_pairs) pre256 = load256(first);
+    const int w8 = warp & 7;
+
     uint32_t ph_load = 0, ph_s = 0, ph_pv = 0;
     for (int pair = first; pair < n_pairs; pair += stride) {
         const int b = pair >> 4, h = pair & 15;
         const size_t tok0 = (size_t)b * kTok;
-        // the 257th token's q / k / v rows as fp32 (plain loads, overlapped with the TMA)
+        const int next = pair + stride;
         if (wt < 96) {
-            const int which = wt >> 5, d2 = (wt & 31) * 2;
-            const uint32_t v2 = *reinterpret_cast<const uint32_t*>(qkv + (tok0 + 256) * (3 * kW) + which * kW + h * kD + d2);
-            float* dst = which == 0 ? X->q256 : (which == 1 ? X->k256 : X->v256);
-            dst[d2] = tc::lo16<F16>(v2);
-            dst[d2 + 1] = tc::hi16<F16>(v2);
+            const int which = wt >> 5, i2 = wt & 31;
+            if (which == 0) X->q256h[i2] = pre256;
+            else if (which == 1) X->k256h[i2] = pre256;
+            else {
+                X->v256[2 * i2] = tc::lo16<F16>(pre256);
+                X->v256[2 * i2 + 1] = tc::hi16<F16>(pre256);
+            }
         }
         wg_sync(wg);
         tc::mbar_wait(&X->bar_qk, ph_load);
@@ -181,67 +229,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             tc::umma_commit(&X->bar_s);
         }
         // score of query row `row` of tile `half` against key 256; CUDA cores, overlaps the MMA
-        X->s256[half][row] = dot64_row<F16>(smem + kOffQ + half * 16384, row, X->k256);
+        X->s256[half][row] = dot64_row<F16>(smem + kOffQ + half * 16384, row, X->k256h);
 
-        // ---- query row 256 against all 257 keys (thread = key) ----
-        tc::mbar_wait(&X->bar_v, ph_load);
-        {
-            const float sa = dot64_row<F16>(smem + kOffK, wt, X->q256);
-            float s_last = -INFINITY;
-            if (wt == 0) {
-                s_last = 0.f;
-                for (int d = 0; d < 64; ++d) s_last = fmaf(X->q256[d], X->k256[d], s_last);
-            }
-            float mx = fmaxf(sa, s_last);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) X->cls_red[warp & 7] = mx;
-            wg_sync(wg);
-            mx = fmaxf(fmaxf(fmaxf(X->cls_red[0], X->cls_red[1]), fmaxf(X->cls_red[2], X->cls_red[3])),
-                       fmaxf(fmaxf(X->cls_red[4], X->cls_red[5]), fmaxf(X->cls_red[6], X->cls_red[7])));
-            const float pa = ex2_fast((sa - mx) * kScaleLog2);
-            X->cls_p[wt] = pa;
-            float sum = pa;
-            if (wt == 0) {
-                const float pl = ex2_fast((s_last - mx) * kScaleLog2);
-                X->cls_p[256] = pl;
-                sum += pl;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) X->cls_red[8 + (warp & 7)] = sum;
-            wg_sync(wg);
-            // o[d] = sum_j p_j V[j][d]: thread = (d, quarter of the keys)
-            const int d = wt & 63, part = wt >> 6;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int j = part * 64; j < part * 64 + 64; ++j) {
-                const uint32_t w = reinterpret_cast<const uint32_t*>(sw_chunk(smem + kOffV, j, d >> 3))[(d & 7) >> 1];
-                acc = fmaf(X->cls_p[j], (d & 1) ? tc::hi16<F16>(w) : tc::lo16<F16>(w), acc);
-            }
-            X->cls_o[part][d] = acc;
-            wg_sync(wg);
-            if (wt < 64) {
-                const float tot = ((X->cls_red[8] + X->cls_red[9]) + (X->cls_red[10] + X->cls_red[11])) +
-                                  ((X->cls_red[12] + X->cls_red[13]) + (X->cls_red[14] + X->cls_red[15]));
-                const float o = (X->cls_o[0][wt] + X->cls_o[1][wt]) + (X->cls_o[2][wt] + X->cls_o[3][wt]) + X->cls_p[256] * X->v256[wt];
-                out[(tok0 + 256) * kW + h * kD + wt] = (uint16_t)(tc::pack16<F16>(o / tot, 0.f) & 0xffffu);
-            }
-        }
-
-        const int next = pair + stride;
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
             tc::mbar_wait(&X->bar_s, ph_s);
             ph_s ^= 1;
             tc::tc_fence_after();
             if (t == 1 && wt == 0 && next < n_pairs) issue_qk(next);     // Q and K are dead once S_1 is complete
-            const float s256 = X->s256[t][row];
             // pass 1: maximum over this thread's 128 keys (four independent chains), key 256 folded into half 0
+            // (X->s256[t][row] of tile 0 was written by this very thread; tile 1 is several barriers later)
             float mx;
             {
                 uint32_t va[32], vb[32];
-                float m0 = half == 0 ? s256 : -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                float m0 = half == 0 ? X->s256[t][row] : -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                 tc::tmem_ld_32x32(t_s, va);
 #pragma unroll 1
                 for (int c = 0; c < 4; c += 2) {
@@ -269,6 +270,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             X->xmax[half][row] = mx;
             wg_sync(wg);
             mx = fmaxf(X->xmax[0][row], X->xmax[1][row]);
+            const float s256 = X->s256[t][row];
             // pass 2: p = exp2((s - m) / 8 * log2 e); P (16-bit pairs) overwrites S columns this thread has consumed
             const float mxs = mx * kScaleLog2;
             const float p_last = ex2_fast(fmaf(s256, kScaleLog2, -mxs));
@@ -304,6 +306,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             tc::tc_fence_before();
             wg_sync(wg);
             const float inv_l = 1.0f / (X->xsum[0][row] + X->xsum[1][row]);
+            if (t == 0) tc::mbar_wait(&X->bar_v, ph_load);
             if (wt == 0) {
                 tc::tc_fence_after();
                 // O = P V : 16 UMMAs of K = 16 keys (8 TMEM columns of P, 16 rows of V each)
@@ -313,10 +316,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
                     umma_bf16_ts(tmem + 64, tmem + (i < 8 ? 8 * i : 128 + 8 * (i - 8)), make_desc_mn_sw128(vbase + i * 2048), idesc_o, i != 0);
                 tc::umma_commit(&X->bar_pv);
             }
+            // ---- the 257th query row on the CUDA cores while P V runs ----
+            if (t == 0) {
+                // scores against all 257 keys (thread = key), maximum, exponentials, sum
+                const float sa = dot64_row<F16>(smem + kOffK, wt, X->q256h);
+                float s_last = -INFINITY;
+                if (wt == 0) {
+                    s_last = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 32; ++d) s_last = mac2<F16>(X->q256h[d], X->k256h[d], s_last);
+                }
+                float cm = fmaxf(sa, s_last);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                if (lane == 0) X->cls_red[w8] = cm;
+                wg_sync(wg);
+                cm = fmaxf(fmaxf(fmaxf(X->cls_red[0], X->cls_red[1]), fmaxf(X->cls_red[2], X->cls_red[3])),
+                           fmaxf(fmaxf(X->cls_red[4], X->cls_red[5]), fmaxf(X->cls_red[6], X->cls_red[7])));
+                const float pa = ex2_fast((sa - cm) * kScaleLog2);
+                X->cls_p[wt] = pa;
+                float sum = pa;
+                if (wt == 0) {
+                    const float pl = ex2_fast((s_last - cm) * kScaleLog2);
+                    X->cls_p[256] = pl;
+                    sum += pl;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) X->cls_red[8 + w8] = sum;      // read after the barriers of tile 1
+            } else {
+                if (wt < 96 && next < n_pairs) pre256 = load256(next);
+                // o[d] = sum_j p_j V[j][d]: warp = 8 values of d, lane = keys lane + 32 i (conflict-free 16-byte reads of the
+                // swizzled tile), then a transposing butterfly leaves one total per group of four lanes
+                float a8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a8[k] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int key = lane + 32 * i;
+                    const uint4 q = *sw_chunk(smem + kOffV, key, w8);
+                    const float pj = X->cls_p[key];
+                    const uint32_t p16 = F16 ? tc::pack_f16(pj, pj) : 0u;
+                    axpy2<F16>(pj, p16, q.x, a8[0], a8[1]);
+                    axpy2<F16>(pj, p16, q.y, a8[2], a8[3]);
+                    axpy2<F16>(pj, p16, q.z, a8[4], a8[5]);
+                    axpy2<F16>(pj, p16, q.w, a8[6], a8[7]);
+                }
+                float b4[4], b2[2];
+                const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float send = u16 ? a8[k] : a8[k + 4];
+                    const float keep = u16 ? a8[k + 4] : a8[k];
+                    b4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = u8 ? b4[k] : b4[k + 2];
+                    const float keep = u8 ? b4[k + 2] : b4[k];
+                    b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                float tot1 = (u4 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, u4 ? b2[0] : b2[1], 4);
+                tot1 += __shfl_xor_sync(0xffffffffu, tot1, 2);
+                tot1 += __shfl_xor_sync(0xffffffffu, tot1, 1);
+                if ((lane & 3) == 0) X->cls_o[8 * w8 + (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0)] = tot1;
+            }
             tc::mbar_wait(&X->bar_pv, ph_pv);
             ph_pv ^= 1;
             tc::tc_fence_after();
-            if (t == 1 && wt == 0 && next < n_pairs) issue_v(next);      // V is dead once O_1 is complete
             // epilogue: this thread's 32 columns of the O row + rank-1 contribution of key 256, normalised, 16-bit
             {
                 uint32_t v0[32];
@@ -331,6 +398,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc::umma_bf16(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     tc::umma_commit(&X->bar_s);
+                }
+                if (t == 1) {
+                    // V is dead: O_1 is complete and every thread is past its reads of the tile (barrier above)
+                    if (wt == 0 && next < n_pairs) issue_v(next);
+                    if (wt < 64) {
+                        const float tot = ((X->cls_red[8] + X->cls_red[9]) + (X->cls_red[10] + X->cls_red[11])) +
+                                          ((X->cls_red[12] + X->cls_red[13]) + (X->cls_red[14] + X->cls_red[15]));
+                        const float o = X->cls_o[wt] + X->cls_p[256] * X->v256[wt];
+                        out[(tok0 + 256) * kW + h * kD + wt] = (uint16_t)(tc::pack16<F16>(o / tot, 0.f) & 0xffffu);
+                    }
                 }
                 uint4* dst = reinterpret_cast<uint4*>(out + (tok0 + t * 128 + row) * kW + h * kD + half * 32);
 #pragma unroll
@@ -347,7 +424,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const uint16_t
             }
         }
         ph_load ^= 1;
-        wg_sync(wg);        // X arrays (q256 / k256 / v256 / cls_* / s256) are rewritten by the next pair
+        wg_sync(wg);        // X arrays (q256h / k256h / v256 / cls_* / s256) are rewritten by the next pair
     }
     tc::tc_fence_before();
     __syncthreads();
