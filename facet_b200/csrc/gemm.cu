@@ -36,12 +36,13 @@ constexpr int kABytes = BM * BK * 2;     // 16 KB
 constexpr int kBBytes = BN * BK * 2;     // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiPitch = 80;                               // bytes per staged row (64 B of bf16 + 16 B pad: conflict-free)
-// Epilogue warps per CTA.  The erf-GELU epilogue of the CTA-pair form is latency-bound with two warps per scheduler
-// (ncu: the MMA issuer waits for accumulator buffers while the tensor pipe idles 29 % of the time), so it runs 16
-// warps = four per scheduler, each on 64 of the tile's 256 columns, and gives one of the six TMA stages to their
-// staging buffers; every other epilogue keeps 8 warps on 128 columns each.
+// Epilogue warps per CTA: 8, each on 128 of the tile's 256 columns.  Round-2 experiment (profiles/r2_gemm_gelu_epilogue.txt):
+// the erf-GELU epilogue of the CTA-pair form with 16 warps (four per scheduler, 64 columns each, five TMA stages, the
+// accumulator handed back before any of the math) is within 2 % of the 8-warp form, and knock-out builds show its cost is
+// proportional to the FMA-pipe instruction count of the erf polynomial (not MUFU, not latency): -DFB_GELU_EPI_WARPS=16
+// builds that variant.
 #ifndef FB_GELU_EPI_WARPS
-#define FB_GELU_EPI_WARPS 16
+#define FB_GELU_EPI_WARPS 8
 #endif
 #ifndef FB_GELU_EARLY_RELEASE
 #define FB_GELU_EARLY_RELEASE 1
