@@ -370,6 +370,19 @@ int fb_cosine_candidates(const void* d_emb_bf16, int64_t n, int dim, float thres
     return rc;
 }
 
+int fb_cosine_block(const void* d_a_bf16, int64_t a_rows, int64_t a_offset, const void* d_b_bf16, int64_t b_rows, int64_t b_offset, int dim,
+                    float threshold, int triangle, int32_t* d_cand, float* d_cand_sims, int64_t cand_cap, uint64_t* d_cand_count,
+                    void* stream) {
+    FB_REQUIRE(a_offset + a_rows < (1ll << 31) && b_offset + b_rows < (1ll << 31) && d_cand_count, "fb_cosine_block: bad arguments");
+    if (a_rows <= 0 || b_rows <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(PROF_COSINE, st);
+    int rc = launch_cosine_block(d_a_bf16, (int)a_rows, (int)a_offset, d_b_bf16, (int)b_rows, (int)b_offset, dim, dim, threshold, triangle,
+                                 d_cand, d_cand_sims, (long long)cand_cap, reinterpret_cast<unsigned long long*>(d_cand_count), st);
+    if (rc == 0) count_launch(1);
+    return rc;
+}
+
 int fb_cosine_recheck(const float* d_emb_f32, int dim, const int32_t* d_cand, const uint64_t* d_cand_count, int64_t cand_cap, float tau,
                       int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count, void* stream) {
     FB_REQUIRE(d_cand_count && d_count, "fb_cosine_recheck: null pointer");

@@ -67,9 +67,12 @@ struct GemmArgs {
     long long ldo;        // elements
     const float* residual;
     long long ldr;
-    // FB_GEMM_THRESHOLD_PAIRS: candidates (row_offset + row, col) with acc >= tau and col > row_offset + row
+    // FB_GEMM_THRESHOLD_PAIRS: candidates (row_offset + row, col_offset + col) with acc >= tau and, when tri_on, global
+    // column > global row (a diagonal block of the all-pairs scan); rectangular blocks (tri_on = 0) report every hit
     float tau;
     int row_offset;
+    int col_offset;
+    int tri_on;
     int* pairs;
     float* pair_sims;
     long long pair_cap;
@@ -167,7 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int kblocks = p.K / BK;
     // similarity mode only needs tiles that contain an element with col > global row
     constexpr bool tri = (MODE == FB_GEMM_THRESHOLD_PAIRS);
-#define FB_TILE_SKIPPED(m0_, n0_) (tri && ((n0_) + BN <= (m0_) + p.row_offset + 1))
+#define FB_TILE_SKIPPED(m0_, n0_) (tri && p.tri_on && ((n0_) + p.col_offset + BN <= (m0_) + p.row_offset + 1))
     // Tile order.  Plain GEMMs walk row-major (their B operand is a weight matrix that stays in L2).  The
     // similarity scan has a B operand far larger than L2, so its tiles are walked in groups of kGroupM tile
     // rows, column by column: the CTAs running at any moment share kGroupM A tiles and every B tile is used
@@ -325,20 +328,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int col0 = ncol0 + c * 32;
                 if (MODE == FB_GEMM_THRESHOLD_PAIRS) {
                     const int grow = p.row_offset + row;
+                    const int gcol0 = p.col_offset + col0;
                     // candidates are rare: one max over the lane's 32 values decides whether to look at them at all
                     float vmax = __uint_as_float(v[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) vmax = fmaxf(vmax, __uint_as_float(v[j]));
-                    if (row_ok && col0 + 31 > grow && vmax >= p.tau) {
+                    if (row_ok && (!p.tri_on || gcol0 + 31 > grow) && vmax >= p.tau) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float sim = __uint_as_float(v[j]);
                             const int col = col0 + j;
-                            if (sim >= p.tau && col > grow && col < p.N) {
+                            if (sim >= p.tau && (!p.tri_on || gcol0 + j > grow) && col < p.N) {
                                 const unsigned long long pos = atomicAdd(p.pair_count, 1ull);
                                 if ((long long)pos < p.pair_cap) {
                                     p.pairs[2 * pos] = grow;
-                                    p.pairs[2 * pos + 1] = col;
+                                    p.pairs[2 * pos + 1] = gcol0 + j;
                                     p.pair_sims[pos] = sim;
                                 }
                             }
@@ -653,18 +657,28 @@ static int launch_gemm_common(const void* d_a, long long lda, const void* d_b, l
     return 0;
 }
 
+// Candidate pairs of one block of the all-pairs scan: the m rows at d_a (global row index a_offset + i) against the n rows at
+// d_b (global index b_offset + j).  triangle != 0 keeps only global column > global row (a block on the diagonal);
+// the candidate counter is NOT reset, so the blocks of one scan append to the same list.
+int launch_cosine_block(const void* d_a_bf16, int m, int a_offset, const void* d_b_bf16, int n, int b_offset, long long ld, int k, float tau,
+                        int triangle, int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count, cudaStream_t stream) {
+    FB_REQUIRE(d_a_bf16 && d_b_bf16 && d_pairs && d_sims && d_count, "fb_cosine_block: null pointer");
+    FB_REQUIRE(n >= 1 && m >= 1 && a_offset >= 0 && b_offset >= 0, "fb_cosine_block: bad block");
+    FB_REQUIRE(k >= BK && k % BK == 0, "fb_cosine_block: embedding dim must be a multiple of %d", BK);
+    GemmArgs p{};
+    p.M = m; p.N = n; p.K = k; p.mode = FB_GEMM_THRESHOLD_PAIRS;
+    p.tau = tau; p.row_offset = a_offset; p.col_offset = b_offset; p.tri_on = triangle ? 1 : 0;
+    p.pairs = d_pairs; p.pair_sims = d_sims; p.pair_cap = cap; p.pair_count = d_count;
+    return launch_gemm_common(d_a_bf16, ld, d_b_bf16, ld, p, stream);
+}
+
 // Candidate pairs of the cosine similarity stage: rows [row_offset, row_offset+m) of E against all n rows.
 int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int row_offset, int m, int k, float tau,
                              int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count,
                              cudaStream_t stream) {
-    FB_REQUIRE(d_emb_bf16 && d_pairs && d_sims && d_count, "fb_cosine_pairs: null pointer");
     FB_REQUIRE(n >= 1 && m >= 1 && row_offset >= 0 && row_offset + m <= n, "fb_cosine_pairs: bad row range");
-    FB_REQUIRE(k >= BK && k % BK == 0, "fb_cosine_pairs: embedding dim must be a multiple of %d", BK);
-    GemmArgs p{};
-    p.M = m; p.N = n; p.K = k; p.mode = FB_GEMM_THRESHOLD_PAIRS;
-    p.tau = tau; p.row_offset = row_offset; p.pairs = d_pairs; p.pair_sims = d_sims; p.pair_cap = cap; p.pair_count = d_count;
     const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(d_emb_bf16) + (size_t)row_offset * ld;
-    return launch_gemm_common(a, ld, d_emb_bf16, ld, p, stream);
+    return launch_cosine_block(a, m, row_offset, d_emb_bf16, n, 0, ld, k, tau, 1, d_pairs, d_sims, cap, d_count, stream);
 }
 
 int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,

@@ -61,6 +61,8 @@ int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long 
 int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int row_offset, int m, int k, float tau,
                              int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count,
                              cudaStream_t stream);
+int launch_cosine_block(const void* d_a_bf16, int m, int a_offset, const void* d_b_bf16, int n, int b_offset, long long ld, int k, float tau,
+                        int triangle, int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count, cudaStream_t stream);
 int launch_cosine_recheck(const float* d_emb_f32, long long ld, int k, const int* d_cand, const unsigned long long* d_ncand,
                           long long cand_cap, float tau, int* d_pairs, float* d_sims, long long cap,
                           unsigned long long* d_count, cudaStream_t stream);

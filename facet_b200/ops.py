@@ -453,6 +453,47 @@ def cosine_pairs_split(emb_bf16, get_emb_f32, tau: float, part: int = 0, nparts:
             cap = _grown_cap(max(nc, m), 'cosine_pairs')
 
 
+def cosine_blocks(blocks, get_emb_f32, dim: int, tau: float, band: float = 0.01, cap: int | None = None, before_block=None):
+    """Cosine pairs of a list of shard-against-shard blocks (the multi-GPU scan).  blocks: [(a_bf16 [m,dim], a_offset, b_bf16
+    [n,dim], b_offset, triangle)] with GLOBAL row offsets; `before_block(k)` is called before block k is launched (the sharded
+    flow waits there for the all-gather the block needs); `get_emb_f32()` returns the gathered float32 matrix for the recheck.
+    Returns (pairs int32 [p,2] with i < j, sims float32 [p]) — the same pairs the single-matrix scan finds for these blocks."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = blocks[0][0].device
+    rows = sum(int(b[0].shape[0]) for b in blocks)
+    e32 = None
+    with torch.cuda.device(dev):
+        cap = int(cap if cap is not None else max(1 << 16, 8 * rows))
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        while True:
+            counts.zero_()
+            cand = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            cand_s = torch.empty((cap,), dtype=torch.float32, device=dev)
+            for k, (a, a_off, b, b_off, tri) in enumerate(blocks):
+                if before_block is not None:
+                    before_block(k)
+                if a.shape[0] == 0 or b.shape[0] == 0:
+                    continue
+                _lib.check(lib.fb_cosine_block(_ptr(a), int(a.shape[0]), int(a_off), _ptr(b), int(b.shape[0]), int(b_off), int(dim),
+                                               float(tau) - float(band), int(bool(tri)), _ptr(cand), _ptr(cand_s), cap,
+                                               C.c_void_p(counts.data_ptr()), _lib.stream_ptr()), "fb_cosine_block")
+            if e32 is None:
+                e32 = get_emb_f32().contiguous()
+            pairs = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            sims = torch.empty((cap,), dtype=torch.float32, device=dev)
+            _lib.check(lib.fb_cosine_recheck(_ptr(e32), int(dim), _ptr(cand), C.c_void_p(counts.data_ptr()), cap, float(tau), _ptr(pairs),
+                                             _ptr(sims), cap, C.c_void_p(counts.data_ptr() + 8), _lib.stream_ptr()), "fb_cosine_recheck")
+            nc, m = (int(x) for x in counts.tolist())
+            if nc <= cap and m <= cap:
+                pairs = pairs[:m]
+                lo = torch.minimum(pairs[:, 0], pairs[:, 1])
+                hi = torch.maximum(pairs[:, 0], pairs[:, 1])
+                return torch.stack([lo, hi], dim=1), sims[:m]
+            cap = _grown_cap(max(nc, m), 'cosine_blocks')
+            before_block = None          # everything has arrived by now
+
+
 def orient(images, exif_orientation: int = 1, swap_rb: bool = False):
     """`ImageOps.exif_transpose` of a same-shaped batch for the given EXIF orientation code (1..8), then an
     optional channel swap (`cv2.cvtColor(RGB2BGR)`): the pixel work of utils/image_loading.py:101-106.

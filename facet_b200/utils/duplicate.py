@@ -168,12 +168,33 @@ def all_gather_embeddings(local_emb, group=None):
     return out
 
 
+def shard_blocks(rank: int, world: int, n_local: int):
+    """The shard-against-shard blocks rank `rank` scans: [(a_shard, a_lo, a_hi, b_shard, b_lo, b_hi, triangle)] with row ranges
+    inside the shards.  Every unordered pair of rows is covered by exactly one block of exactly one rank, every rank scans
+    the same number of row pairs: its own shard against itself (upper triangle; needs no other rank's data), the next
+    (world - 1) // 2 shards in ring order in full, and for an even world half of the opposite shard's block (the lower ranks
+    take the first half of their own rows against the whole opposite shard, the upper ranks their whole shard against the second
+    half of the opposite one)."""
+    blocks = [(rank, 0, n_local, rank, 0, n_local, True)]
+    for k in range(1, (world - 1) // 2 + 1):
+        blocks.append((rank, 0, n_local, (rank + k) % world, 0, n_local, False))
+    if world % 2 == 0 and world > 1:
+        half = n_local // 2
+        if rank < world // 2:
+            blocks.append((rank, 0, half, rank + world // 2, 0, n_local, False))
+        else:
+            blocks.append((rank, 0, n_local, rank - world // 2, half, n_local, False))
+    return blocks
+
+
 def cosine_pairs_sharded(local_emb, tau: float, group=None):
     """This rank's share of the all-pairs cosine scan over the shards of every rank.  [n_local, d] float32 (equal n_local
-    everywhere) -> (pairs int32 [m,2] with global row indices, sims float32 [m]).
+    everywhere) -> (pairs int32 [m,2] with global row indices i < j, sims float32 [m]).
 
-    The bf16 copy of each shard is gathered first (half the bytes) and the tensor-core scan starts on it; the float32 rows,
-    which only the recheck of the few candidates needs, are gathered by NCCL on its own stream while the scan computes."""
+    The scan is cut into shard-against-shard blocks (`shard_blocks`).  The block of the rank's own shard against itself starts at
+    once, on the local bf16 copy, WHILE NCCL gathers the bf16 copies of the other shards (half the bytes of the float32 rows) on
+    its own stream; the other blocks wait for that gather; the float32 rows, which only the recheck of the few candidates
+    needs, are gathered behind it and are waited for last."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -181,16 +202,26 @@ def cosine_pairs_sharded(local_emb, tau: float, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = local_emb.contiguous()
     n_local, d = local.shape
+    eb_local = ops.to_bf16(local)
     eb = torch.empty((world * n_local, d), dtype=torch.bfloat16, device=local.device)
-    dist.all_gather_into_tensor(eb, ops.to_bf16(local), group=group)
+    work_b = dist.all_gather_into_tensor(eb, eb_local, group=group, async_op=True)
     e32 = torch.empty((world * n_local, d), dtype=torch.float32, device=local.device)
-    work = dist.all_gather_into_tensor(e32, local, group=group, async_op=True)
+    work_f = dist.all_gather_into_tensor(e32, local, group=group, async_op=True)
+    blocks = []
+    for (sa, a_lo, a_hi, sb, b_lo, b_hi, tri) in shard_blocks(rank, world, n_local):
+        a = eb_local[a_lo:a_hi] if sa == rank else eb[sa * n_local + a_lo: sa * n_local + a_hi]
+        b = eb_local[b_lo:b_hi] if sb == rank else eb[sb * n_local + b_lo: sb * n_local + b_hi]
+        blocks.append((a, sa * n_local + a_lo, b, sb * n_local + b_lo, tri))
+
+    def before_block(k):
+        if k == 1:
+            work_b.wait()           # the compute stream waits for the NCCL stream; the host does not block
 
     def wait_f32():
-        work.wait()             # the compute stream waits for the NCCL stream; the host does not block
+        work_f.wait()
         return e32
 
-    return ops.cosine_pairs_split(eb, wait_f32, tau, part=rank, nparts=world)
+    return ops.cosine_blocks(blocks, wait_f32, d, tau, before_block=before_block)
 
 
 def find_similar_groups(local_emb, aggregates, tau: float, group=None):

@@ -276,6 +276,15 @@ int fb_cosine_pairs(const float* d_emb_f32, const void* d_emb_bf16, int64_t n, i
  * whose float64-accumulated dot product of the float32 rows is >= tau. */
 int fb_cosine_candidates(const void* d_emb_bf16, int64_t n, int dim, float threshold, int64_t row_offset, int64_t rows,
                          int32_t* d_cand, float* d_cand_sims, int64_t cand_cap, uint64_t* d_cand_count, void* stream);
+/* One block of the all-pairs scan, for the multi-GPU flow in which every rank scans shard-against-shard blocks: the a_rows
+ * rows at d_a_bf16 (global row index a_offset + i) against the b_rows rows at d_b_bf16 (global index b_offset + j), both
+ * [rows][dim] bf16 with row pitch dim.  triangle != 0 keeps only global column > global row (the block of a shard against
+ * itself); rectangular blocks report every hit as (global row, global column) — the caller orders the pair.  Candidates are
+ * APPENDED: d_cand_count is not reset, so a rank's blocks fill one list.  A rank can scan its own shard against itself while
+ * the all-gather of the other shards is still in flight (utils/duplicate.py `cosine_pairs_sharded`). */
+int fb_cosine_block(const void* d_a_bf16, int64_t a_rows, int64_t a_offset, const void* d_b_bf16, int64_t b_rows,
+                    int64_t b_offset, int dim, float threshold, int triangle, int32_t* d_cand, float* d_cand_sims,
+                    int64_t cand_cap, uint64_t* d_cand_count, void* stream);
 int fb_cosine_recheck(const float* d_emb_f32, int dim, const int32_t* d_cand, const uint64_t* d_cand_count, int64_t cand_cap, float tau,
                       int32_t* d_pairs, float* d_sims, int64_t cap, uint64_t* d_count, void* stream);
 

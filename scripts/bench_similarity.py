@@ -1,5 +1,6 @@
 """BASELINE.json configs[3]: all-pairs cosine similarity over N 768-d embeddings (planted near-duplicate clusters),
-sharded by rows across the ranks of one node; embeddings are all-gathered with NCCL when world > 1.
+sharded across the ranks of one node in shard-against-shard blocks (utils/duplicate.py cosine_pairs_sharded); the bf16 /
+float32 shards are all-gathered with NCCL inside the timed region, behind the scan of each rank's own block.
 
     python scripts/bench_similarity.py --embeddings 1000000            (1 GPU: the whole upper triangle)
     torchrun --nproc-per-node 8 ... scripts/bench_similarity.py --embeddings 1000000
@@ -23,7 +24,7 @@ def main():
     import torch
     import torch.distributed as dist
     from facet_b200 import ops
-    from facet_b200.utils.duplicate import all_gather_embeddings
+    from facet_b200.utils.duplicate import cosine_pairs_sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,8 +44,8 @@ def main():
     e = torch.nn.functional.normalize(e, dim=1)
 
     def step():
-        full = all_gather_embeddings(e) if world > 1 else e
-        return ops.cosine_pairs(full, args.tau, part=rank, nparts=world)
+        # world > 1: shard-against-shard blocks; the rank's own diagonal block runs while NCCL gathers the other shards
+        return cosine_pairs_sharded(e, args.tau)
 
     pairs, _ = step()
     torch.cuda.synchronize()

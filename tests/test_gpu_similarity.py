@@ -53,3 +53,32 @@ def test_cosine_parts_and_grouping():
     # truncated candidate buffer -> retried
     small = {tuple(p) for p in ops.cosine_pairs(et, 0.9, cap=5)[0].cpu().numpy().tolist()}
     assert small == full
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_block_decomposition_equals_the_single_scan(world):
+    """The shard-against-shard blocks of the multi-GPU flow (fb_cosine_block: diagonal blocks with the triangle test,
+    rectangular blocks, wrapped blocks whose columns lie before their rows), scanned one rank after the other on one GPU,
+    find exactly the pairs of the single-matrix scan."""
+    import torch
+    from facet_b200 import ops
+    from facet_b200.synth import synth_embeddings
+    from facet_b200.utils.duplicate import shard_blocks
+    n_local = 1000 if world != 8 else 520
+    n = world * n_local
+    emb = torch.from_numpy(synth_embeddings(n, seed=23 + world)).cuda()
+    emb = emb[torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()].contiguous()     # near-duplicates across shards
+    want, want_s = ops.cosine_pairs(emb, 0.9)
+    eb = ops.to_bf16(emb)
+    got = []
+    for rank in range(world):
+        blocks = []
+        for sa, a_lo, a_hi, sb, b_lo, b_hi, tri in shard_blocks(rank, world, n_local):
+            blocks.append((eb[sa * n_local + a_lo: sa * n_local + a_hi], sa * n_local + a_lo,
+                           eb[sb * n_local + b_lo: sb * n_local + b_hi], sb * n_local + b_lo, tri))
+        p, s = ops.cosine_blocks(blocks, lambda: emb, emb.shape[1], 0.9)
+        got.append(torch.cat([p.long(), s.view(torch.int32).long()[:, None]], dim=1))
+    got = torch.cat(got).cpu().numpy()
+    ref = torch.cat([want.long(), want_s.view(torch.int32).long()[:, None]], dim=1).cpu().numpy()
+    assert len(ref) > 50
+    assert sorted(map(tuple, got)) == sorted(map(tuple, ref))
