@@ -55,13 +55,13 @@ _SIGNATURES = {
 
 class VitLayer(C.Structure):
     _fields_ = [(n, _P) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_out", "b_out",
-                                  "w_fc", "b_fc", "w_proj", "b_proj")]
+                                  "w_fc", "b_fc", "w_proj", "b_proj", "w_qkv_ln", "s_qkv", "c_qkv", "w_fc_ln", "s_fc", "c_fc")]
 
 
 class VitWeights(C.Structure):
     _fields_ = [(n, _P) for n in ("w_patch", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b",
                                   "proj", "head_w1", "head_b1", "head_w2", "head_b2", "tag_emb")] + [
-        ("n_tags", C.c_int), ("f16", C.c_int), ("n_layers", C.c_int), ("layers", C.POINTER(VitLayer))]
+        ("n_tags", C.c_int), ("f16", C.c_int), ("n_layers", C.c_int), ("layers", C.POINTER(VitLayer)), ("fused_ln", C.c_int)]
 
 
 _SIGNATURES.update({

@@ -50,12 +50,13 @@ constexpr int kEpiPitch = 80;                               // bytes per staged 
 #ifndef FB_GELU_STAGES
 #define FB_GELU_STAGES 5
 #endif
+__host__ __device__ constexpr bool bf16_out_mode(int mode) { return mode == FB_GEMM_BIAS_BF16 || mode == FB_GEMM_BIAS_GELU_BF16; }
 __host__ __device__ constexpr int epi_warps(int mode, bool cl2) { return (mode == FB_GEMM_BIAS_GELU_BF16 && cl2) ? FB_GELU_EPI_WARPS : 8; }
 __host__ __device__ constexpr int gemm_threads(int mode, bool cl2) { return 64 + 32 * epi_warps(mode, cl2); }
 __host__ __device__ constexpr int gemm_stages(int mode, bool cl2) { return cl2 ? (epi_warps(mode, cl2) == 16 ? FB_GELU_STAGES : 6) : STAGES; }
 __host__ __device__ constexpr int gemm_stage_bytes(bool cl2) { return kABytes + (cl2 ? kBBytes / 2 : kBBytes); }
 __host__ __device__ constexpr int gemm_smem_bytes(int mode, bool cl2) {
-    return gemm_stages(mode, cl2) * gemm_stage_bytes(cl2) + epi_warps(mode, cl2) * (32 * kEpiPitch + 512) + 1024 /*alignment slack*/ +
+    return gemm_stages(mode, cl2) * gemm_stage_bytes(cl2) + epi_warps(mode, cl2) * (32 * kEpiPitch + 1024) + 1024 /*alignment slack*/ +
            256 /*barriers*/;
 }
 
@@ -78,6 +79,17 @@ struct GemmArgs {
     long long pair_cap;
     unsigned long long* pair_count;
     int f16;              // operands (and 16-bit outputs) are fp16 instead of bf16
+    // LayerNorm fold (csrc/vit_forward.cu).  Producer side, FB_GEMM_BIAS_RESIDUAL_F32: besides the fp32 residual stream the
+    // epilogue writes a 16-bit copy of it (the A operand of the next GEMM) and, per row and per 128-column slice, the sum and the
+    // sum of squares of the new values.  Consumer side, FB_GEMM_BIAS_BF16 / _GELU_BF16: the A operand is that raw copy and the
+    // weights carry the LayerNorm gain, so LayerNorm(x) W^T + b = rstd_r (acc - mean_r s_n) + c_n with s_n = sum_k gamma_k W_nk
+    // and c_n = sum_k beta_k W_nk + b_n (passed as `bias`); mean / rstd come from the producer's row sums.
+    void* out16;          // [M][ldo16] 16-bit copy of the output, or nullptr
+    long long ldo16;
+    float* row_stats;     // producer: [M][ln_slots][2] (sum, sum of squares); consumer: the same array, read
+    int ln_slots;         // slices per row (N / 128 of the producer)
+    const float* ln_s;    // consumer: [N] column sums of the folded weights, or nullptr (no fold)
+    int ln_width;         // consumer: number of elements a row of the normalised operand has (1024)
 };
 
 // Exact (erf) GELU, nn.GELU() of the reference tower.  erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
@@ -143,7 +155,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     constexpr int kEpiWarps = epi_warps(MODE, CL2);
     constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch;             // per-warp 32x32 bf16 transpose buffers
-    constexpr int kEpiBiasBytes = kEpiWarps * 512;                         // per-warp copy of the bias values of its columns
+    constexpr int kEpiBiasBytes = kEpiWarps * 1024;                        // per-warp copy of the bias (and LayerNorm-fold column sum) values of its columns
     constexpr int kColsPerWarp = BN / (kEpiWarps / 4);                     // 128, or 64 with 16 epilogue warps
     constexpr int kChunks = kColsPerWarp / 32;
     constexpr int NS = gemm_stages(MODE, CL2);                             // pipeline stages
@@ -289,7 +301,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
         const int half = ew >> 2;              // which kColsPerWarp of the 256 accumulator columns
         uint8_t* stg = epi_stage + ew * (32 * kEpiPitch);
-        float* bias_s = reinterpret_cast<float*>(epi_bias + ew * 512);
+        float* bias_s = reinterpret_cast<float*>(epi_bias + ew * 1024);
+        float* lns_s = bias_s + 128;
+        const bool ln_fold = bf16_out_mode(MODE) && p.ln_s != nullptr;
         constexpr bool bf16_out = (MODE == FB_GEMM_BIAS_BF16 || MODE == FB_GEMM_BIAS_GELU_BF16);
         int iter = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
@@ -306,7 +320,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias && lane * 4 < kColsPerWarp && ncol0 + lane * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + lane * 4));
                 if (lane * 4 < kColsPerWarp) *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+                if (ln_fold && lane * 4 < kColsPerWarp) {
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ncol0 + lane * 4 < p.N) s4 = __ldg(reinterpret_cast<const float4*>(p.ln_s + ncol0 + lane * 4));
+                    *reinterpret_cast<float4*>(lns_s + lane * 4) = s4;
+                }
             }
+            // LayerNorm fold: mean and 1 / std of this thread's row from the producer's per-slice sums (fixed order)
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (ln_fold && row_ok) {
+                const float* st2 = p.row_stats + (size_t)row * p.ln_slots * 2;
+                float sx = 0.f, sq = 0.f;
+                for (int i = 0; i < p.ln_slots; ++i) {
+                    const float2 v2 = *reinterpret_cast<const float2*>(st2 + 2 * i);
+                    sx += v2.x;
+                    sq += v2.y;
+                }
+                const float inv_w = 1.0f / (float)p.ln_width;
+                ln_mean = sx * inv_w;
+                ln_rstd = rsqrtf(fmaxf(sq * inv_w - ln_mean * ln_mean, 0.f) + 1e-5f);
+            }
+            // producer side: running (sum, sum of squares) of the rows this lane sees after the transpose: rows (lane >> 2) + 8 j
+            float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
             __syncwarp();
             tc::mbar_wait(&tmem_full[acc], (iter >> 1) & 1);
             tc::tc_fence_after();
@@ -355,10 +390,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
-                    f[j] = __uint_as_float(v[j]) + b4.x;
-                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    if (ln_fold) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + j);
+                        f[j] = fmaf(ln_rstd, fmaf(-ln_mean, s4.x, __uint_as_float(v[j])), b4.x);
+                        f[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, s4.y, __uint_as_float(v[j + 1])), b4.y);
+                        f[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, s4.z, __uint_as_float(v[j + 2])), b4.z);
+                        f[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, s4.w, __uint_as_float(v[j + 3])), b4.w);
+                    } else {
+                        f[j] = __uint_as_float(v[j]) + b4.x;
+                        f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                        f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                        f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    }
                 }
                 if (MODE == FB_GEMM_BIAS_GELU_BF16) {
 #pragma unroll
@@ -398,6 +441,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 if (MODE == FB_GEMM_BIAS_RESIDUAL_F32) {
                                     const float4 r4 = rr[hh * 4 + j];
                                     val.x += r4.x; val.y += r4.y; val.z += r4.z; val.w += r4.w;
+                                    if (p.out16) {
+                                        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out16) + (size_t)(rbase + rl) * p.ldo16 + col0 + 16 * hh + 4 * (lane & 3)) =
+                                            make_uint2(tc::pack16<F16>(val.x, val.y), tc::pack16<F16>(val.z, val.w));
+                                        st_s[j] += (val.x + val.y) + (val.z + val.w);
+                                        st_q[j] += fmaf(val.x, val.x, val.y * val.y) + fmaf(val.z, val.z, val.w * val.w);
+                                    }
                                 }
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)(rbase + rl) * p.ldo + col0 + 16 * hh + 4 * (lane & 3)) = val;
                             }
@@ -468,6 +517,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             else tc::mbar_arrive(&tmem_empty[acc]);
                         }
                 process(va, 3, rb);
+                if (p.out16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a = st_s[j], b = st_q[j];
+                        a += __shfl_xor_sync(0xffffffffu, a, 1);
+                        b += __shfl_xor_sync(0xffffffffu, b, 1);
+                        a += __shfl_xor_sync(0xffffffffu, a, 2);
+                        b += __shfl_xor_sync(0xffffffffu, b, 2);
+                        const int rl = (lane >> 2) + 8 * j;
+                        if ((lane & 3) == 0 && rbase + rl < p.M && ncol0 < p.N)
+                            *reinterpret_cast<float2*>(p.row_stats + ((size_t)(rbase + rl) * p.ln_slots + (ncol0 >> 7)) * 2) = make_float2(a, b);
+                    }
+                }
             } else {
                 // two register sets: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
                 uint32_t va[32], vb[32];
@@ -681,9 +743,9 @@ int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int ro
     return launch_cosine_block(a, m, row_offset, d_emb_bf16, n, 0, ld, k, tau, 1, d_pairs, d_sims, cap, d_count, stream);
 }
 
-int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
-                     const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
-                     cudaStream_t stream) {
+int launch_gemm_bf16_ln(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
+                        const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
+                        const GemmLnFold* ln, cudaStream_t stream) {
     FB_REQUIRE(d_a && d_b && d_out, "fb_gemm_bf16: null pointer");
     FB_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % BK == 0, "fb_gemm_bf16: K must be a positive multiple of %d (got %d)", BK, K);
     FB_REQUIRE(N % 32 == 0, "fb_gemm_bf16: N must be a multiple of 32 (got %d)", N);
@@ -698,7 +760,26 @@ int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long 
     GemmArgs p{};
     p.M = M; p.N = N; p.K = K; p.mode = mode; p.bias = d_bias; p.out = d_out; p.ldo = ldo;
     p.residual = d_residual; p.ldr = ldr; p.f16 = f16;
+    if (ln) {
+        if (mode == FB_GEMM_BIAS_RESIDUAL_F32) {
+            FB_REQUIRE(ln->out16 && ln->row_stats && ln->ln_slots * 128 == N && (ln->ldo16 * 2) % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(ln->out16) & 7) == 0 && (reinterpret_cast<uintptr_t>(ln->row_stats) & 7) == 0,
+                       "LayerNorm fold (producer): needs the 16-bit copy, the row sums and N = 128 * slots");
+            p.out16 = ln->out16; p.ldo16 = ln->ldo16; p.row_stats = ln->row_stats; p.ln_slots = ln->ln_slots;
+        } else {
+            FB_REQUIRE((mode == FB_GEMM_BIAS_BF16 || mode == FB_GEMM_BIAS_GELU_BF16) && ln->ln_s && ln->row_stats && ln->ln_slots >= 1 &&
+                       ln->ln_width >= 1 && d_bias && (reinterpret_cast<uintptr_t>(ln->ln_s) & 15) == 0,
+                       "LayerNorm fold (consumer): needs the column sums, the folded bias and the row sums");
+            p.ln_s = ln->ln_s; p.row_stats = ln->row_stats; p.ln_slots = ln->ln_slots; p.ln_width = ln->ln_width;
+        }
+    }
     return launch_gemm_common(d_a, lda, d_b, ldb, p, stream);
+}
+
+int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
+                     const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
+                     cudaStream_t stream) {
+    return launch_gemm_bf16_ln(d_a, lda, d_b, ldb, M, N, K, mode, d_bias, d_out, ldo, d_residual, ldr, nullptr, stream);
 }
 
 }  // namespace fb

@@ -58,6 +58,19 @@ int launch_roi_laplacian(const uint8_t* d_image, int H, int W, int rgb_order, co
 int launch_gemm_bf16(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
                      const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
                      cudaStream_t stream);
+// LayerNorm fold of the ViT tower (csrc/gemm.cu GemmArgs): producer (residual epilogue) writes out16 + row_stats, consumer
+// (bias / GELU epilogue) reads row_stats + ln_s.
+struct GemmLnFold {
+    void* out16;
+    long long ldo16;
+    float* row_stats;
+    int ln_slots;
+    const float* ln_s;
+    int ln_width;
+};
+int launch_gemm_bf16_ln(const void* d_a, long long lda, const void* d_b, long long ldb, int M, int N, int K, int mode,
+                        const float* d_bias, void* d_out, long long ldo, const float* d_residual, long long ldr,
+                        const GemmLnFold* ln, cudaStream_t stream);
 int launch_cosine_candidates(const void* d_emb_bf16, long long ld, int n, int row_offset, int m, int k, float tau,
                              int* d_pairs, float* d_sims, long long cap, unsigned long long* d_count,
                              cudaStream_t stream);
@@ -71,6 +84,11 @@ int launch_im2col_patch14(const float* d_x, int batch, void* d_out, int f16, cud
 int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta,
                      const float* cls, const float* pos, void* d_out, long long ld_out, int out_bf16,
                      cudaStream_t stream);   // out_bf16: 0 = fp32, 1 = bf16, 2 = fp16
+// ln_pre with the class-token / positional-embedding assembly, additionally writing the 16-bit copy of the residual stream and
+// the row sums the LayerNorm fold of the first block needs (slot 0 carries the whole row, the other slots are zero)
+int launch_layernorm_pre_fold(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta, const float* cls,
+                              const float* pos, float* d_out, long long ld_out, void* d_out16, int f16, float* d_row_stats, int ln_slots,
+                              cudaStream_t stream);
 int launch_attention_tc(const void* d_qkv, int batch, void* d_out, int f16, cudaStream_t stream);   // tcgen05
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,

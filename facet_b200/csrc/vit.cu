@@ -295,6 +295,89 @@ int launch_layernorm(const float* d_in, long long ld_in, int rows, const float* 
     return 0;
 }
 
+// ln_pre (class token + positional embedding assembly) for the LayerNorm-fold path: fp32 residual stream, its 16-bit copy and
+// the (sum, sum of squares) of every output row in slot 0 of the row-sum array (the other slots are zeroed).
+template <bool F16>
+__global__ void __launch_bounds__(256) layernorm_pre_fold_kernel(const float* __restrict__ in, long long ld_in, int rows,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ cls, const float* __restrict__ pos,
+                                                                 float* __restrict__ out, long long ld_out, uint16_t* __restrict__ out16,
+                                                                 float* __restrict__ row_stats, int ln_slots) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float v[32];
+    const int b = row / kTokens, t = row - b * kTokens;
+    const float* src = (t == 0) ? cls : in + ((size_t)b * 256 + (t - 1)) * ld_in;
+    const float* pp = pos + (size_t)t * kWidth;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(src + j * 128 + lane * 4);
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j * 128 + lane * 4));
+        v[4 * j] = a.x + p4.x; v[4 * j + 1] = a.y + p4.y; v[4 * j + 2] = a.z + p4.z; v[4 * j + 3] = a.w + p4.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / kWidth);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float d = v[j] - mean;
+        q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / kWidth) + 1e-5f);
+    float os = 0.f, oq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + j * 128 + lane * 4));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + j * 128 + lane * 4));
+        const float o0 = (v[4 * j] - mean) * rstd * g4.x + b4.x;
+        const float o1 = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+        const float o2 = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
+        const float o3 = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+        *reinterpret_cast<float4*>(out + (size_t)row * ld_out + j * 128 + lane * 4) = make_float4(o0, o1, o2, o3);
+        uint2 pk;
+        if (F16) {
+            __half2 lo = __floats2half2_rn(o0, o1), hi = __floats2half2_rn(o2, o3);
+            pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+            pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * kWidth + j * 128 + lane * 4) = pk;
+        os += (o0 + o1) + (o2 + o3);
+        oq += fmaf(o0, o0, o1 * o1) + fmaf(o2, o2, o3 * o3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        os += __shfl_xor_sync(0xffffffffu, os, o);
+        oq += __shfl_xor_sync(0xffffffffu, oq, o);
+    }
+    if (lane < ln_slots) {
+        const float2 v2 = lane == 0 ? make_float2(os, oq) : make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(row_stats + ((size_t)row * ln_slots + lane) * 2) = v2;
+    }
+}
+
+int launch_layernorm_pre_fold(const float* d_in, long long ld_in, int rows, const float* gamma, const float* beta, const float* cls,
+                              const float* pos, float* d_out, long long ld_out, void* d_out16, int f16, float* d_row_stats, int ln_slots,
+                              cudaStream_t stream) {
+    FB_REQUIRE(d_in && gamma && beta && cls && pos && d_out && d_out16 && d_row_stats && rows >= 1 && ln_slots >= 1 && ln_slots <= 32,
+               "fb_vit_layernorm (fold): bad arguments");
+    const int blocks = (rows + 7) / 8;
+    if (f16) layernorm_pre_fold_kernel<true><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, cls, pos, d_out, ld_out,
+                                                                         reinterpret_cast<uint16_t*>(d_out16), d_row_stats, ln_slots);
+    else layernorm_pre_fold_kernel<false><<<blocks, 256, 0, stream>>>(d_in, ld_in, rows, gamma, beta, cls, pos, d_out, ld_out,
+                                                                      reinterpret_cast<uint16_t*>(d_out16), d_row_stats, ln_slots);
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_vit_tail(const float* d_x, int batch, const float* g, const float* be, const float* proj, const float* w1,
                     const float* b1, const float* w2, const float* b2, const float* tags, int ntags, float* feat,
                     float* emb, float* raw, float* sims, cudaStream_t stream) {

@@ -80,7 +80,7 @@ def random_state_dict(seed: int = 0, layers: int = LAYERS, dtype=None):
 class ClipVitL14:
     """Device-resident packed weights + workspace; ``encode`` runs the whole tower in one C call."""
 
-    def __init__(self, state_dict, tag_embeddings=None, device=None, dtype="fp16"):
+    def __init__(self, state_dict, tag_embeddings=None, device=None, dtype="fp16", fold_layernorm=True):
         """dtype: 16-bit format of GEMM weights and activations.  "fp16" (default) is the precision the
         reference itself runs on CUDA (`self.model.half()`, processing/scorer.py:515) and keeps the
         aesthetic score within 0.01 of the fp32 oracle with a wide margin; "bf16" has the same
@@ -118,6 +118,19 @@ class ClipVitL14:
             L.w_out, L.b_out = bf16(sd[p + "attn.out_proj.weight"]).data_ptr(), f32(sd[p + "attn.out_proj.bias"]).data_ptr()
             L.w_fc, L.b_fc = bf16(sd[p + "mlp.c_fc.weight"]).data_ptr(), f32(sd[p + "mlp.c_fc.bias"]).data_ptr()
             L.w_proj, L.b_proj = bf16(sd[p + "mlp.c_proj.weight"]).data_ptr(), f32(sd[p + "mlp.c_proj.bias"]).data_ptr()
+            if fold_layernorm:
+                # LayerNorm(x) W^T + b = rstd (x (W * gamma)^T - mean * s) + c, s = row sums of the 16-bit (W * gamma), c = W beta + b
+                for ln, wk, bk, names in (("ln_1", "attn.in_proj_weight", "attn.in_proj_bias", ("w_qkv_ln", "s_qkv", "c_qkv")),
+                                          ("ln_2", "mlp.c_fc.weight", "mlp.c_fc.bias", ("w_fc_ln", "s_fc", "c_fc"))):
+                    wt = sd[p + wk].detach().to(self.device, torch.float32)
+                    gam = sd[p + ln + ".weight"].detach().to(self.device, torch.float32)
+                    bet = sd[p + ln + ".bias"].detach().to(self.device, torch.float32)
+                    w_ln = bf16(wt * gam[None, :])
+                    s_n = f32(w_ln.to(torch.float64).sum(dim=1).to(torch.float32))
+                    c_n = f32((wt.to(torch.float64) @ bet.to(torch.float64) + sd[p + bk].detach().to(self.device, torch.float64)).to(torch.float32))
+                    setattr(L, names[0], w_ln.data_ptr())
+                    setattr(L, names[1], s_n.data_ptr())
+                    setattr(L, names[2], c_n.data_ptr())
         w = _lib.VitWeights()
         w.w_patch = bf16(wp).data_ptr()
         w.class_emb = f32(sd["class_embedding"]).data_ptr()
@@ -134,6 +147,7 @@ class ClipVitL14:
             self.n_tags = int(te.shape[0])
         w.n_tags = self.n_tags
         w.f16 = 1 if dtype == "fp16" else 0
+        w.fused_ln = 1 if fold_layernorm else 0
         w.n_layers = self.n_layers
         w.layers = C.cast(self.layers, C.POINTER(_lib.VitLayer))
         self.weights = w

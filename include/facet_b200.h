@@ -315,6 +315,13 @@ typedef struct fb_vit_layer {
     const void *w_out;  const float *b_out;    /* [1024][1024] */
     const void *w_fc;   const float *b_fc;     /* [4096][1024] */
     const void *w_proj; const float *b_proj;   /* [1024][4096] */
+    /* LayerNorm fold (optional, all six or none; used when fb_vit_weights.fused_ln != 0): the two LayerNorms of the block are
+     * folded into the GEMMs that consume them.  w_*_ln = the weight with LayerNorm's gain on its input columns
+     * (W[n][k] * gamma[k], 16-bit), s_* [n] = sum_k of those 16-bit values, c_* [n] = sum_k beta[k] * W[n][k] + b[n].  The
+     * residual GEMM in front writes the 16-bit copy of the residual stream and per-row sums; LayerNorm(x) W^T + b is then
+     * rstd_r * (x16 W_ln^T - mean_r * s) + c in the consumer's epilogue: no LayerNorm pass over the residual stream. */
+    const void *w_qkv_ln; const float *s_qkv; const float *c_qkv;
+    const void *w_fc_ln;  const float *s_fc;  const float *c_fc;
 } fb_vit_layer;
 
 typedef struct fb_vit_weights {
@@ -331,6 +338,7 @@ typedef struct fb_vit_weights {
                                                   `.half()` on CUDA, processing/scorer.py:515) */
     int n_layers;                              /* 24 */
     const fb_vit_layer *layers;                /* HOST array of n_layers entries */
+    int fused_ln;                              /* != 0: use the layers' LayerNorm-fold fields (see fb_vit_layer) */
 } fb_vit_weights;
 
 size_t fb_vit_workspace_bytes(int batch);

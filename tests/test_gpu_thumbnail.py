@@ -53,7 +53,7 @@ def test_jpeg_bytes_equal_the_reference_call():
     assert generate_photo_thumbnails(bgr[None])[0] == buf.getvalue()
 
 
-@pytest.mark.parametrize("shape", [(4000, 6000), (3001, 4504), (2667, 4000), (515, 1032), (402, 600)])
+@pytest.mark.parametrize("shape", [(4000, 6000), (3001, 4504), (2667, 4000), (515, 1032), (402, 600), (403, 1001)])
 def test_box_reduction_rides_the_technical_pass(shape):
     """fb_tech_stats_fused: the (4, 4) box reduction (and the luma plane) written by the technical pass itself equal
     Pillow's `reduce(4)`; the statistics are those of the plain pass; the thumbnail finished from the reduced plane
