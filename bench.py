@@ -414,6 +414,25 @@ def main():
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     ms_step_profiled = pe0.elapsed_time(pe1) / K
+    # the same K steps with the LayerNorm fold switched off (49 separate LayerNorm launches, plain GEMM epilogues): the GEMM
+    # figure of the fold carries the LayerNorm work, this one is the GEMM alone
+    unfused = None
+    if not os.environ.get("FB_VIT_NO_LN_FOLD"):
+        os.environ["FB_VIT_NO_LN_FOLD"] = "1"
+        try:
+            step(0)
+            _lib.profile_enable(True)
+            qe0, qe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            qe0.record()
+            for k in range(K):
+                step(k)
+            qe1.record()
+            prof_u = _lib.profile_read()
+            _lib.profile_enable(False)
+            unfused = {"step_ms_with_event_pairs": qe0.elapsed_time(qe1) / K, "gemm_ms_per_step": prof_u["gemm"][0] / K,
+                       "layernorm_ms_per_step": prof_u["layernorm"][0] / K, "layernorm_launches_per_step": prof_u["layernorm"][1] / K}
+        finally:
+            del os.environ["FB_VIT_NO_LN_FOLD"]
     per_step = {k: (v[0] / K, v[1] / K) for k, v in prof.items() if v[1]}
     ms_tech, ms_pre = per_step["technical"][0], per_step["preprocess"][0]
     ms_phash = per_step.get("other", (0.0, 0))[0]
@@ -437,6 +456,12 @@ def main():
                 "algorithmic_flops_per_step": B * GEMM_GFLOP_PER_IMAGE * 1e9, "kernel_ms_per_step": gemm_ms,
                 "timing": "CUDA-event pairs around every launch of the kernel, on the launching stream, over K steps",
                 "peak_source": peaks["source"], "share_of_step": gemm_ms / ms_step_profiled,
+                "note": "the GEMM epilogues carry the LayerNorm work of the tower (fold: 16-bit copy of the residual stream + row sums out of "
+                        "the residual epilogues, normalisation finished in the QKV / fc epilogues; 1 LayerNorm launch per step instead of 49)",
+                "with_separate_layernorm": None if unfused is None else dict(
+                    unfused, achieved=B * GEMM_GFLOP_PER_IMAGE * 1e9 / (unfused["gemm_ms_per_step"] * 1e-3) / 1e12,
+                    frac=B * GEMM_GFLOP_PER_IMAGE * 1e9 / (unfused["gemm_ms_per_step"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                    note="same K steps with FB_VIT_NO_LN_FOLD=1: plain GEMM epilogues + 49 layernorm_kernel launches"),
                 "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
                                      "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"],
                                      "algorithmic_bytes_per_step": B * TECH_BYTES_PER_IMAGE,
