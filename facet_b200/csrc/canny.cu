@@ -272,7 +272,7 @@ int launch_canny(const uint8_t* d_gray, int H, int W, int blur, int low, int hig
         blur5_kernel<<<tiles, kCThreads, 0, stream>>>(d_gray, d_blur, H, W);
         src = d_blur;
     }
-    FB_CUDA_OK(cudaMemsetAsync(d_cls + (n & ~(size_t)3), 0, 8, stream));      // padding bytes of the last class word
+    if (n & 3) FB_CUDA_OK(cudaMemsetAsync(d_cls + n, 0, 4 - (n & 3), stream));      // padding bytes of the last class word
     if (d_count) FB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
     sobel_nms_kernel<<<tiles, kCThreads, 0, stream>>>(src, H, W, low, high, d_cls, d_label);
     long long want = ((long long)n + 255) / 256;

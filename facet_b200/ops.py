@@ -396,7 +396,7 @@ def cosine_pairs(emb_f32, tau: float, part: int = 0, nparts: int = 1, band: floa
     with torch.cuda.device(e.device):
         eb = torch.empty((n, d), dtype=torch.bfloat16, device=e.device)
         _lib.check(lib.fb_f32_to_bf16(_ptr(e), _ptr(eb), n * d, _lib.stream_ptr()), "fb_f32_to_bf16")
-        cap = int(cap if cap is not None else max(1 << 16, 8 * n))
+        cap = int(cap if cap is not None else max(1 << 20, 8 * n))      # 1 M candidates (12 MB): small, dense sets need no second pass
         counts = torch.zeros(2, dtype=torch.int64, device=e.device)
         while True:
             cand = torch.empty((cap, 2), dtype=torch.int32, device=e.device)
@@ -434,7 +434,7 @@ def cosine_pairs_split(emb_bf16, get_emb_f32, tau: float, part: int = 0, nparts:
     r0, r1 = bounds[part], bounds[part + 1]
     e32 = None
     with torch.cuda.device(eb.device):
-        cap = int(cap if cap is not None else max(1 << 16, 8 * n))
+        cap = int(cap if cap is not None else max(1 << 20, 8 * n))      # 1 M candidates (12 MB): small, dense sets need no second pass
         counts = torch.zeros(2, dtype=torch.int64, device=eb.device)
         while True:
             cand = torch.empty((cap, 2), dtype=torch.int32, device=eb.device)
@@ -464,7 +464,7 @@ def cosine_blocks(blocks, get_emb_f32, dim: int, tau: float, band: float = 0.01,
     rows = sum(int(b[0].shape[0]) for b in blocks)
     e32 = None
     with torch.cuda.device(dev):
-        cap = int(cap if cap is not None else max(1 << 16, 8 * rows))
+        cap = int(cap if cap is not None else max(1 << 20, 8 * rows))   # 1 M candidates (12 MB): small, dense sets need no second pass
         counts = torch.zeros(2, dtype=torch.int64, device=dev)
         while True:
             counts.zero_()
