@@ -203,3 +203,16 @@ class ScoringConfig:
         if isinstance(standalone, dict):
             vocab.update(standalone)
         return vocab
+
+    def get_category_tags(self, category):
+        """scoring_config.py:752-766: the tag names (keys of the category's `tags` dict) that trigger a category."""
+        for cat in self.config.get("categories", []):
+            if cat.get("name") == category:
+                tags = cat.get("tags", {})
+                if isinstance(tags, dict):
+                    return list(tags.keys())
+        return []
+
+    def get_art_tags(self):
+        """scoring_config.py:748-750."""
+        return set(self.get_category_tags("art"))

@@ -36,7 +36,7 @@ class CLIPTagger:
         self.text_embeddings = None
         self.tag_names = None
         self.tag_vocabulary = config.get_tag_vocabulary() if config is not None else {}
-        self.art_tags = set()
+        self.art_tags = config.get_art_tags() if (config is not None and hasattr(config, "get_art_tags")) else set()
         if text_embeddings is not None:
             self.set_text_embeddings(text_embeddings, tag_names)
 
@@ -89,3 +89,8 @@ class CLIPTagger:
             if name not in scores or sim > scores[name]:
                 scores[name] = float(sim)
         return {t: round(s, 3) for t, s in scores.items() if s >= threshold}
+
+    def is_artwork(self, clip_embedding_bytes, threshold=0.24):
+        """tagger.py:146-158: any art-category tag among the ten best tags at this threshold."""
+        tags = self.get_tags_from_embedding(clip_embedding_bytes, threshold=threshold, max_tags=10)
+        return bool(set(tags) & self.art_tags)

@@ -104,6 +104,15 @@ def test_tagger_and_single_image_twins(scorer):
     want = [t for t, _ in sorted(best.items(), key=lambda kv: -kv[1])[:3]]
     assert got == want
     assert 0.0 <= sc.score_from_embedding(e) <= 10.0
+    # tagger.py:116-158: scores of the tags above a threshold, and the art test on the ten best tags
+    scores = sc.tagger.get_tags_with_scores(e, threshold=-1.0)
+    assert set(scores) == set(best) and all(abs(scores[t] - round(best[t], 3)) <= 2e-3 for t in best)
+    ten = set(sc.tagger.get_tags_from_embedding(e, threshold=-1.0, max_tags=10))
+    sc.tagger.art_tags = {want[0]}
+    assert sc.tagger.is_artwork(e, threshold=-1.0) is True
+    sc.tagger.art_tags = {"no such tag"}
+    assert sc.tagger.is_artwork(e, threshold=-1.0) is False and len(ten) == 10
+    sc.tagger.art_tags = set()
 
 
 def test_batch_processor_with_config_fills_aggregate_and_category(tmp_path):
