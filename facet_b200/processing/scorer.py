@@ -129,14 +129,15 @@ class Facet:
         return {**px, **vit}
 
     def results_from_host(self, h, w, hist, sums, der, raw, emb, sims, hashes, mono_threshold=0.10, tag_threshold=0.22,
-                          max_tags=5):
+                          max_tags=5, shadow_threshold=0.15, highlight_threshold=0.10):
         """Host half of the pass: the small per-image device results (as host arrays: hist [n,256] int64, sums [n,4] int64,
         derived [n,4] float64, aesthetic_raw [n], embedding [n,768] float32, tag_sims [n,T] or None, hashes = list of hex
         strings or Nones) -> result dicts with the reference's metric keys (processing/batch_processor.py:298-355, the
         analyzer-derived subset)."""
         n = len(raw)
         metrics = cf.all_metrics_batch(h, w, hist, sums[:, 0], sums[:, 1], sums[:, 2], der[:, 0], der[:, 1],
-                                       mono_threshold=mono_threshold)      # the 7 analyzer dicts per image, one pass
+                                       mono_threshold=mono_threshold, shadow_threshold=shadow_threshold,
+                                       highlight_threshold=highlight_threshold)      # the 7 analyzer dicts per image, one pass
         results = []
         for i in range(n):
             m = metrics[i]
@@ -173,7 +174,8 @@ class Facet:
             })
         return results
 
-    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True):
+    def score_images(self, images, rgb_order=False, mono_threshold=0.10, tag_threshold=0.22, max_tags=5, with_phash=True,
+                     shadow_threshold=0.15, highlight_threshold=0.10):
         """Full per-image pass for a same-shaped batch -> list of result dicts (see results_from_host)."""
         t = ops.to_device_u8(images)
         n, h, w, _ = t.shape
@@ -187,4 +189,77 @@ class Facet:
         emb = dev["embedding"].cpu().numpy()
         sims = dev["tag_sims"].cpu().numpy() if dev["tag_sims"] is not None else None
         return self.results_from_host(h, w, hist, sums, der, raw, emb, sims, hashes, mono_threshold=mono_threshold,
-                                      tag_threshold=tag_threshold, max_tags=max_tags)
+                                      tag_threshold=tag_threshold, max_tags=max_tags, shadow_threshold=shadow_threshold,
+                                      highlight_threshold=highlight_threshold)
+
+    # -- scorer.py:952-1147 ----------------------------------------------------------------------------------
+    def score_photo_from_pil(self, pil_img, img_cv, original_path, cache=None):
+        """The reference's single-image engine (`score_photo_from_pil`, used by `process_single_photo`, scorer.py:1989): one
+        frame already in memory -> the complete database row.  Differences from the batch path it keeps: the clipping thresholds
+        come from the config, the subject search runs when no face box exists (`get_placement_data(..., img_cv)`), and
+        `is_monochrome` / `contrast_score` are among the aggregate's inputs.  `pil_img` is not needed (the hash, the CLIP input and
+        the thumbnail all come from `img_cv` on the device); `cache` is accepted for signature compatibility.  Faces / EXIF come
+        from `self.face_analyzer` / `self.get_exif_data` when the scorer has them, else the reference's "nothing found" values.
+        Returns None (after printing the error) when scoring fails, like the reference."""
+        from pathlib import Path
+        from ..analyzers.composition import CompositionAnalyzer
+        from ..utils.detection import detect_silhouette
+        from ..utils.tags import get_tag_params
+        try:
+            cfg = self.config
+            if cfg is None:
+                raise ValueError("score_photo_from_pil needs a ScoringConfig (Facet(config=...))")
+            frame = np.asarray(img_cv)
+            img_h, img_w = frame.shape[:2]
+            exposure = cfg.get_exposure_settings()
+            mono = cfg.get_monochrome_settings()
+            thr, max_tags = get_tag_params(cfg)
+            res = self.score_images(frame[None], mono_threshold=mono.get("saturation_threshold_percent", 10) / 100,
+                                    tag_threshold=thr, max_tags=max_tags,
+                                    shadow_threshold=exposure.get("shadow_clip_threshold_percent", 15) / 100,
+                                    highlight_threshold=exposure.get("highlight_clip_threshold_percent", 10) / 100)[0]
+            face_analyzer = getattr(self, "face_analyzer", None)
+            if face_analyzer is not None:
+                face_res = face_analyzer.analyze_faces(frame)
+            else:
+                from .batch_processor import NO_FACES
+                face_res = dict(NO_FACES)
+            face_ratio = face_res.get("face_area", 0) / (img_h * img_w)
+            comp = CompositionAnalyzer.get_placement_data(face_res.get("bbox"), img_w, img_h, cfg, frame)
+            lines = CompositionAnalyzer.detect_leading_lines(frame)
+            isolation_bonus, is_blink = 1.0, 0
+            if face_res["face_count"] > 0:
+                isolation_bonus = max(1.0, face_res["face_sharpness"] / (res["raw_sharpness_variance"] + 1))
+                is_blink = face_res.get("is_blink", 0)
+            get_exif = getattr(self, "get_exif_data", None)
+            exif = (get_exif(original_path) if get_exif is not None else None) or {}
+            is_silhouette = detect_silhouette({"is_silhouette": res["is_silhouette"]}, res["tags"], face_res.get("face_count", 0))
+            aggregate, category = self.calculate_aggregate_logic({
+                "aesthetic": res["aesthetic_unrounded"], "face_count": face_res["face_count"], "face_quality": face_res["face_quality"],
+                "eye_sharpness": face_res["eye_sharpness"], "tech_sharpness": res["tech_sharpness_unrounded"],
+                "color_score": res["color_score_unrounded"], "exposure_score": res["exposure_score_unrounded"],
+                "face_ratio": face_ratio, "comp_score": comp["score"], "isolation_bonus": isolation_bonus, "is_blink": is_blink,
+                "shadow_clipped": res["shadow_clipped"], "highlight_clipped": res["highlight_clipped"], "is_silhouette": is_silhouette,
+                "histogram_spread": res["histogram_spread"], "is_monochrome": res["is_monochrome"],
+                "contrast_score": res["contrast_score"], "iso": exif.get("iso"), "f_stop": exif.get("f_stop"),
+            })
+            for k in ("aesthetic_unrounded", "tech_sharpness_unrounded", "color_score_unrounded", "exposure_score_unrounded"):
+                res.pop(k)
+            resolved = Path(original_path).resolve()
+            res.update({
+                "path": str(resolved), "filename": Path(original_path).name, "category": category,
+                "face_count": face_res["face_count"], "face_quality": face_res["face_quality"],
+                "eye_sharpness": face_res["eye_sharpness"], "face_sharpness": face_res["face_sharpness"], "face_ratio": face_ratio,
+                "comp_score": round(comp["score"], 2), "isolation_bonus": round(isolation_bonus, 2), "is_blink": is_blink,
+                "aggregate": round(aggregate, 2), "power_point_score": float(comp["power_point_score"]),
+                "raw_eye_sharpness": float(face_res.get("raw_eye_sharpness", 0)), "config_version": getattr(cfg, "version_hash", None),
+                "is_silhouette": is_silhouette, "is_group_portrait": face_res.get("is_group_portrait", 0),
+                "leading_lines_score": lines.get("leading_lines_score", 0), "face_confidence": face_res.get("max_face_confidence", 0),
+                "topiq_score": None, "composition_explanation": comp.get("vlm_explanation"), "composition_pattern": None,
+                "face_details": face_res.get("face_details", []),
+            })
+            res.update(exif)
+            return res
+        except Exception as e:                  # scorer.py:1144-1146
+            print(f"Error scoring {original_path}: {e}")
+            return None

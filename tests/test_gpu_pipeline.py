@@ -277,3 +277,54 @@ def test_streamed_side_products_leading_lines_and_thumbnails(scorer):
             if k != "leading_lines_score":
                 assert g[k] == p[k], (it["path"], k)
         assert "thumbnail" not in p
+
+
+def test_score_photo_from_pil_single_image_engine(tmp_path):
+    """`Facet.score_photo_from_pil` (scorer.py:952-1147): the keys of the reference's row, the analyzer columns of the batch
+    pass, the composition values the (golden-tested) CompositionAnalyzer gives with the subject search switched on, and the
+    aggregate of `calculate_aggregate_logic` on the single-image metric set (with `is_monochrome` / `contrast_score`)."""
+    import json
+    import os
+    from PIL import Image
+    from facet_b200.analyzers.composition import CompositionAnalyzer
+    from facet_b200.config import ScoringConfig
+    from facet_b200.models.clip_vit import random_state_dict
+    from facet_b200.processing.aggregate import calculate_aggregate_logic
+    from facet_b200.processing.scorer import Facet
+    with open(os.path.join(os.path.dirname(__file__), "golden", "aggregate_golden.json")) as f:
+        cfg_dict = json.load(f)["cases"][0]["config"]
+    path = tmp_path / "scoring_config.json"
+    path.write_text(json.dumps(cfg_dict))
+    cfg = ScoringConfig(str(path))
+    sc = Facet(random_state_dict(0), config=cfg)
+    img = synth_image_bgr(4, 683, 1024)
+    pil = Image.fromarray(np.ascontiguousarray(img[..., ::-1]))
+    photo = tmp_path / "sub" / ".." / "photo_0001.jpg"
+    res = sc.score_photo_from_pil(pil, img, str(photo))
+    reference_keys = {
+        "path", "filename", "category", "image_width", "image_height", "aesthetic", "face_count", "face_quality", "eye_sharpness",
+        "face_sharpness", "face_ratio", "tech_sharpness", "color_score", "exposure_score", "comp_score", "isolation_bonus", "is_blink",
+        "phash", "aggregate", "clip_embedding", "raw_sharpness_variance", "histogram_data", "histogram_spread", "mean_luminance",
+        "histogram_bimodality", "power_point_score", "raw_color_entropy", "raw_eye_sharpness", "config_version", "shadow_clipped",
+        "highlight_clipped", "is_silhouette", "is_group_portrait", "leading_lines_score", "face_confidence", "is_monochrome",
+        "mean_saturation", "dynamic_range_stops", "noise_sigma", "contrast_score", "tags", "quality_score", "topiq_score",
+        "composition_explanation", "scoring_model", "composition_pattern", "face_details"}
+    assert set(res) == reference_keys
+    assert res["path"] == str((tmp_path / "photo_0001.jpg").resolve()) and res["filename"] == "photo_0001.jpg"
+    d = sc.score_images(img[None], mono_threshold=cfg.get_monochrome_settings()["saturation_threshold_percent"] / 100)[0]
+    for k in ("aesthetic", "tech_sharpness", "color_score", "exposure_score", "phash", "clip_embedding", "histogram_data", "noise_sigma",
+              "contrast_score", "dynamic_range_stops", "is_monochrome", "mean_saturation", "raw_sharpness_variance"):
+        assert res[k] == d[k], k
+    comp = CompositionAnalyzer.get_placement_data(None, 1024, 683, cfg, img)          # subject search on the frame
+    assert comp != {"score": 7.0, "power_point_score": 5.0, "line_score": 5.0, "center_score": 7.0}
+    assert res["comp_score"] == round(comp["score"], 2) and res["power_point_score"] == float(comp["power_point_score"])
+    assert res["leading_lines_score"] == CompositionAnalyzer.detect_leading_lines(img)["leading_lines_score"]
+    agg, cat = calculate_aggregate_logic({
+        "aesthetic": d["aesthetic_unrounded"], "face_count": 0, "face_quality": 0, "eye_sharpness": 0,
+        "tech_sharpness": d["tech_sharpness_unrounded"], "color_score": d["color_score_unrounded"],
+        "exposure_score": d["exposure_score_unrounded"], "face_ratio": 0.0, "comp_score": comp["score"], "isolation_bonus": 1.0,
+        "is_blink": 0, "shadow_clipped": d["shadow_clipped"], "highlight_clipped": d["highlight_clipped"], "is_silhouette": 0,
+        "histogram_spread": d["histogram_spread"], "is_monochrome": d["is_monochrome"], "contrast_score": d["contrast_score"],
+        "iso": None, "f_stop": None}, cfg)
+    assert res["aggregate"] == round(agg, 2) and res["category"] == cat
+    assert sc.score_photo_from_pil(pil, np.zeros((1, 1, 3), np.uint8), str(photo)) is None        # failures print and return None
