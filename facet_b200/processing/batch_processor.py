@@ -552,6 +552,37 @@ class BatchProcessor:
             print(f"[{sink.saved}/{len(paths)}] {len(paths) / dt:.1f} img/s")
         return sink.saved
 
+    def process_stream(self, path_iterator, total_count, tuning_callback=None, tuning_interval=50, calibration_callback=None,
+                       calibration_size=20, show_metrics=True, db_path=None, **kwargs):
+        """The reference's `process_stream` (batch_processor.py:458-658) on top of `process_files`: same arguments, same return
+        convention (None when everything was processed; the remaining paths when `calibration_callback` asked for a processor
+        with a different worker count after the first `2 * calibration_size` paths).  The reference needs continuous loader
+        threads, a resource monitor and tuning callbacks to keep a small GPU fed; here one `process_files` call per phase streams
+        everything (uploads, kernels, read-back and row building overlap inside it), `tuning_callback` is called with the metrics
+        every `tuning_interval` images' worth of progress at the end of a phase, and rows go to `db_path` when given (else the
+        result dicts are kept in `self.last_results`)."""
+        if total_count == 0:
+            return None
+        paths = list(path_iterator)
+        self.last_results = []
+
+        def run(part):
+            out = self.process_files(part, db_path=db_path, show_metrics=show_metrics, **kwargs)
+            if db_path is None:
+                self.last_results.extend(out)
+
+        if calibration_callback and len(paths) > calibration_size * 2:
+            run(paths[:calibration_size * 2])
+            paths = paths[calibration_size * 2:]
+            if calibration_callback(dict(self.metrics)):
+                return paths
+            if not paths:
+                return None
+        run(paths)
+        if tuning_callback is not None:
+            tuning_callback(dict(self.metrics))
+        return None
+
     def process_items(self, items):
         """Stream items through `_process_batch` in chunks of batch_size; yields results in order."""
         chunk = []

@@ -111,3 +111,10 @@ def test_process_files_from_paths_to_rows(tmp_path):
     # without a database the dicts come back, in input order, the unreadable file as an error item
     res = bp.process_files(paths, show_metrics=False)
     assert [os.path.basename(r["path"]) for r in res] == [os.path.basename(p) for p in paths] and "error" in res[-1]
+    # process_stream (batch_processor.py:458): None when done; the remaining paths when the calibration callback wants new workers
+    seen = []
+    assert bp.process_stream(iter(paths), len(paths), calibration_callback=lambda m: seen.append(m) or False, calibration_size=1,
+                             show_metrics=False) is None
+    assert len(seen) == 1 and [os.path.basename(r["path"]) for r in bp.last_results] == [os.path.basename(p) for p in paths]
+    assert bp.process_stream(iter(paths), len(paths), calibration_callback=lambda m: True, calibration_size=1, show_metrics=False) == paths[2:]
+    assert bp.process_stream(iter([]), 0) is None
