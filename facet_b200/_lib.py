@@ -45,6 +45,9 @@ _SIGNATURES = {
                                _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fb_thumbnail_from_reduced": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P,
                                             C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "fb_jpeg_encode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "fb_jpeg_encode_out_stride": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "fb_jpeg_encode": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, _P, C.c_size_t, _P, C.c_int64, _P, _P]),
     "fb_jpeg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "fb_jpeg_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int,
                                  _P, C.c_size_t, _P, C.c_int64, _P, _P]),

@@ -285,6 +285,19 @@ int fb_thumbnail_from_reduced(const uint8_t* d_reduced, int n, int height, int w
                             d_out, 1, (cudaStream_t)stream);
 }
 
+size_t fb_jpeg_encode_workspace_bytes(int n, int height, int width) { return jpeg_encode_workspace_bytes(n, height, width); }
+size_t fb_jpeg_encode_out_stride(int height, int width, int header_bytes) { return jpeg_encode_out_stride(height, width, header_bytes); }
+
+int fb_jpeg_encode(const uint8_t* d_rgb, int n, int height, int width, int64_t image_stride, const void* d_tables, const uint8_t* d_header,
+                   int header_bytes, void* d_workspace, size_t workspace_bytes, uint8_t* d_out, int64_t out_stride, uint32_t* d_length,
+                   void* stream) {
+    ProfScope ps(PROF_OTHER, (cudaStream_t)stream);
+    int rc = launch_jpeg_encode(d_rgb, n, height, width, (long long)image_stride, d_tables, d_header, header_bytes, d_workspace,
+                                workspace_bytes, d_out, (long long)out_stride, d_length, (cudaStream_t)stream);
+    if (rc == 0) count_launch(4);
+    return rc;
+}
+
 int fb_orient(const uint8_t* d_src, int n, int height, int width, int64_t src_stride, int exif_orientation, int swap_rb,
               uint8_t* d_dst, int64_t dst_stride, void* stream) {
     // PIL's transpose method per EXIF orientation (ImageOps.exif_transpose) as (swap, flip_x, flip_y):

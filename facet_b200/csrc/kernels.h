@@ -100,6 +100,11 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
                        const void* d_tables, int n, int width, int height, int ncomp, const int* hs, const int* vs, const int* tq,
                        const int* td, const int* ta, int restart_interval, long long max_scan_bytes, int bgr, void* d_workspace,
                        size_t workspace_bytes, uint8_t* d_out, long long out_stride, int* d_status, cudaStream_t stream);
+size_t jpeg_encode_workspace_bytes(int n, int H, int W);
+size_t jpeg_encode_out_stride(int H, int W, int header_len);
+int launch_jpeg_encode(const uint8_t* d_rgb, int n, int H, int W, long long image_stride, const void* d_tables, const uint8_t* d_header,
+                       int header_len, void* d_ws, size_t ws_bytes, uint8_t* d_out, long long out_stride, unsigned int* d_length,
+                       cudaStream_t stream);
 void count_launch(int k);
 
 // Optional per-category CUDA-event timing of the library's launches (bench.py roofline): when enabled every

@@ -564,6 +564,39 @@ def thumbnails(images, size: int = 640, rgb_order: bool = False, to_rgb: bool = 
     return out
 
 
+_JPEG_ENC_DEV: dict = {}
+
+
+def jpeg_encode(images_rgb, quality: int = 80, as_device: bool = False):
+    """JPEG streams of a same-shaped batch of RGB images (CUDA uint8 [n,H,W,3] or numpy), byte-exact with
+    `PIL.Image.fromarray(img).save(buf, format='JPEG', quality=quality)` — the encoder call of utils/image_transforms.py:47.
+    Returns a list of `bytes`, or with as_device the (streams uint8 [n, stride], lengths int32 [n]) CUDA tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    from .utils import jpeg as fj
+    t = to_device_u8(images_rgb)
+    n, h, w, _ = t.shape
+    header, packed = fj.encoder_tables(h, w, quality)
+    key = (h, w, int(quality), str(t.device))
+    if key not in _JPEG_ENC_DEV:
+        _JPEG_ENC_DEV[key] = (torch.from_numpy(np.frombuffer(header, np.uint8).copy()).to(t.device),
+                              torch.from_numpy(np.frombuffer(packed, np.uint8).copy()).to(t.device))
+    d_header, d_tables = _JPEG_ENC_DEV[key]
+    with torch.cuda.device(t.device):
+        ws_bytes = int(lib.fb_jpeg_encode_workspace_bytes(n, h, w))
+        stride = int(lib.fb_jpeg_encode_out_stride(h, w, len(header)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=t.device)
+        out = torch.empty((n, stride), dtype=torch.uint8, device=t.device)
+        lengths = torch.empty(n, dtype=torch.int32, device=t.device)
+        _lib.check(lib.fb_jpeg_encode(_ptr(t), n, h, w, h * w * 3, _ptr(d_tables), _ptr(d_header), len(header), _ptr(ws), ws_bytes,
+                                      _ptr(out), stride, _ptr(lengths), _lib.stream_ptr()), "fb_jpeg_encode")
+    if as_device:
+        return out, lengths
+    lens = lengths.cpu().numpy()
+    host = out[:, :int(lens.max())].cpu().numpy()
+    return [host[i, :lens[i]].tobytes() for i in range(n)]
+
+
 _PHASH_PLANS: dict = {}
 
 

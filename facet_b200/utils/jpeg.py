@@ -248,3 +248,74 @@ def _pack_table_set(qtables, huff) -> bytes:
 def pack_tables(info: JpegInfo) -> bytes:
     """One table set (TABLESET_BYTES): q[4][64] uint16 in natural order, DC tables 0..3, AC tables 0..3."""
     return info.packed_tables
+
+
+# ---- encoder side: what fb_jpeg_encode needs beside the pixels ---------------------------------------------------------------
+_ZIGZAG = (0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63)
+_ENC_CACHE: dict = {}
+
+
+def encoder_tables(height: int, width: int, quality: int = 80):
+    """(header bytes, packed tables) for `Image.save(format='JPEG', quality=quality)` of an RGB image of this size.
+
+    The header — SOI, JFIF APP0, the two DQT and four DHT segments, SOF0, the SOS header — does not depend on the pixels, so it is
+    taken from the stream Pillow (the reference's encoder, utils/image_transforms.py:47) writes for a blank image of this size; the
+    quantisation and Huffman tables fb_jpeg_encode uses are parsed from that same header.  Packed layout (3328 bytes): uint16
+    q8[2][64] = 8 x quantisation value in natural order (luma, chroma), uint16 code[4][256], uint8 size[4][256] for the DC luma,
+    AC luma, DC chroma and AC chroma tables."""
+    key = (int(height), int(width), int(quality))
+    if key in _ENC_CACHE:
+        return _ENC_CACHE[key]
+    import io
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.new("RGB", (int(width), int(height))).save(buf, format="JPEG", quality=int(quality))
+    data = buf.getvalue()
+    i, q, huff = 2, {}, {}
+    while True:
+        if data[i] != 0xFF:
+            raise ValueError("unexpected byte in the JPEG header Pillow wrote")
+        marker, length = data[i + 1], (data[i + 2] << 8) | data[i + 3]
+        seg = data[i + 4:i + 2 + length]
+        if marker == 0xDB:
+            p = 0
+            while p < len(seg):
+                if seg[p] >> 4:
+                    raise ValueError("16-bit quantisation table")
+                nat = np.zeros(64, np.uint16)
+                nat[list(_ZIGZAG)] = np.frombuffer(seg[p + 1:p + 65], np.uint8)
+                q[seg[p] & 15] = nat
+                p += 65
+        elif marker == 0xC4:
+            p = 0
+            while p < len(seg):
+                bits = list(seg[p + 1:p + 17])
+                n = sum(bits)
+                huff[(seg[p] >> 4, seg[p] & 15)] = (bits, list(seg[p + 17:p + 17 + n]))
+                p += 17 + n
+        elif marker == 0xC0:
+            # 3 components, 2x2 / 1x1 / 1x1 sampling is what the encoder kernels implement (Pillow's default at quality <= 100... )
+            comps = [(seg[6 + 3 * c], seg[7 + 3 * c], seg[8 + 3 * c]) for c in range(seg[5])]
+            if seg[5] != 3 or [c[1] for c in comps] != [0x22, 0x11, 0x11] or [c[2] for c in comps] != [0, 1, 1]:
+                raise ValueError("Pillow did not choose YCbCr 4:2:0 with two quantisation tables for this setting")
+        elif marker == 0xDA:
+            header = bytes(data[:i + 2 + length])
+            break
+        i += 2 + length
+    packed = np.zeros(3328, np.uint8)
+    packed[:256].view(np.uint16)[:] = np.concatenate([q[0] * 8, q[1] * 8]).astype(np.uint16)
+    code = packed[256:256 + 2048].view(np.uint16).reshape(4, 256)
+    size = packed[256 + 2048:].reshape(4, 256)
+    for t, key2 in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        bits, vals = huff[key2]
+        c, k = 0, 0
+        for length in range(1, 17):
+            for _ in range(bits[length - 1]):
+                code[t, vals[k]] = c
+                size[t, vals[k]] = length
+                c += 1
+                k += 1
+            c <<= 1
+    _ENC_CACHE[key] = (header, packed.tobytes())
+    return _ENC_CACHE[key]

@@ -190,6 +190,24 @@ int fb_thumbnail_from_reduced(const uint8_t* d_reduced, int n, int height, int w
                               const int32_t* d_vbounds, const int32_t* d_vcoef, int vk,
                               int out_h, int out_w, int swap_rb, uint8_t* d_tmp, uint8_t* d_out, void* stream);
 
+/* JPEG encoding of the thumbnails — the encoder half of utils/image_transforms.py:32-50 `generate_photo_thumbnail`
+ * (`thumb.save(buf, format='JPEG', quality=80)`, processing/scorer.py:1681-1686), byte-exact with Pillow / libjpeg(-turbo) at its
+ * defaults: YCbCr 4:2:0, standard Huffman tables, no restart markers (colour conversion, h2v2 downsampling with edge replication,
+ * jpeg_fdct_islow, round-half-up quantisation, dummy blocks, Huffman coding with 0xFF stuffing and one-bit padding).
+ *   d_rgb     [n][height][width][3] uint8, RGB
+ *   d_tables  3328 bytes as packed by facet_b200/utils/jpeg.py `encoder_tables`: uint16 q8[2][64] (8 x quantisation value, natural
+ *             order, luma / chroma), uint16 code[4][256], uint8 size[4][256] (DC luma, AC luma, DC chroma, AC chroma)
+ *   d_header  the header_bytes bytes SOI .. end of the SOS header that Pillow writes for this size and quality (they do not depend
+ *             on the pixels)
+ *   d_out     [n] slots of out_stride >= fb_jpeg_encode_out_stride(height, width, header_bytes) bytes; d_length [n] uint32 receives
+ *             the length of every stream (header + entropy-coded data + EOI)
+ *   d_workspace  fb_jpeg_encode_workspace_bytes(n, height, width) bytes, 256-byte aligned */
+size_t fb_jpeg_encode_workspace_bytes(int n, int height, int width);
+size_t fb_jpeg_encode_out_stride(int height, int width, int header_bytes);
+int fb_jpeg_encode(const uint8_t* d_rgb, int n, int height, int width, int64_t image_stride, const void* d_tables,
+                   const uint8_t* d_header, int header_bytes, void* d_workspace, size_t workspace_bytes, uint8_t* d_out,
+                   int64_t out_stride, uint32_t* d_length, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Frame orientation — the pixel work of utils/image_loading.py:101-106 for frames already in device
  * memory: ImageOps.exif_transpose (PIL transpose method chosen by EXIF tag 0x0112: 2 FLIP_LEFT_RIGHT,
