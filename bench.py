@@ -585,7 +585,7 @@ def main():
 
         # ---- the same call with the two side products of the reference's loop switched on: leading-lines score per image
         # (batch_processor.py:245) and the 640-px thumbnail JPEG (scorer.py:1681-1686).  Edge maps / thumbnail pixels come from
-        # the device in the same visit of the frame; OpenCV's Hough transform and Pillow's JPEG encoder run on host threads ----
+        # the device in the same visit of the frame (the thumbnail as a finished JPEG stream); OpenCV's Hough transform runs on host threads ----
         if not args.no_e2e_side:
             workers = max(2, min(16, (os.cpu_count() or 2) // max(1, world)))
             bps = BatchProcessor(scorer, batch_size=B, num_workers=workers, leading_lines=True)
@@ -609,7 +609,7 @@ def main():
                 "h2d_bytes_per_step": bps.metrics["h2d_bytes"] * B // len(sitems), "d2h_bytes_per_step": bps.metrics["d2h_bytes"] * B // len(sitems),
                 "note": "gray / 5x5 blur / Canny (csrc/canny.cu, bit-exact with OpenCV) and the thumbnail pixels (4x4 box sums emitted by the "
                         "technical pass, csrc/thumbnail.cu) on the device; the 24 MB edge map and the thumbnail pixels leave on the D2H "
-                        "stream; cv2.HoughLinesP and the JPEG encoder on host threads bound this leg; the pool's pure-noise frames are "
+                        "stream, the thumbnails as JPEG streams encoded on the device (csrc/jpeg_encode.cu); cv2.HoughLinesP on host threads bounds this leg; the pool's pure-noise frames are "
                         "left out of this leg (seconds of HoughLinesP each, in the reference too)"}
 
         # ---- e2e from FILE BYTES: the same call with items that carry JPEG streams (what the reference's loader reads from

@@ -192,7 +192,8 @@ class BatchProcessor:
           side products   with `leading_lines` (constructor) the Canny edge map of every frame (csrc/canny.cu) and with
                           `thumbnails` the 640-px LANCZOS thumbnail pixels of every frame (csrc/thumbnail.cu) are produced in
                           the same visit of the frame on the compute stream, leave on the D2H stream, and `num_workers`
-                          host threads run OpenCV's Hough transform / Pillow's JPEG encoder on them; a result then carries
+                          the thumbnails are JPEG-encoded on the device as well (csrc/jpeg_encode.cu); host threads run OpenCV's
+                          Hough transform on the edge maps and slice the streams; a result then carries
                           `leading_lines_score` (batch_processor.py:245,334) / `thumbnail` (the JPEG bytes of scorer.py:1681-1686)
 
         `self.metrics` gains h2d_bytes / d2h_bytes of the call."""
@@ -252,14 +253,21 @@ class BatchProcessor:
             finally:
                 q.put(host)
 
-        def thumbs_job(q, host, done, m):
-            from ..utils.image_transforms import _encode_jpeg
+        thumb_cap = 1 << 18          # bytes of every stream fetched with the first copy (photographs: 15-60 KB at 640 px)
+
+        def thumbs_job(q, host, done, m, streams, lengths):
+            """host: pinned [chunk, 4 + thumb_cap] uint8 = (length, first thumb_cap bytes) of every stream of the chunk."""
             try:
                 done.synchronize()
-                px = host[:m].numpy().copy()
+                a = host[:m].numpy()
+                lens = a[:, :4].view(np.int32).reshape(-1).copy()
+                out = [a[k, 4:4 + min(int(lens[k]), thumb_cap)].tobytes() for k in range(m)]
             finally:
                 q.put(host)
-            return [_encode_jpeg(t, 80) for t in px]
+            for k in range(m):                       # a stream longer than the first copy (noise-like frames): fetch it whole
+                if lens[k] > thumb_cap:
+                    out[k] = streams[k, :int(lens[k])].cpu().numpy().tobytes()
+            return out
 
         def side_products(frames, metas, thumbs):
             if want_lines:
@@ -268,10 +276,15 @@ class BatchProcessor:
                         edges = ops.canny_edges(ops.gray_plane(frames[k], rgb_order=rgb_order), 50, 150, blur=True)
                         side.setdefault(pos, {})["lines"] = pool.submit(lines_job, *d2h_async(edges, "edges", 2 * self.num_workers + 2), h, w)
             if thumbs is not None:
-                px = thumbs
-                if px.shape[0] < chunk:          # one pinned shape per frame shape: pad short chunks
-                    px = torch.cat([px, px.new_zeros((chunk - px.shape[0],) + tuple(px.shape[1:]))])
-                fut = pool.submit(thumbs_job, *d2h_async(px, "thumbs", 4), len(metas))
+                # the JPEG streams are made on the device too (csrc/jpeg_encode.cu, the bytes Pillow's encoder writes): what
+                # leaves is (length, stream) per frame instead of 820 KB of pixels and a host-side encode
+                streams, lengths = ops.jpeg_encode(thumbs, quality=80, as_device=True)
+                m = len(metas)
+                rec = torch.zeros((chunk, 4 + thumb_cap), dtype=torch.uint8, device=dev)
+                rec[:m, :4] = lengths.view(torch.uint8).reshape(m, 4)
+                w_ = min(thumb_cap, int(streams.shape[1]))
+                rec[:m, 4:4 + w_] = streams[:, :w_]
+                fut = pool.submit(thumbs_job, *d2h_async(rec, "thumbs", 4), m, streams, lengths)
                 for k, (pos, _item, _h, _w) in enumerate(metas):
                     side.setdefault(pos, {})["thumb"] = (fut, k)
 

@@ -6,18 +6,9 @@ the pixels come from the CUDA kernels (csrc/thumbnail.cu, bit-exact with Pillow'
 """
 from __future__ import annotations
 
-from io import BytesIO
-
 import numpy as np
 
 from .. import ops
-
-
-def _encode_jpeg(rgb: np.ndarray, quality: int) -> bytes:
-    from PIL import Image
-    buf = BytesIO()
-    Image.fromarray(rgb).save(buf, format="JPEG", quality=quality)
-    return buf.getvalue()
 
 
 def generate_photo_thumbnails(images, size: int = 640, quality: int = 80, rgb_order: bool = False) -> list[bytes]:
