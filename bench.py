@@ -465,6 +465,12 @@ def main():
                 "technical_kernel": {"bound": "hbm", "achieved": stages["technical_gbs"], "peak": peaks["hbm_gbs"],
                                      "unit": "GB/s", "frac": stages["technical_gbs"] / peaks["hbm_gbs"],
                                      "algorithmic_bytes_per_step": B * TECH_BYTES_PER_IMAGE,
+                                     # SURVEY 8(d) counts the frame read only; in the step the same launch also WRITES the
+                                     # Pillow luma plane the pHash pass consumes (H W bytes / image), so `traffic` is to be
+                                     # held against read + write, not against the read alone
+                                     "algorithmic_bytes_with_outputs_per_step": B * (TECH_BYTES_PER_IMAGE + H * W),
+                                     "achieved_with_outputs": B * (TECH_BYTES_PER_IMAGE + H * W) / (ms_tech * 1e-3) / 1e9,
+                                     "frac_with_outputs": B * (TECH_BYTES_PER_IMAGE + H * W) / (ms_tech * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                      "traffic": (tr["technical"]["dram_bytes_per_frame"] * B) if tr else None,
                                      "traffic_source": tr["technical"]["source"] if tr else None}}
 
