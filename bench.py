@@ -223,13 +223,22 @@ def run_reference(args, rank, world):
     One step = CPU_SAMPLE_FRAMES 24 MP frames, batched through the tower, + the cosine grouping of what was scored so far."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is to use every host thread it can, so the BLAS / OpenMP
+    # pools are sized before NumPy / SciPy / torch are imported (nothing above this line imports them)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import numpy as np
     import torch
     from facet_b200.models.clip_vit import random_state_dict
     from facet_b200.synth import synth_embeddings
     from oracle import cpu_port, grouping
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    try:
+        import cv2
+        cv2.setNumThreads(cores)
+    except ImportError:
+        pass
     sd = random_state_dict(0)
     tags = torch.from_numpy(synth_embeddings(240, seed=7, cluster_fraction=0.0))
     ref, kind, desc = cpu_arm()
