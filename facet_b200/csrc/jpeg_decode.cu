@@ -13,6 +13,7 @@
 // Host parsing of the marker segments and the table layout: facet_b200/utils/jpeg.py.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -639,6 +640,8 @@ struct SyncArrays {
     const uint8_t* clean;
     long long clean_stride;
     int T;
+    int16_t* dc;             // [n][blocks per image] DC differences / values in scan order (compact DC integration), or nullptr
+    long long dc_image_stride;
 };
 
 // round 0: every thread starts at the first bit of its subsequence in the guessed state (block 0, DC next) — true for thread 0.
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(1024) jpeg_sync_prefix_kernel(SyncArrays A, in
 // are stored as differences.  `q` = number of blocks completed before the start state (jpeg_sync_prefix_kernel).
 __device__ bool span_write_coop(const uint8_t* u, long long len_bits, SyncState st, long long limit_bits, bool active, const JpegGeom& g,
                                 const JpegTableSet& T, const uint8_t* zz, uint64_t lay, int nblk, int q, int total_blocks, int16_t* cimg,
-                                int16_t* stage_warp, int lane) {
+                                int16_t* stage_warp, int lane, int16_t* dc_img) {
     CleanReader r;
     r.u = u;
     r.next = 0;
@@ -801,7 +804,10 @@ __device__ bool span_write_coop(const uint8_t* u, long long len_bits, SyncState 
                     }
                     if (k >= 64 && ok) {
                         k = 0;
-                        if (!skip) flush_blk = blk;
+                        if (!skip) {
+                            flush_blk = blk;
+                            if (dc_img) dc_img[q] = stage_row[0];        // compact copy of the DC difference, scan order
+                        }
                         skip = false;
                         b = b + 1 == nblk ? 0 : b + 1;
                         c = (int)(lay >> (4 * b)) & 3;
@@ -861,7 +867,8 @@ __global__ void __launch_bounds__(kSyncWriteThreads) jpeg_sync_write_kernel(Sync
     int nblk;
     const uint64_t lay = mcu_layout(g, nblk);
     const bool ok = span_write_coop(A.clean + (size_t)img * A.clean_stride, len_bits, st, limit, active, g, T, s_zz, lay, nblk, q, total_blocks,
-                                    coef + (size_t)img * g.coef_image_stride, stage_warp, tid & 31);
+                                    coef + (size_t)img * g.coef_image_stride, stage_warp, tid & 31,
+                                    A.dc ? A.dc + (size_t)img * A.dc_image_stride : nullptr);
     if (!ok) atomicOr(status + img, 2);
 }
 
@@ -915,6 +922,74 @@ __global__ void __launch_bounds__(kDcThreads) jpeg_dc_segment_kernel(int16_t* __
     for (int i = 0; i < kDcPerThread; ++i) {
         run += v[i];
         if (ptr[i]) *ptr[i] = (int16_t)run;
+    }
+}
+
+// Compact form of the same integration: the write pass also stores every block's DC difference at dc[img][q], q = index of the
+// block in scan order, so the prefix sums read and write 2 bytes per block contiguously instead of one 32-byte sector of the
+// coefficient area per block (twice), and the inverse DCT takes its DC term from this array.  A thread owns kDcxMcus
+// consecutive MCUs (nblk values each); segments of kDcxSeg MCUs; same three steps.  grid = (segments, n)
+constexpr int kDcxMcus = 8, kDcxSeg = kDcxMcus * kDcThreads;
+
+template <int PHASE>
+__global__ void __launch_bounds__(kDcThreads) jpeg_dcx_segment_kernel(int16_t* __restrict__ dc, long long dc_image_stride, JpegGeom g, int segs,
+                                                                       int* __restrict__ seg_sum) {
+    __shared__ int s_part[3][kDcThreads];
+    const int seg = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    int nblk;
+    const uint64_t lay = mcu_layout(g, nblk);
+    const int total_mcus = g.mcux * g.mcuy;
+    const int m0 = seg * kDcxSeg + tid * kDcxMcus;
+    int16_t* base = dc + (size_t)img * dc_image_stride;
+    int sum[3] = {0, 0, 0};
+    for (int i = 0; i < kDcxMcus; ++i) {
+        if (m0 + i >= total_mcus) break;
+        const int16_t* v = base + (size_t)(m0 + i) * nblk;
+        for (int b = 0; b < nblk; ++b) sum[(int)(lay >> (4 * b)) & 3] += v[b];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s_part[c][tid] = sum[c];
+    __syncthreads();
+    for (int o = 1; o < kDcThreads; o <<= 1) {
+        int x[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = tid >= o ? s_part[c][tid - o] : 0;
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_part[c][tid] += x[c];
+        __syncthreads();
+    }
+    int* ss = seg_sum + (size_t)img * 3 * segs;
+    if (PHASE == 0) {
+        if (tid == kDcThreads - 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ss[c * segs + seg] = s_part[c][tid];
+        }
+        return;
+    }
+    int run[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) run[c] = ss[c * segs + seg] + s_part[c][tid] - sum[c];
+    const bool words = (nblk & 1) == 0 && (dc_image_stride & 1) == 0;      // MCUs start on 4-byte boundaries: 32-bit loads / stores
+    for (int i = 0; i < kDcxMcus; ++i) {
+        if (m0 + i >= total_mcus) break;
+        int16_t* v = base + (size_t)(m0 + i) * nblk;
+        if (words) {
+            for (int b = 0; b < nblk; b += 2) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(v + b);
+                const int c0 = (int)(lay >> (4 * b)) & 3, c1 = (int)(lay >> (4 * b + 4)) & 3;
+                run[c0] += (int)(int16_t)(w & 0xffffu);
+                const uint32_t lo = (uint32_t)run[c0] & 0xffffu;
+                run[c1] += (int)(int16_t)(w >> 16);
+                *reinterpret_cast<uint32_t*>(v + b) = lo | ((uint32_t)run[c1] << 16);
+            }
+        } else {
+            for (int b = 0; b < nblk; ++b) {
+                const int c = (int)(lay >> (4 * b)) & 3;
+                run[c] += v[b];
+                v[b] = (int16_t)run[c];
+            }
+        }
     }
 }
 
@@ -995,7 +1070,7 @@ FB_HD void idct8(int (&d)[8], int shift) {
 }
 
 // One 8x8 block: 64 quantised coefficients (natural order) -> 8 rows of 8 samples at `out` (row pitch `pitch` bytes).
-FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch) {
+FB_HD void idct_block_dc(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch, bool dc_given, int dc) {
     int ws[8][8];
     // dequantise; pass 1 runs down the columns
 #pragma unroll
@@ -1009,6 +1084,7 @@ FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_
             ws[r][2 * j + 1] = (int)(int16_t)(w[j] >> 16) * (int)(qw[j] >> 16);
         }
     }
+    if (dc_given) ws[0][0] = dc * (int)q[0];
 #pragma unroll
     for (int col = 0; col < 8; ++col) {
         int d[8];
@@ -1036,9 +1112,13 @@ FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_
     }
 }
 
+FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch) { idct_block_dc(src, q, out, pitch, false, 0); }
+
+// `dc` (optional): DC values in scan order (compact integration of the streams without restart markers); the block at
+// (brow, bcol) of component c is block c_first + (brow % vs) * hs + bcol % hs of MCU (brow / vs) * mcux + bcol / hs.
 __global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t* __restrict__ coef, const int* __restrict__ table_slot,
                                                         const JpegTableSet* __restrict__ tables, JpegGeom g, int n,
-                                                        uint8_t* __restrict__ planes) {
+                                                        uint8_t* __restrict__ planes, const int16_t* __restrict__ dc, long long dc_image_stride) {
     long long blocks_per_image = 0;
     for (int c = 0; c < g.ncomp; ++c) blocks_per_image += (long long)g.blocks_w[c] * g.blocks_h[c];
     const long long total = blocks_per_image * n;
@@ -1052,9 +1132,19 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t* __restric
         }
         const int bw = g.blocks_w[c];
         const int brow = (int)(b / bw), bcol = (int)(b - (long long)brow * bw);
-        idct_block(coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c] + b * 64, tables[table_slot[img]].q[g.tq[c]],
-                   planes + (size_t)img * g.plane_image_stride + g.plane_comp_off[c] + ((size_t)brow * 8) * ((size_t)bw * 8) + (size_t)bcol * 8,
-                   (size_t)bw * 8);
+        int dcv = 0;
+        if (dc) {
+            int nblk = 0, first = 0;
+            for (int cc = 0; cc < g.ncomp; ++cc) {
+                if (cc == c) first = nblk;
+                nblk += g.hs[cc] * g.vs[cc];
+            }
+            const int my = brow / g.vs[c], by = brow - my * g.vs[c], mx = bcol / g.hs[c], bx = bcol - mx * g.hs[c];
+            dcv = dc[(size_t)img * dc_image_stride + ((size_t)my * g.mcux + mx) * nblk + first + by * g.hs[c] + bx];
+        }
+        idct_block_dc(coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c] + b * 64, tables[table_slot[img]].q[g.tq[c]],
+                      planes + (size_t)img * g.plane_image_stride + g.plane_comp_off[c] + ((size_t)brow * 8) * ((size_t)bw * 8) + (size_t)bcol * 8,
+                      (size_t)bw * 8, dc != nullptr, dcv);
     }
 }
 
@@ -1213,7 +1303,7 @@ size_t jpeg_workspace_bytes(int n, int width, int height, int ncomp, int hs0, in
         const long long T = selfsync_subsequences(max_scan_bytes);
         total += al(selfsync_clean_stride(max_scan_bytes) * n) + al(8ll * n) + 3 * al((long long)sizeof(SyncState) * T * n) +
                  2 * al(4 * T * n) + al(4ll * (kSyncRounds + 1) * n) + al(4ll * ((n + 63) & ~63)) +
-                 al(4ll * 3 * n * ((total_mcus * hmax * vmax + 2047) / 2048 + 1));
+                 al(4ll * 3 * n * ((total_mcus * hmax * vmax + 2047) / 2048 + 1)) + al(2ll * blocks * n);
     }
     return (size_t)total;
 }
@@ -1274,6 +1364,8 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
     w += al((long long)chunks * 4 * n);
     const bool selfsync = g.restart_interval == 0 && total_mcus > kSerialMcus;
     const JpegTableSet* tables = reinterpret_cast<const JpegTableSet*>(d_tables);
+    const int16_t* dc_values = nullptr;          // set when the DC terms come from the compact array instead of coef[0]
+    long long dc_stride = 0;
 
     FB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int) * n, stream));
     if (selfsync) {
@@ -1296,6 +1388,11 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         A.changed = reinterpret_cast<int*>(w);
         w += al(4ll * (kSyncRounds + 1) * n);
         A.settled = reinterpret_cast<int*>(w);
+        w += al(4ll * ((n + 63) & ~63));
+        w += al(4ll * 3 * n * ((total_mcus * hmax * vmax + 2047) / 2048 + 1));          // segment sums of the DC integration
+        static const bool dc_strided = getenv("FB_JPEG_DC_STRIDED") != nullptr;          // A/B switch: integrate inside the coefficient area
+        A.dc = dc_strided ? nullptr : reinterpret_cast<int16_t*>(w);
+        A.dc_image_stride = blocks;
         A.clean = clean;
         A.clean_len = clean_len;
         const int total_blocks = (int)(blocks);
@@ -1322,7 +1419,16 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
             jpeg_sync_write_kernel<<<dim3((A.T + kSyncWriteThreads - 1) / kSyncWriteThreads, n), kSyncWriteThreads, kSyncWriteSmem, stream>>>(
                 A, d_table_slot, tables, g, total_blocks, coef, d_status);
         }
-        {
+        if (A.dc) {
+            // compact DC integration: prefix sums over the 2-byte-per-block copy the write pass made; the inverse DCT reads it
+            const int segs = (int)((total_mcus + kDcxSeg - 1) / kDcxSeg);
+            int* seg_sum = reinterpret_cast<int*>(A.settled + ((n + 63) & ~63));
+            jpeg_dcx_segment_kernel<0><<<dim3(segs, n), kDcThreads, 0, stream>>>(A.dc, A.dc_image_stride, g, segs, seg_sum);
+            jpeg_dc_scan_kernel<<<n * 3, 32, 0, stream>>>(seg_sum, segs);
+            jpeg_dcx_segment_kernel<1><<<dim3(segs, n), kDcThreads, 0, stream>>>(A.dc, A.dc_image_stride, g, segs, seg_sum);
+            dc_values = A.dc;
+            dc_stride = A.dc_image_stride;
+        } else {
             const int segs = (int)((g.mcux * (long long)g.mcuy * g.hs[0] * g.vs[0] + kDcSeg - 1) / kDcSeg);
             int* seg_sum = reinterpret_cast<int*>(A.settled + ((n + 63) & ~63));
             jpeg_dc_segment_kernel<0><<<dim3(segs, n, ncomp), kDcThreads, 0, stream>>>(coef, g, segs, seg_sum);
@@ -1350,7 +1456,8 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         const long long total = blocks * n;
         long long gb = (total + 127) / 128;
         if (gb > (long long)sm_count() * 32) gb = (long long)sm_count() * 32;
-        jpeg_idct_kernel<<<(unsigned)gb, 128, 0, stream>>>(coef, d_table_slot, reinterpret_cast<const JpegTableSet*>(d_tables), g, n, planes);
+        jpeg_idct_kernel<<<(unsigned)gb, 128, 0, stream>>>(coef, d_table_slot, reinterpret_cast<const JpegTableSet*>(d_tables), g, n, planes, dc_values,
+                                                           dc_stride);
     }
     {
         const int groups = (width + 7) / 8;
