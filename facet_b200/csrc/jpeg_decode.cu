@@ -1030,7 +1030,7 @@ constexpr int CONST_BITS = 13, PASS1_BITS = 2;
 
 // 1-D pass on eight values (libjpeg works in `JLONG`; 32 bits are enough for 8-bit data: |input| <= 2^15 * 2^2 after
 // pass 1, constants < 2^15, four-term sums), results descaled by `shift` with rounding.
-FB_HD void idct8(int (&d)[8], int shift) {
+FB_HD void idct8(int (&d)[8], int shift, int extra = 0) {
     int z2 = d[2], z3 = d[6];
     int z1 = (z2 + z3) * FIX_0_541196100;
     const int tmp2 = z1 + z3 * (-FIX_1_847759065);
@@ -1058,7 +1058,7 @@ FB_HD void idct8(int (&d)[8], int shift) {
     t1 += z2 + z4;
     t2 += z2 + z3;
     t3 += z1 + z4;
-    const int r = 1 << (shift - 1);
+    const int r = (1 << (shift - 1)) + extra;          // `extra` = a multiple of 1 << shift: added to every output after the shift
     d[0] = (tmp10 + t3 + r) >> shift;
     d[7] = (tmp10 - t3 + r) >> shift;
     d[1] = (tmp11 + t2 + r) >> shift;
@@ -1069,8 +1069,25 @@ FB_HD void idct8(int (&d)[8], int shift) {
     d[4] = (tmp13 - t0 + r) >> shift;
 }
 
+// clamp(v, 0, 255) of four values packed into one word, v0 in the low byte: two I2IP (cvt.pack.sat) on the device
+FB_HD uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 720
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+#else
+    const int v[4] = {v0, v1, v2, v3};
+    uint32_t d = 0;
+    for (int i = 0; i < 4; ++i) d |= (uint32_t)(v[i] < 0 ? 0 : (v[i] > 255 ? 255 : v[i])) << (8 * i);
+    return d;
+#endif
+}
+
 // One 8x8 block: 64 quantised coefficients (natural order) -> 8 rows of 8 samples at `out` (row pitch `pitch` bytes).
-FB_HD void idct_block_dc(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch, bool dc_given, int dc) {
+// `emit(r, s)` receives row r of the block as eight samples BEFORE the final clamp to [0, 255] (values in [-384, 639]).
+template <class F>
+FB_HD void idct_block_rows(const int16_t* src, const uint16_t* q, bool dc_given, int dc, F&& emit) {
     int ws[8][8];
     // dequantise; pass 1 runs down the columns
 #pragma unroll
@@ -1099,19 +1116,20 @@ FB_HD void idct_block_dc(const int16_t* src, const uint16_t* q, uint8_t* out, si
         int d[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = ws[r][j];
-        idct8(d, CONST_BITS + PASS1_BITS + 3);
-        uint32_t pk[2] = {0u, 0u};
+        // libjpeg's range-limit table is indexed with the low 10 bits of the result v: wrap v to [-512, 511], then clamp(v + 128).
+        // wrap(v) + 128 = ((v + 512) & 1023) - 384, and the + 512 rides the rounding constant of the pass
+        idct8(d, CONST_BITS + PASS1_BITS + 3, 512 << (CONST_BITS + PASS1_BITS + 3));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            // libjpeg's range-limit table is indexed with the low 10 bits: wrap to [-512, 511], then clamp(v + 128)
-            const int v10 = ((d[j] & 1023) ^ 512) - 512;
-            const int s = v10 + 128 < 0 ? 0 : (v10 + 128 > 255 ? 255 : v10 + 128);
-            pk[j >> 2] |= (uint32_t)s << (8 * (j & 3));
-        }
-        *reinterpret_cast<uint2*>(out + (size_t)r * pitch) = make_uint2(pk[0], pk[1]);
+        for (int j = 0; j < 8; ++j) d[j] = (d[j] & 1023) - 384;
+        emit(r, d);
     }
 }
 
+FB_HD void idct_block_dc(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch, bool dc_given, int dc) {
+    idct_block_rows(src, q, dc_given, dc, [&](int r, const int (&d)[8]) {
+        *reinterpret_cast<uint2*>(out + (size_t)r * pitch) = make_uint2(pack4_sat_u8(d[0], d[1], d[2], d[3]), pack4_sat_u8(d[4], d[5], d[6], d[7]));
+    });
+}
 FB_HD void idct_block(const int16_t* src, const uint16_t* q, uint8_t* out, size_t pitch) { idct_block_dc(src, q, out, pitch, false, 0); }
 
 // `dc` (optional): DC values in scan order (compact integration of the streams without restart markers); the block at
@@ -1172,6 +1190,44 @@ FB_HD void chroma_cols(const uint8_t* row, int c0, int cw, int (&v)[6]) {
             const int c = c0 - 1 + j;
             v[j] = row[c < 0 ? 0 : (c > cw - 1 ? cw - 1 : c)];
         }
+    }
+}
+
+// YCbCr -> RGB (jdcolor.c tables as integer arithmetic) of eight consecutive pixels and their 24 output bytes at o.
+template <bool BGR>
+FB_HD void color_pack8(const int (&yy)[8], const int (&cbv)[8], const int (&crv)[8], bool three, uint32_t (&pk)[6]) {
+    // y + ((k * (c - 128) + ONE_HALF) >> 16) = (y * 65536 + k * c + ONE_HALF - 128 k) >> 16: the - 128 and the rounding sit in one
+    // constant per channel; the clamp to [0, 255] is the saturation of the packing instruction
+    constexpr int kR0 = ONE_HALF - 128 * kCrR, kG0 = ONE_HALF + 128 * kCbG + 128 * kCrG, kB0 = ONE_HALF - 128 * kCbB;
+    int v[24];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int r = yy[j], gg = yy[j], b = yy[j];
+        if (three) {
+            r = (yy[j] * 65536 + kR0 + kCrR * crv[j]) >> SCALEBITS;
+            gg = (yy[j] * 65536 + kG0 - kCbG * cbv[j] - kCrG * crv[j]) >> SCALEBITS;
+            b = (yy[j] * 65536 + kB0 + kCbB * cbv[j]) >> SCALEBITS;
+        }
+        v[3 * j] = BGR ? b : r;
+        v[3 * j + 1] = gg;
+        v[3 * j + 2] = BGR ? r : b;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pk[i] = pack4_sat_u8(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+FB_HD void color_store8(const int (&yy)[8], const int (&cbv)[8], const int (&crv)[8], bool three, int bgr, int W, int x0, uint8_t* o) {
+    uint32_t pk[6];
+    if (bgr) color_pack8<true>(yy, cbv, crv, three, pk);
+    else color_pack8<false>(yy, cbv, crv, three, pk);
+    if (x0 + 8 <= W && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+        uint2* o64 = reinterpret_cast<uint2*>(o);
+        o64[0] = make_uint2(pk[0], pk[1]);
+        o64[1] = make_uint2(pk[2], pk[3]);
+        o64[2] = make_uint2(pk[4], pk[5]);
+    } else {
+        const int nb = 3 * (W - x0 < 8 ? W - x0 : 8);
+        for (int k = 0; k < nb; ++k) o[k] = (uint8_t)(pk[k >> 2] >> (8 * (k & 3)));
     }
 }
 
@@ -1242,31 +1298,49 @@ FB_HD void color_group(const uint8_t* P, const JpegGeom& g, int y, int x0, int b
             }
         }
     }
-    uint32_t pk[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+    color_store8(yy, cbv, crv, g.ncomp == 3, bgr, W, x0, o);
+}
+
+// h2v2 frames, two rows per call: rows y (even) and y + 1 share their near chroma row y / 2 and differ only in the far row
+// (y / 2 - 1 above, y / 2 + 1 below, clamped), so a pair needs three chroma rows per plane instead of four and one set of
+// addresses.  Same arithmetic as color_group<2>.
+FB_HD void color_pair420(const uint8_t* P, const JpegGeom& g, int y, int x0, int bgr, uint8_t* o) {
+    const int W = g.width, H = g.height;
+    const int yp = g.blocks_w[0] * 8, cp = g.blocks_w[1] * 8;
+    const int cw = (W + 1) / 2, ch = (H + 1) / 2;
+    const uint8_t* CB = P + g.plane_comp_off[1];
+    const uint8_t* CR = P + g.plane_comp_off[2];
+    const int c0 = x0 >> 1, cy = y >> 1;
+    const int up = cy - 1 < 0 ? 0 : cy - 1, dn = cy + 1 > ch - 1 ? ch - 1 : cy + 1;
+    int nb[6], nr[6], fb[6], fr[6];
+    chroma_cols(CB + (size_t)cy * cp, c0, cw, nb);
+    chroma_cols(CR + (size_t)cy * cp, c0, cw, nr);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        int r = yy[j], gg = yy[j], b = yy[j];
-        if (g.ncomp == 3) {
-            const int cb = cbv[j] - 128, cr = crv[j] - 128;
-            r = clamp8(yy[j] + ((kCrR * cr + ONE_HALF) >> SCALEBITS));
-            gg = clamp8(yy[j] + ((-kCbG * cb + ONE_HALF - kCrG * cr) >> SCALEBITS));
-            b = clamp8(yy[j] + ((kCbB * cb + ONE_HALF) >> SCALEBITS));
-        }
-        const int c3[3] = {bgr ? b : r, gg, bgr ? r : b};
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int byte = 3 * j + e;
-            pk[byte >> 2] |= (uint32_t)c3[e] << (8 * (byte & 3));
-        }
+    for (int j = 0; j < 6; ++j) {
+        nb[j] *= 3;
+        nr[j] *= 3;
     }
-    if (x0 + 8 <= W && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
-        uint2* o64 = reinterpret_cast<uint2*>(o);
-        o64[0] = make_uint2(pk[0], pk[1]);
-        o64[1] = make_uint2(pk[2], pk[3]);
-        o64[2] = make_uint2(pk[4], pk[5]);
-    } else {
-        const int nb = 3 * (W - x0 < 8 ? W - x0 : 8);
-        for (int k = 0; k < nb; ++k) o[k] = (uint8_t)(pk[k >> 2] >> (8 * (k & 3)));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && y + 1 >= H) break;
+        chroma_cols(CB + (size_t)(half ? dn : up) * cp, c0, cw, fb);
+        chroma_cols(CR + (size_t)(half ? dn : up) * cp, c0, cw, fr);
+        int yy[8], cbv[8], crv[8];
+        const uint2 w = *reinterpret_cast<const uint2*>(P + g.plane_comp_off[0] + (size_t)(y + half) * yp + x0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            yy[j] = (w.x >> (8 * j)) & 255u;
+            yy[4 + j] = (w.y >> (8 * j)) & 255u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 1 + (j >> 1);
+            const int nbk = (j & 1) ? k + 1 : k - 1;
+            const int bias = (j & 1) ? 7 : 8;
+            cbv[j] = (3 * (nb[k] + fb[k]) + nb[nbk] + fb[nbk] + bias) >> 4;
+            crv[j] = (3 * (nr[k] + fr[k]) + nr[nbk] + fr[nbk] + bias) >> 4;
+        }
+        color_store8(yy, cbv, crv, true, bgr, W, x0, o + (size_t)half * W * 3);
     }
 }
 
@@ -1280,6 +1354,18 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restri
     const int img = (int)(blockIdx.x / (unsigned)H), y = (int)(blockIdx.x - (unsigned)img * (unsigned)H);
     color_group<MODE>(planes + (size_t)img * g.plane_image_stride, g, y, gx * 8, bgr,
                       out + (size_t)img * out_stride + ((size_t)y * W + gx * 8) * 3);
+}
+
+
+// h2v2: one thread = 8 consecutive pixels of a PAIR of rows; blockIdx.x = image * ceil(H / 2) + pair
+__global__ void __launch_bounds__(256) jpeg_color420_pair_kernel(const uint8_t* __restrict__ planes, JpegGeom g, int n, int bgr,
+                                                                 uint8_t* __restrict__ out, long long out_stride) {
+    const int W = g.width, H = g.height;
+    const unsigned pairs = (unsigned)(H + 1) >> 1;
+    const int gx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (gx * 8 >= W) return;
+    const int img = (int)(blockIdx.x / pairs), y = 2 * (int)(blockIdx.x - (unsigned)img * pairs);
+    color_pair420(planes + (size_t)img * g.plane_image_stride, g, y, gx * 8, bgr, out + (size_t)img * out_stride + ((size_t)y * W + gx * 8) * 3);
 }
 
 }  // namespace
@@ -1466,7 +1552,11 @@ int launch_jpeg_decode(const uint8_t* d_bytes, const long long* d_scan_off, cons
         const int mode = ncomp == 1 ? 0 : (hmax == 1 ? 0 : (vmax == 1 ? 1 : 2));
         if (mode == 0) jpeg_color_kernel<0><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
         else if (mode == 1) jpeg_color_kernel<1><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
-        else jpeg_color_kernel<2><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        else {
+            static const bool single_rows = getenv("FB_JPEG_COLOR_SINGLE_ROWS") != nullptr;       // A/B switch
+            if (single_rows) jpeg_color_kernel<2><<<grid, threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+            else jpeg_color420_pair_kernel<<<dim3((unsigned)((long long)n * ((height + 1) / 2)), grid.y), threads, 0, stream>>>(planes, g, n, bgr, d_out, out_stride);
+        }
     }
     FB_CUDA_OK(cudaGetLastError());
     return 0;

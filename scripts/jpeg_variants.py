@@ -1,7 +1,8 @@
-"""Decode time of 32 x 24 MP streams WITHOUT restart markers for library variants (CUDA events, best of 3)."""
+"""Decode time of 32 x 24 MP streams for library variants (CUDA events, best of 3): WITHOUT restart markers, or with a restart
+interval of JV_RI MCUs when that environment variable is set."""
 import io, os, subprocess, sys
 CHILD = r'''
-import io, sys
+import io, os, sys
 import numpy as np, torch
 from PIL import Image
 sys.path.insert(0, ".")
@@ -12,7 +13,8 @@ H, W, n = 4000, 6000, 32
 datas = []
 for i in range(2):
     buf = io.BytesIO()
-    Image.fromarray(synth_image_bgr(2000 + i, H, W)[:, :, ::-1].copy()).save(buf, "JPEG", quality=90)
+    kw = {"restart_marker_blocks": int(os.environ["JV_RI"])} if os.environ.get("JV_RI") else {}
+    Image.fromarray(synth_image_bgr(2000 + i, H, W)[:, :, ::-1].copy()).save(buf, "JPEG", quality=90, **kw)
     datas.append(np.frombuffer(buf.getvalue(), np.uint8).copy())
 streams = [datas[i % 2] for i in range(n)]
 infos = [fj.parse(s) for s in streams]
