@@ -153,8 +153,37 @@ struct JpegGeom {
 // ---- restart scan ---------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256, kScanWarpBytes = 2048, kScanChunk = (kScanThreads / 32) * kScanWarpBytes;      // 16 KB per CTA
 
-// RSTn markers (0xFF 0xD0..0xD7) of one 16 KB chunk of one stream.  A warp walks its 2 KB in 32-byte steps (coalesced byte
-// loads); ballots keep the markers in stream order.  WRITE = false: counts[img][chunk] = number of markers; WRITE = true
+// 0x80 in every byte of x that is zero (exact, no carries between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
+
+// RSTn markers among the stream positions p0 .. p0+7 (a marker at p = bytes 0xFF, 0xD0..0xD7 at p, p + 1, counted when p + 1 < len):
+// bit 8 j + 7 of h[j / 4 ...] — returned as two words of 0x80 flags, byte i of (lo, hi) = position p0 + i.  Nine bytes come from the
+// three aligned words around s + p0 (streams carry 15 bytes of slack behind their end); SIMD-in-word compares, no branches.
+__device__ __forceinline__ void rst_flags8(const uint8_t* s, long long p0, long long len, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0u;
+    if (p0 + 1 >= len) return;
+    const uintptr_t q = reinterpret_cast<uintptr_t>(s + p0);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(q & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(q & 3) * 8;
+    const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2);
+    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);       // bytes 0..3, 4..7
+    const uint32_t b8 = (w2 >> sh) & 0xFFu;                                                  // byte 8
+    const uint32_t y0 = __funnelshift_r(b0, b1, 8), y1 = (b1 >> 8) | (b8 << 24);            // bytes 1..4, 5..8
+    lo = zero_bytes(~b0) & zero_bytes((y0 & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+    hi = zero_bytes(~b1) & zero_bytes((y1 & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+    const long long valid = len - 1 - p0;                    // positions p0 + i with i < valid count
+    if (valid < 8) {
+        const int v = (int)valid;
+        lo &= v >= 4 ? 0xFFFFFFFFu : ((1u << (8 * v)) - 1u);
+        hi &= v <= 4 ? 0u : ((1u << (8 * (v - 4))) - 1u);
+    }
+}
+
+// RSTn markers (0xFF 0xD0..0xD7) of one 16 KB chunk of one stream.  A warp walks its 2 KB in 256-byte steps, 8 positions per
+// lane (rst_flags8); lane order = stream order.  WRITE = false: counts[img][chunk] = number of markers; WRITE = true
 // (after the prefix kernel turned counts into exclusive offsets): starts[img][1 + k] = byte after the k-th marker.
 template <bool WRITE>
 __global__ void __launch_bounds__(kScanThreads) jpeg_restart_scan_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ scan_off,
@@ -166,11 +195,12 @@ __global__ void __launch_bounds__(kScanThreads) jpeg_restart_scan_kernel(const u
     const long long len = scan_len[img];
     const long long w0 = (long long)chunk * kScanChunk + (long long)warp * kScanWarpBytes;
     int cnt = 0;
-    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
-        const long long p = w0 + it * 32 + lane;
-        const bool hit = p + 1 < len && s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0;
-        cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    for (int it = 0; it < kScanWarpBytes / 256; ++it) {
+        uint32_t lo, hi;
+        rst_flags8(s, w0 + it * 256 + lane * 8, len, lo, hi);
+        cnt += __popc(lo) + __popc(hi);
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_warp[warp] = cnt;
     __syncthreads();
     if (!WRITE) {
@@ -185,15 +215,24 @@ __global__ void __launch_bounds__(kScanThreads) jpeg_restart_scan_kernel(const u
     for (int w = 0; w < warp; ++w) base += s_warp[w];
     if (cnt == 0) return;
     uint32_t* out = starts + (size_t)img * n_intervals + 1;
-    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
-        const long long p = w0 + it * 32 + lane;
-        const bool hit = p + 1 < len && s[p] == 0xFF && (s[p + 1] & 0xF8) == 0xD0;
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const int k = base + __popc(m & ((1u << lane) - 1u));
-            if (k < n_intervals - 1) out[k] = (uint32_t)(p + 2);
+    for (int it = 0; it < kScanWarpBytes / 256; ++it) {
+        const long long p0 = w0 + it * 256 + lane * 8;
+        uint32_t lo, hi;
+        rst_flags8(s, p0, len, lo, hi);
+        const int c = __popc(lo) + __popc(hi);
+        if (!__any_sync(0xffffffffu, c != 0)) continue;
+        int incl = c;                                        // inclusive prefix of the lanes' counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
         }
-        base += __popc(m);
+        int k = base + incl - c;
+        for (uint32_t m = lo; m; m &= m - 1, ++k)
+            if (k < n_intervals - 1) out[k] = (uint32_t)(p0 + (__ffs(m) >> 3) + 1);          // flag bit 8 i + 7 -> position p0 + i, + 2
+        for (uint32_t m = hi; m; m &= m - 1, ++k)
+            if (k < n_intervals - 1) out[k] = (uint32_t)(p0 + 4 + (__ffs(m) >> 3) + 1);
+        base += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
