@@ -612,12 +612,29 @@ __global__ void __launch_bounds__(kScanThreads) jpeg_unstuff_kernel(const uint8_
     const uint8_t* s = bytes + scan_off[img];
     const long long len = scan_len[img];
     const long long w0 = (long long)chunk * kScanChunk + (long long)warp * kScanWarpBytes;
+    // the count (both passes need it per warp): 8 positions per lane from three aligned words, SIMD-in-word compares as in rst_flags8
     int cnt = 0;
-    for (int it = 0; it < kScanWarpBytes / 32; ++it) {
-        const long long p = w0 + it * 32 + lane;
-        const bool stuffed = p < len && p > 0 && s[p] == 0x00 && s[p - 1] == 0xFF;
-        cnt += __popc(__ballot_sync(0xffffffffu, stuffed));
+    for (int it = 0; it < kScanWarpBytes / 256; ++it) {
+        const long long p0 = w0 + it * 256 + lane * 8;
+        if (p0 >= len) continue;
+        const uintptr_t q = reinterpret_cast<uintptr_t>(s + p0) - 1;                      // byte p0 - 1 (p0 = 0: the last header byte, masked below)
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(q & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(q & 3) * 8;
+        const uint32_t x0 = __ldg(a), x1 = __ldg(a + 1), x2 = __ldg(a + 2);
+        const uint32_t b0 = __funnelshift_r(x0, x1, sh), b1 = __funnelshift_r(x1, x2, sh);  // bytes p0-1 .. p0+2, p0+3 .. p0+6
+        const uint32_t b8 = (x2 >> sh) & 0xFFu;                                              // byte p0+7
+        const uint32_t y0 = __funnelshift_r(b0, b1, 8), y1 = (b1 >> 8) | (b8 << 24);        // bytes p0 .. p0+3, p0+4 .. p0+7
+        uint32_t lo = zero_bytes(~b0) & zero_bytes(y0), hi = zero_bytes(~b1) & zero_bytes(y1);   // flag byte i: position p0 + i is a stuffed zero
+        if (p0 == 0) lo &= ~0xFFu;
+        const long long valid = len - p0;
+        if (valid < 8) {
+            const int v = (int)valid;
+            lo &= v >= 4 ? 0xFFFFFFFFu : ((1u << (8 * v)) - 1u);
+            hi &= v <= 4 ? 0u : ((1u << (8 * (v - 4))) - 1u);
+        }
+        cnt += __popc(lo) + __popc(hi);
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_warp[warp] = cnt;
     __syncthreads();
     if (!WRITE) {
