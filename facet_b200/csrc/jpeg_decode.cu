@@ -451,8 +451,11 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const uint8_
 //      thread started from the true state (thread 0 always does; the truth advances at least one subsequence per round, and in
 //      practice everywhere within two or three rounds because of the self-synchronisation);
 //   4. a prefix sum over the blocks completed per subsequence gives every thread its first block index; a last pass decodes once
-//      more and stores coefficients, the DC ones as DIFFERENCES (jpeg_sync_write_kernel);
-//   5. a prefix sum per component turns the DC differences into DC values (jpeg_dc_prefix_kernel).
+//      more and stores coefficients, the DC ones as DIFFERENCES — also into a compact array, 2 bytes per block in scan order
+//      (jpeg_sync_write_kernel);
+//   5. a prefix sum per component over the compact array turns the differences into DC values (jpeg_dcx_segment_kernel), which
+//      the inverse DCT reads instead of coefficient 0 (FB_JPEG_DC_STRIDED: the same inside the coefficient area,
+//      jpeg_dc_segment_kernel).
 #ifndef FB_SUBSEQ_BYTES
 #define FB_SUBSEQ_BYTES 512
 #endif
