@@ -525,6 +525,17 @@ FB_HD int16_t* scan_block_ptr(int q, const JpegGeom& g, uint64_t lay, int nblk, 
     return cimg + g.coef_comp_off[c] + ((size_t)row * g.blocks_w[c] + col) * 64;
 }
 
+// The inverse: index in scan order of the block at (brow, bcol) of component c's block grid.
+FB_HD long long scan_index_of_block(const JpegGeom& g, int c, int brow, int bcol) {
+    int nblk = 0, first = 0;
+    for (int cc = 0; cc < g.ncomp; ++cc) {
+        if (cc == c) first = nblk;
+        nblk += g.hs[cc] * g.vs[cc];
+    }
+    const int my = brow / g.vs[c], by = brow - my * g.vs[c], mx = bcol / g.hs[c], bx = bcol - mx * g.hs[c];
+    return ((long long)my * g.mcux + mx) * nblk + first + by * g.hs[c] + bx;
+}
+
 // Decode from state `st` up to the first symbol boundary at or after `limit_bits` (or the end of the data).
 // WRITE = false: only the state evolves (garbage from a wrong start state is tolerated: an invalid code skips one bit, an
 // overlong run ends the block).  WRITE = true: the start state is the true one; non-zero coefficients are stored into the
@@ -1209,16 +1220,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(const int16_t* __restric
         }
         const int bw = g.blocks_w[c];
         const int brow = (int)(b / bw), bcol = (int)(b - (long long)brow * bw);
-        int dcv = 0;
-        if (dc) {
-            int nblk = 0, first = 0;
-            for (int cc = 0; cc < g.ncomp; ++cc) {
-                if (cc == c) first = nblk;
-                nblk += g.hs[cc] * g.vs[cc];
-            }
-            const int my = brow / g.vs[c], by = brow - my * g.vs[c], mx = bcol / g.hs[c], bx = bcol - mx * g.hs[c];
-            dcv = dc[(size_t)img * dc_image_stride + ((size_t)my * g.mcux + mx) * nblk + first + by * g.hs[c] + bx];
-        }
+        const int dcv = dc ? dc[(size_t)img * dc_image_stride + scan_index_of_block(g, c, brow, bcol)] : 0;
         idct_block_dc(coef + (size_t)img * g.coef_image_stride + g.coef_comp_off[c] + b * 64, tables[table_slot[img]].q[g.tq[c]],
                       planes + (size_t)img * g.plane_image_stride + g.plane_comp_off[c] + ((size_t)brow * 8) * ((size_t)bw * 8) + (size_t)bcol * 8,
                       (size_t)bw * 8, dc != nullptr, dcv);

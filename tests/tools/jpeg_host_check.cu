@@ -63,6 +63,21 @@ int main(int argc, char** argv) {
     int16_t* coef = (int16_t*)aligned_alloc(16, (size_t)blocks * 128 + 16);
     memset(coef, 0, (size_t)blocks * 128 + 16);
     uint8_t* planes = (uint8_t*)aligned_alloc(256, ((size_t)blocks * 64 + 511) & ~(size_t)255);
+    {
+        // scan_index_of_block (the inverse DCT's look-up into the compact DC array) must invert scan_block_ptr
+        int nblk_;
+        const uint64_t lay_ = mcu_layout(g, nblk_);
+        for (long long q = 0; q < blocks; ++q) {
+            const int16_t* ptr = scan_block_ptr((int)q, g, lay_, nblk_, coef);
+            int c = g.ncomp - 1;
+            while (c > 0 && ptr < coef + g.coef_comp_off[c]) --c;
+            const long long b = (ptr - (coef + g.coef_comp_off[c])) / 64;
+            if (scan_index_of_block(g, c, (int)(b / g.blocks_w[c]), (int)(b % g.blocks_w[c])) != q) {
+                fprintf(stderr, "scan_index_of_block does not invert scan_block_ptr at block %lld\n", q);
+                return 7;
+            }
+        }
+    }
     if (hdr[21]) {
         // self-synchronising path (streams without restart markers), the kernels' algorithm executed sequentially
         std::vector<uint8_t> clean;
