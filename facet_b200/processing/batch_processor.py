@@ -464,7 +464,8 @@ class BatchProcessor:
                 if info is not None:
                     # slots of a power-of-two size >= the stream (streams of one camera setting vary by a few 10 %)
                     slot_bytes = max(1 << 20, 1 << int(nbytes * 5 // 4).bit_length())
-                    bufs = self._chunk_buffers(torch, dev, ("jpeg", slot_bytes, chunk), (chunk * slot_bytes,))
+                    # + 256: the device bit reader / marker scan read up to 15 bytes past the end of a stream
+                    bufs = self._chunk_buffers(torch, dev, ("jpeg", slot_bytes, chunk), (chunk * slot_bytes + 256,))
                     cur.update(infos=[], slot_bytes=slot_bytes)
                 else:
                     bufs = self._chunk_buffers(torch, dev, ("raw", h, w, chunk), (chunk, h, w, 3))
